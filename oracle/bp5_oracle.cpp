@@ -1,0 +1,726 @@
+// ============================================================================
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  Not product code.
+//
+// CPU restatement (C++17 + OpenMP) of the BP5 / step-64 hot path of
+// peterrum/deal-and-ceed-on-gpu.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load this library.
+// The product (deal-and-ceed-on-gpu_b200/csrc) never links, loads or calls it.
+//
+// PARITY PIN: the reference tree holds NO golden vectors, known-answer tests
+// or fixtures for this path, and its arithmetic lives in
+// an un-vendored dependency: deal.II, fork peterrum/dealii, branch
+// dealii-on-gpu, version string 9.2.0-pre, no commit pinned
+// (scripts/daint-gcc/make_dealii.sh:91, make_step-64.sh:60).  deal.II cannot
+// be built here (no MPI/p4est/Boost/LAPACK, no network).  => "parity unpinned"
+// BY THE REFERENCE'S OWN TESTS.  The external anchors this file is checked
+// against (tests/test_oracle_known_answers.py) are
+//   (1) the published output of the upstream deal.II step-64 tutorial, which
+//       step-64/step-64.cu is a modified copy of (343 DoFs -> 27 its,
+//       |u|_L2 = 0.0205439; 2197 -> 60, 0.0205269; 15625 -> 114, 0.0205261),
+//   (2) an independent numpy/scipy dense restatement (oracle/bp5_numpy.py),
+//   (3) structural identities (Kronecker form on Cartesian cells, symmetry,
+//       A*1 = 0, stored vs recomputed geometry).
+//
+// What follows which reference line:
+//   basis           FE_Q<dim>(fe_degree): tensor Lagrange on Gauss-Lobatto
+//                   nodes                          bp5/step-64.cu:312,334
+//   quadrature      QGauss<1>(p+1), or QGaussLobatto<1>(p+1) under COLLOCATION
+//                                                  bp5/step-64.cu:243-247
+//   geometry        MappingQGeneric(p)             bp5/step-64.cu:234
+//   metric          JacobianFunctor::operator()    bp5/step-64.cu:84-114
+//                   plane order xx,yy,zz,xy,xz,yz  bp5/step-64.cu:107-113
+//   cell kernel     LocalPoissonOperator::operator() bp5/step-64.cu:147-194
+//   local ordering  x fastest                      bp5/fe_evaluation_gl.h:139-142
+//   gather/scatter  read_dof_values / distribute_local_to_global
+//                                                  bp5/fe_evaluation_gl.h:133-181
+//   vmult           zero, cell loop, copy constrained  bp5/step-64.cu:263-276
+//   constraints     zero Dirichlet on the whole boundary bp5/step-64.cu:351-358
+//   rhs             assemble_rhs                   bp5/step-64.cu:372-418
+//   merged CG       SolverCGFullMerge::solve       bp5/solver.h:343-542
+//                   scalars                        bp5/solver.h:502-505,533
+//   stopping        IterationNumberControl / SolverControl
+//                                                  bp5/step-64.cu:443-445,
+//                                                  step-64/step-64.cu:513-514
+//   Helmholtz       VaryingCoefficientFunctor, HelmholtzOperatorQuad,
+//                   LocalHelmholtzOperator         step-64/step-64.cu:100-118,
+//                                                  154-160,201-219
+//   L2 norm         integrate_difference with QGauss(p+2)
+//                                                  bp5/step-64.cu:604-615
+// ============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// ---------------------------------------------------------------- 1D tables
+// Legendre P_n(x) and P_n'(x) by the three-term recurrence.
+void legendre(int n, double x, double &P, double &dP) {
+  double p0 = 1.0, p1 = x;
+  if (n == 0) { P = 1.0; dP = 0.0; return; }
+  for (int k = 2; k <= n; ++k) {
+    const double pk = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
+    p0 = p1; p1 = pk;
+  }
+  P = p1;
+  dP = n * (x * p1 - p0) / (x * x - 1.0);
+}
+
+// Gauss-Legendre on [0,1] (QGauss<1>(n)).
+void gauss01(int n, double *x, double *w) {
+  for (int i = 0; i < n; ++i) {
+    double z = -std::cos(M_PI * (i + 0.75) / (n + 0.5));
+    for (int it = 0; it < 100; ++it) {
+      double P, dP; legendre(n, z, P, dP);
+      const double dz = P / dP; z -= dz;
+      if (std::fabs(dz) < 1e-16) break;
+    }
+    double P, dP; legendre(n, z, P, dP);
+    x[i] = 0.5 * (z + 1.0);
+    w[i] = 1.0 / ((1.0 - z * z) * dP * dP);   // (2/((1-z^2)P'^2))/2
+  }
+}
+
+// Gauss-Lobatto on [0,1] (QGaussLobatto<1>(n); also the FE_Q support points).
+void lobatto01(int n, double *x, double *w) {
+  const int N = n - 1;
+  for (int i = 0; i < n; ++i) {
+    double z;
+    if (i == 0) z = -1.0;
+    else if (i == N) z = 1.0;
+    else {
+      z = -std::cos(M_PI * i / N);
+      for (int it = 0; it < 100; ++it) {
+        // root of P_N'(z): Newton with P_N'' from the Legendre ODE
+        double P, dP; legendre(N, z, P, dP);
+        const double d2P = (2.0 * z * dP - N * (N + 1.0) * P) / (1.0 - z * z);
+        const double dz = dP / d2P; z -= dz;
+        if (std::fabs(dz) < 1e-16) break;
+      }
+    }
+    double P, dP; legendre(N, z, P, dP);
+    x[i] = 0.5 * (z + 1.0);
+    w[i] = 1.0 / (N * (N + 1.0) * P * P);     // (2/(N(N+1)P^2))/2
+  }
+  // symmetrise (kills 1e-17 asymmetries from the Newton iteration)
+  for (int i = 0; i < n / 2; ++i) {
+    const double xs = 0.5 * (x[i] + (1.0 - x[n - 1 - i]));
+    x[i] = xs; x[n - 1 - i] = 1.0 - xs;
+    const double ws = 0.5 * (w[i] + w[n - 1 - i]);
+    w[i] = ws; w[n - 1 - i] = ws;
+  }
+  if (n % 2) x[n / 2] = 0.5;
+}
+
+// Lagrange basis through nodes[0..n) evaluated at x: value and derivative.
+void lagrange(int n, const double *nodes, double x, double *val, double *der) {
+  for (int a = 0; a < n; ++a) {
+    double v = 1.0;
+    for (int b = 0; b < n; ++b)
+      if (b != a) v *= (x - nodes[b]) / (nodes[a] - nodes[b]);
+    val[a] = v;
+    double d = 0.0;
+    for (int c = 0; c < n; ++c) {
+      if (c == a) continue;
+      double t = 1.0 / (nodes[a] - nodes[c]);
+      for (int b = 0; b < n; ++b)
+        if (b != a && b != c) t *= (x - nodes[b]) / (nodes[a] - nodes[b]);
+      d += t;
+    }
+    der[a] = d;
+  }
+}
+
+struct Tables {
+  int n = 0;                   // p+1 = dofs per direction = q-points per direction
+  std::vector<double> xi;      // FE_Q support points (GLL) on [0,1]
+  std::vector<double> xq, wq;  // 1D quadrature
+  std::vector<double> B;       // B[q*n+i]  = phi_i(xq_q)
+  std::vector<double> Dg;      // Dg[q*n+i] = phi_i'(xq_q)
+  void init(int p, int quad_kind) {
+    n = p + 1;
+    xi.resize(n); xq.resize(n); wq.resize(n); B.resize(n * n); Dg.resize(n * n);
+    std::vector<double> tmp(n);
+    lobatto01(n, xi.data(), tmp.data());
+    if (quad_kind == 0) gauss01(n, xq.data(), wq.data());
+    else                lobatto01(n, xq.data(), wq.data());
+    for (int q = 0; q < n; ++q)
+      lagrange(n, xi.data(), xq[q], &B[q * n], &Dg[q * n]);
+    if (quad_kind == 1)  // collocation: B is exactly the identity
+      for (int q = 0; q < n; ++q)
+        for (int i = 0; i < n; ++i) B[q * n + i] = (q == i) ? 1.0 : 0.0;
+  }
+};
+
+// ------------------------------------------------------------------- mesh
+struct Mesh {
+  int p, n, quad_kind;
+  int nc[3];                   // cells per direction
+  int nd[3];                   // dofs per direction = nc*p+1
+  double lo[3], hi[3];
+  int deform; double eps;
+  Tables T;
+  int64_t n_cells, n_dofs;
+  // per cell, per q-point (x fastest):
+  std::vector<double> invJ;    // [cell][9][n^3]  invJ[d*3+f] = d xi_d / d x_f
+  std::vector<double> JxW;     // [cell][n^3]
+  std::vector<double> G;       // [6][cell][n^3]  (reference plane-major layout)
+  std::vector<double> xq;      // [cell][3][n^3]  real coordinates of q-points
+  std::vector<double> helm_a;  // [cell][n^3]     a(x_q) for Helmholtz
+
+  int64_t dof(int gx, int gy, int gz) const {
+    return gx + (int64_t)nd[0] * (gy + (int64_t)nd[1] * gz);
+  }
+  bool on_boundary(int gx, int gy, int gz) const {
+    return gx == 0 || gy == 0 || gz == 0 || gx == nd[0] - 1 ||
+           gy == nd[1] - 1 || gz == nd[2] - 1;
+  }
+  // smooth deformation of the physical point (config 5; new input, the
+  // reference only has subdivided_hyper_rectangle, bp5/step-64.cu:661)
+  void map_point(const double *x, double *y) const {
+    if (deform == 0) { y[0] = x[0]; y[1] = x[1]; y[2] = x[2]; return; }
+    double s = 1.0;
+    for (int d = 0; d < 3; ++d)
+      s *= std::sin(M_PI * (x[d] - lo[d]) / (hi[d] - lo[d]));
+    for (int d = 0; d < 3; ++d) y[d] = x[d] + eps * (hi[d] - lo[d]) * s;
+  }
+};
+
+// geometry of one cell with MappingQGeneric(p): x(xi) = sum_a X_a phi_a(xi),
+// X_a = image of the GLL support points.
+void cell_geometry(const Mesh &m, int cx, int cy, int cz, double *invJ /*[9][n3]*/,
+                   double *JxW, double *xq /*[3][n3]*/) {
+  const int n = m.n, n3 = n * n * n;
+  const Tables &T = m.T;
+  std::vector<double> X(3 * n3);
+  const int c[3] = {cx, cy, cz};
+  double h[3];
+  for (int d = 0; d < 3; ++d) h[d] = (m.hi[d] - m.lo[d]) / m.nc[d];
+  for (int k = 0; k < n; ++k)
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) {
+        const int loc[3] = {i, j, k};
+        double x[3], y[3];
+        for (int d = 0; d < 3; ++d) x[d] = m.lo[d] + h[d] * (c[d] + T.xi[loc[d]]);
+        m.map_point(x, y);
+        for (int d = 0; d < 3; ++d) X[d * n3 + (k * n + j) * n + i] = y[d];
+      }
+  for (int qz = 0; qz < n; ++qz)
+    for (int qy = 0; qy < n; ++qy)
+      for (int qx = 0; qx < n; ++qx) {
+        const int q = (qz * n + qy) * n + qx;
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        double xr[3] = {0, 0, 0};
+        for (int k = 0; k < n; ++k)
+          for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+              const int a = (k * n + j) * n + i;
+              const double bx = T.B[qx * n + i], by = T.B[qy * n + j], bz = T.B[qz * n + k];
+              const double dx = T.Dg[qx * n + i], dy = T.Dg[qy * n + j], dz = T.Dg[qz * n + k];
+              const double g0 = dx * by * bz, g1 = bx * dy * bz, g2 = bx * by * dz;
+              const double v = bx * by * bz;
+              for (int d = 0; d < 3; ++d) {
+                const double Xa = X[d * n3 + a];
+                J[d][0] += Xa * g0; J[d][1] += Xa * g1; J[d][2] += Xa * g2;
+                xr[d] += Xa * v;
+              }
+            }
+        const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
+                           J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        const double id = 1.0 / det;
+        double I[3][3];
+        I[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * id;
+        I[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+        I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+        I[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * id;
+        I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+        I[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+        I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * id;
+        I[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+        I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+        for (int d = 0; d < 3; ++d)
+          for (int f = 0; f < 3; ++f) invJ[(d * 3 + f) * n3 + q] = I[d][f];
+        JxW[q] = det * T.wq[qx] * T.wq[qy] * T.wq[qz];
+        for (int d = 0; d < 3; ++d) xq[d * n3 + q] = xr[d];
+      }
+}
+
+void build_geometry(Mesh &m) {
+  const int n3 = m.n * m.n * m.n;
+  m.invJ.resize((size_t)m.n_cells * 9 * n3);
+  m.JxW.resize((size_t)m.n_cells * n3);
+  m.G.resize((size_t)6 * m.n_cells * n3);
+  m.xq.resize((size_t)m.n_cells * 3 * n3);
+  m.helm_a.resize((size_t)m.n_cells * n3);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < m.n_cells; ++c) {
+    const int cx = c % m.nc[0], cy = (c / m.nc[0]) % m.nc[1], cz = c / ((int64_t)m.nc[0] * m.nc[1]);
+    double *iJ = &m.invJ[(size_t)c * 9 * n3], *jw = &m.JxW[(size_t)c * n3], *xq = &m.xq[(size_t)c * 3 * n3];
+    cell_geometry(m, cx, cy, cz, iJ, jw, xq);
+    // JacobianFunctor (bp5/step-64.cu:84-114): G = JxW * invJ invJ^T, upper
+    // triangle, planes (xx,yy,zz,xy,xz,yz), layout coef[plane][cell][q].
+    for (int q = 0; q < n3; ++q) {
+      double my[3][3];
+      for (int d = 0; d < 3; ++d)
+        for (int e = d; e < 3; ++e) {
+          double sum = iJ[(d * 3 + 0) * n3 + q] * iJ[(e * 3 + 0) * n3 + q];
+          for (int f = 1; f < 3; ++f) sum += iJ[(d * 3 + f) * n3 + q] * iJ[(e * 3 + f) * n3 + q];
+          my[d][e] = sum;
+        }
+      for (int d = 0; d < 3; ++d)
+        m.G[((size_t)d * m.n_cells + c) * n3 + q] = jw[q] * my[d][d];
+      int pl = 3;
+      for (int d = 0; d < 3; ++d)
+        for (int e = d + 1; e < 3; ++e, ++pl)
+          m.G[((size_t)pl * m.n_cells + c) * n3 + q] = jw[q] * my[d][e];
+      // VaryingCoefficientFunctor (step-64/step-64.cu:100-118)
+      double p2 = 0.0;
+      for (int d = 0; d < 3; ++d) p2 += xq[d * n3 + q] * xq[d * n3 + q];
+      m.helm_a[(size_t)c * n3 + q] = 10.0 / (0.05 + 2.0 * p2);
+    }
+  }
+}
+
+// ------------------------------------------------------- operator on a cell
+// evaluate_general-style: gradient component d = derivative matrix in
+// direction d, interpolation matrix in the two others (9 contractions),
+// then the q-point operation, then the exact transpose.
+// kind 0: Poisson with merged coefficients (bp5/step-64.cu:160-188)
+// kind 1: Helmholtz through invJ / JxW (get_gradient / submit_gradient /
+//         submit_value, bp5/fe_evaluation_gl.h:297-369; step-64.cu:154-160)
+template <int N>
+void cell_apply(const Mesh &m, int64_t c, int kind, const double *u, double *v) {
+  constexpr int N3 = N * N * N;
+  const double *B = m.T.B.data(), *D = m.T.Dg.data();
+  double t1[N3], t2[N3], val[N3], gr[3][N3];
+  auto contract = [&](const double *M, int dir, const double *in, double *out, bool transpose, bool add) {
+    // out(q) = sum_i M[q][i] in(i) along direction dir (or M^T when transpose)
+    const int stride = dir == 0 ? 1 : dir == 1 ? N : N * N;
+    for (int o = 0; o < N * N; ++o) {
+      int base;
+      if (dir == 0) base = o * N;
+      else if (dir == 1) base = (o / N) * N * N + (o % N);
+      else base = o;
+      for (int q = 0; q < N; ++q) {
+        double s = 0.0;
+        for (int i = 0; i < N; ++i)
+          s += (transpose ? M[i * N + q] : M[q * N + i]) * in[base + i * stride];
+        if (add) out[base + q * stride] += s; else out[base + q * stride] = s;
+      }
+    }
+  };
+  // gradients at q-points (reference coordinates)
+  contract(D, 0, u, t1, false, false); contract(B, 1, t1, t2, false, false); contract(B, 2, t2, gr[0], false, false);
+  contract(B, 0, u, t1, false, false); contract(D, 1, t1, t2, false, false); contract(B, 2, t2, gr[1], false, false);
+  contract(B, 0, u, t1, false, false); contract(B, 1, t1, t2, false, false); contract(D, 2, t2, gr[2], false, false);
+  if (kind == 1) { contract(B, 2, t2, val, false, false); }  // t2 = B_x B_y u
+  if (kind == 0) {
+    const int64_t nc = m.n_cells;
+    const double *G0 = &m.G[((size_t)0 * nc + c) * N3], *G1 = &m.G[((size_t)1 * nc + c) * N3],
+                 *G2 = &m.G[((size_t)2 * nc + c) * N3], *G3 = &m.G[((size_t)3 * nc + c) * N3],
+                 *G4 = &m.G[((size_t)4 * nc + c) * N3], *G5 = &m.G[((size_t)5 * nc + c) * N3];
+    for (int q = 0; q < N3; ++q) {
+      const double g0 = gr[0][q], g1 = gr[1][q], g2 = gr[2][q];
+      gr[0][q] = g0 * G0[q] + g1 * G3[q] + g2 * G4[q];
+      gr[1][q] = g0 * G3[q] + g1 * G1[q] + g2 * G5[q];
+      gr[2][q] = g0 * G4[q] + g1 * G5[q] + g2 * G2[q];
+    }
+  } else {
+    const double *iJ = &m.invJ[(size_t)c * 9 * N3], *jw = &m.JxW[(size_t)c * N3], *a = &m.helm_a[(size_t)c * N3];
+    for (int q = 0; q < N3; ++q) {
+      double g[3], r[3];
+      for (int d1 = 0; d1 < 3; ++d1) {   // get_gradient: J^{-T} grad_ref
+        double s = 0.0;
+        for (int d2 = 0; d2 < 3; ++d2) s += iJ[(3 * d2 + d1) * N3 + q] * gr[d2][q];
+        g[d1] = s;
+      }
+      for (int d1 = 0; d1 < 3; ++d1) {   // submit_gradient: J^{-1} g * JxW
+        double s = 0.0;
+        for (int d2 = 0; d2 < 3; ++d2) s += iJ[(3 * d1 + d2) * N3 + q] * g[d2];
+        r[d1] = s * jw[q];
+      }
+      gr[0][q] = r[0]; gr[1][q] = r[1]; gr[2][q] = r[2];
+      val[q] = a[q] * val[q] * jw[q];    // submit_value(coef * get_value)
+    }
+  }
+  // integrate: exact transpose
+  contract(B, 2, gr[0], t1, true, false); contract(B, 1, t1, t2, true, false); contract(D, 0, t2, v, true, false);
+  contract(B, 2, gr[1], t1, true, false); contract(D, 1, t1, t2, true, false); contract(B, 0, t2, v, true, true);
+  contract(D, 2, gr[2], t1, true, false); contract(B, 1, t1, t2, true, false); contract(B, 0, t2, v, true, true);
+  if (kind == 1) {
+    contract(B, 2, val, t1, true, false); contract(B, 1, t1, t2, true, false); contract(B, 0, t2, v, true, true);
+  }
+}
+
+template <int N>
+void apply_all(const Mesh &m, int kind, const double *src, double *dst) {
+  constexpr int N3 = N * N * N;
+  const int p = m.p;
+  // 8 parity colours: cells of one colour share no DoF => race-free scatter.
+  for (int colour = 0; colour < 8; ++colour) {
+    const int bx = colour & 1, by = (colour >> 1) & 1, bz = (colour >> 2) & 1;
+    const int mx = (m.nc[0] - bx + 1) / 2, my = (m.nc[1] - by + 1) / 2, mz = (m.nc[2] - bz + 1) / 2;
+    const int64_t cnt = (int64_t)mx * my * mz;
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < cnt; ++t) {
+      const int cx = 2 * (t % mx) + bx, cy = 2 * ((t / mx) % my) + by, cz = 2 * (t / ((int64_t)mx * my)) + bz;
+      const int64_t c = cx + (int64_t)m.nc[0] * (cy + (int64_t)m.nc[1] * cz);
+      double u[N3], v[N3];
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < N; ++j)
+          for (int i = 0; i < N; ++i)
+            u[(k * N + j) * N + i] = src[m.dof(cx * p + i, cy * p + j, cz * p + k)];
+      cell_apply<N>(m, c, kind, u, v);
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < N; ++j)
+          for (int i = 0; i < N; ++i)
+            dst[m.dof(cx * p + i, cy * p + j, cz * p + k)] += v[(k * N + j) * N + i];
+    }
+  }
+}
+
+void apply_dispatch(const Mesh &m, int kind, const double *src, double *dst) {
+  switch (m.n) {
+    case 2: apply_all<2>(m, kind, src, dst); break;
+    case 3: apply_all<3>(m, kind, src, dst); break;
+    case 4: apply_all<4>(m, kind, src, dst); break;
+    case 5: apply_all<5>(m, kind, src, dst); break;
+    case 6: apply_all<6>(m, kind, src, dst); break;
+    case 7: apply_all<7>(m, kind, src, dst); break;
+    case 8: apply_all<8>(m, kind, src, dst); break;
+    case 9: apply_all<9>(m, kind, src, dst); break;
+    default: std::abort();
+  }
+}
+
+// vmult (bp5/step-64.cu:263-276).
+// semantics 0 ("device"): dst (+)= cell loop over the unconstrained operator,
+//   then dst[c] = src[c] on Dirichlet DoFs  ->  [A_ii A_ib; 0 I] src
+// semantics 1 ("cpu"): deal.II CPU MatrixFree reads constrained DoFs as 0
+//   ->  [A_ii 0; 0 I] src.   Identical whenever src vanishes on the boundary.
+void vmult(const Mesh &m, int kind, int semantics, bool zero_dst, const double *src, double *dst) {
+  const int64_t N = m.n_dofs;
+  if (zero_dst) std::memset(dst, 0, sizeof(double) * N);
+  std::vector<double> tmp;
+  const double *s = src;
+  if (semantics == 1) {
+    tmp.assign(src, src + N);
+    for (int gz = 0; gz < m.nd[2]; ++gz)
+      for (int gy = 0; gy < m.nd[1]; ++gy)
+        for (int gx = 0; gx < m.nd[0]; ++gx)
+          if (m.on_boundary(gx, gy, gz)) tmp[m.dof(gx, gy, gz)] = 0.0;
+    s = tmp.data();
+  }
+  apply_dispatch(m, kind, s, dst);
+#pragma omp parallel for schedule(static)
+  for (int gz = 0; gz < m.nd[2]; ++gz)
+    for (int gy = 0; gy < m.nd[1]; ++gy)
+      for (int gx = 0; gx < m.nd[0]; ++gx)
+        if (m.on_boundary(gx, gy, gz)) dst[m.dof(gx, gy, gz)] = src[m.dof(gx, gy, gz)];
+}
+
+double dot(int64_t N, const double *a, const double *b) {
+  double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+  for (int64_t i = 0; i < N; ++i) s += a[i] * b[i];
+  return s;
+}
+
+}  // namespace
+
+// =============================================================== C interface
+extern "C" {
+
+// 1D rules and shape tables (for cross-checks from Python)
+void orc_gauss01(int n, double *x, double *w) { gauss01(n, x, w); }
+void orc_lobatto01(int n, double *x, double *w) { lobatto01(n, x, w); }
+void orc_shape(int p, int quad_kind, double *B, double *Dg, double *xq, double *wq, double *xi) {
+  Tables T; T.init(p, quad_kind);
+  const int n = p + 1;
+  std::memcpy(B, T.B.data(), sizeof(double) * n * n);
+  std::memcpy(Dg, T.Dg.data(), sizeof(double) * n * n);
+  std::memcpy(xq, T.xq.data(), sizeof(double) * n);
+  std::memcpy(wq, T.wq.data(), sizeof(double) * n);
+  std::memcpy(xi, T.xi.data(), sizeof(double) * n);
+}
+
+void *orc_mesh_create(int p, int quad_kind, int nx, int ny, int nz, double lx0, double ly0, double lz0,
+                      double hx, double hy, double hz, int deform, double eps) {
+  if (p < 1 || p > 8) return nullptr;
+  Mesh *m = new Mesh;
+  m->p = p; m->n = p + 1; m->quad_kind = quad_kind;
+  m->nc[0] = nx; m->nc[1] = ny; m->nc[2] = nz;
+  for (int d = 0; d < 3; ++d) m->nd[d] = m->nc[d] * p + 1;
+  m->lo[0] = lx0; m->lo[1] = ly0; m->lo[2] = lz0;
+  m->hi[0] = hx; m->hi[1] = hy; m->hi[2] = hz;
+  m->deform = deform; m->eps = eps;
+  m->T.init(p, quad_kind);
+  m->n_cells = (int64_t)nx * ny * nz;
+  m->n_dofs = (int64_t)m->nd[0] * m->nd[1] * m->nd[2];
+  build_geometry(*m);
+  return m;
+}
+void orc_mesh_destroy(void *h) { delete static_cast<Mesh *>(h); }
+int64_t orc_n_dofs(void *h) { return static_cast<Mesh *>(h)->n_dofs; }
+int64_t orc_n_cells(void *h) { return static_cast<Mesh *>(h)->n_cells; }
+
+// merged coefficient, reference layout coef[plane][cell][q]  (bp5/step-64.cu:108,112)
+void orc_metric(void *h, double *G) {
+  Mesh *m = static_cast<Mesh *>(h);
+  std::memcpy(G, m->G.data(), sizeof(double) * m->G.size());
+}
+void orc_jxw(void *h, double *out) { Mesh *m = static_cast<Mesh *>(h); std::memcpy(out, m->JxW.data(), sizeof(double) * m->JxW.size()); }
+void orc_inv_jacobian(void *h, double *out) { Mesh *m = static_cast<Mesh *>(h); std::memcpy(out, m->invJ.data(), sizeof(double) * m->invJ.size()); }
+
+// coordinates of every global DoF (lexicographic), for comparing partitioned runs
+void orc_dof_coords(void *h, double *xyz /*[n_dofs][3]*/) {
+  Mesh *m = static_cast<Mesh *>(h);
+  const int p = m->p;
+  for (int gz = 0; gz < m->nd[2]; ++gz)
+    for (int gy = 0; gy < m->nd[1]; ++gy)
+      for (int gx = 0; gx < m->nd[0]; ++gx) {
+        const int g[3] = {gx, gy, gz};
+        double x[3], y[3];
+        for (int d = 0; d < 3; ++d) {
+          int c = g[d] / p, l = g[d] % p;
+          if (c == m->nc[d]) { c -= 1; l = p; }
+          x[d] = m->lo[d] + (m->hi[d] - m->lo[d]) / m->nc[d] * (c + m->T.xi[l]);
+        }
+        m->map_point(x, y);
+        double *o = &xyz[3 * m->dof(gx, gy, gz)];
+        o[0] = y[0]; o[1] = y[1]; o[2] = y[2];
+      }
+}
+
+void orc_boundary_mask(void *h, uint8_t *mask) {
+  Mesh *m = static_cast<Mesh *>(h);
+  for (int gz = 0; gz < m->nd[2]; ++gz)
+    for (int gy = 0; gy < m->nd[1]; ++gy)
+      for (int gx = 0; gx < m->nd[0]; ++gx) mask[m->dof(gx, gy, gz)] = m->on_boundary(gx, gy, gz);
+}
+
+// kind: 0 Poisson (BP5), 1 Helmholtz (step-64); semantics: 0 device, 1 cpu
+void orc_vmult(void *h, int kind, int semantics, int zero_dst, const double *src, double *dst) {
+  vmult(*static_cast<Mesh *>(h), kind, semantics, zero_dst != 0, src, dst);
+}
+
+// assemble_rhs (bp5/step-64.cu:372-418): b_i = int phi_i * 1, QGauss(p+1)
+// regardless of the operator's quadrature, constrained rows dropped (= 0).
+void orc_rhs(void *h, double *b) {
+  Mesh *m = static_cast<Mesh *>(h);
+  const int n = m->n, n3 = n * n * n, p = m->p;
+  Mesh g = *m;   // geometry with QGauss(p+1) if the operator uses GLL
+  const Mesh *mg = m;
+  if (m->quad_kind != 0) { g.quad_kind = 0; g.T.init(p, 0); build_geometry(g); mg = &g; }
+  std::memset(b, 0, sizeof(double) * m->n_dofs);
+  const double *B = mg->T.B.data();
+  for (int64_t c = 0; c < m->n_cells; ++c) {
+    const int cx = c % m->nc[0], cy = (c / m->nc[0]) % m->nc[1], cz = c / ((int64_t)m->nc[0] * m->nc[1]);
+    const double *jw = &mg->JxW[(size_t)c * n3];
+    for (int k = 0; k < n; ++k)
+      for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+          const int gx = cx * p + i, gy = cy * p + j, gz = cz * p + k;
+          if (m->on_boundary(gx, gy, gz)) continue;
+          double s = 0.0;
+          for (int qz = 0; qz < n; ++qz)
+            for (int qy = 0; qy < n; ++qy)
+              for (int qx = 0; qx < n; ++qx)
+                s += B[qx * n + i] * B[qy * n + j] * B[qz * n + k] * jw[(qz * n + qy) * n + qx];
+          b[m->dof(gx, gy, gz)] += s;
+        }
+  }
+}
+
+// ||u||_L2 with QGauss(p+2) (bp5/step-64.cu:604-615).  The reference stores the
+// cellwise norms in a Vector<float>; reproduce that rounding.
+double orc_l2_norm(void *h, const double *u) {
+  Mesh *m = static_cast<Mesh *>(h);
+  const int n = m->n, p = m->p, nq = p + 2;
+  std::vector<double> xq(nq), wq(nq), Bq(nq * n), Dq(nq * n);
+  gauss01(nq, xq.data(), wq.data());
+  for (int q = 0; q < nq; ++q) lagrange(n, m->T.xi.data(), xq[q], &Bq[q * n], &Dq[q * n]);
+  double total = 0.0;
+  const int n3 = n * n * n;
+  std::vector<double> X(3 * n3), ul(n3);
+  double hh[3];
+  for (int d = 0; d < 3; ++d) hh[d] = (m->hi[d] - m->lo[d]) / m->nc[d];
+  for (int64_t c = 0; c < m->n_cells; ++c) {
+    const int cc[3] = {(int)(c % m->nc[0]), (int)((c / m->nc[0]) % m->nc[1]), (int)(c / ((int64_t)m->nc[0] * m->nc[1]))};
+    for (int k = 0; k < n; ++k)
+      for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+          const int loc[3] = {i, j, k};
+          double x[3], y[3];
+          for (int d = 0; d < 3; ++d) x[d] = m->lo[d] + hh[d] * (cc[d] + m->T.xi[loc[d]]);
+          m->map_point(x, y);
+          for (int d = 0; d < 3; ++d) X[d * n3 + (k * n + j) * n + i] = y[d];
+          ul[(k * n + j) * n + i] = u[m->dof(cc[0] * p + i, cc[1] * p + j, cc[2] * p + k)];
+        }
+    double cell = 0.0;
+    for (int qz = 0; qz < nq; ++qz)
+      for (int qy = 0; qy < nq; ++qy)
+        for (int qx = 0; qx < nq; ++qx) {
+          double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, val = 0.0;
+          for (int k = 0; k < n; ++k)
+            for (int j = 0; j < n; ++j)
+              for (int i = 0; i < n; ++i) {
+                const int a = (k * n + j) * n + i;
+                const double bx = Bq[qx * n + i], by = Bq[qy * n + j], bz = Bq[qz * n + k];
+                const double dx = Dq[qx * n + i], dy = Dq[qy * n + j], dz = Dq[qz * n + k];
+                val += bx * by * bz * ul[a];
+                for (int d = 0; d < 3; ++d) {
+                  J[d][0] += X[d * n3 + a] * dx * by * bz;
+                  J[d][1] += X[d * n3 + a] * bx * dy * bz;
+                  J[d][2] += X[d * n3 + a] * bx * by * dz;
+                }
+              }
+          const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
+                             J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                             J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+          cell += val * val * det * wq[qx] * wq[qy] * wq[qz];
+        }
+    const float cn = (float)std::sqrt(cell);
+    total += (double)cn * (double)cn;
+  }
+  return std::sqrt(total);
+}
+
+// -------------------------------------------------------------------- CG
+// control: 0 = IterationNumberControl(max_its, tol): success at tol OR at
+//              max_its (bp5/step-64.cu:443-445)
+//          1 = SolverControl(max_its, tol): failure at max_its
+//              (step-64/step-64.cu:513-514)
+// variant: 0 = textbook preconditioned CG as in deal.II SolverCG ("pcg-standard")
+//          1 = SolverCGFullMerge scalar recurrences (bp5/solver.h:502-505,533)
+//              with the two-step x update applied with the CORRECT parity
+//              (the shipped :425 test is wrong for it >= 4; SURVEY finding 4)
+//          2 = SolverCGFullMerge exactly AS SHIPPED (x wrong, residuals right)
+// diag: diagonal preconditioner entries (DiagonalMatrix), or NULL for identity.
+// returns 0 success, 1 no convergence.  history[it] = residual norm, it=0..its
+int orc_cg(void *h, int kind, int variant, int control, double tol, int max_its, const double *diag,
+           double *x, const double *b, int *its_out, double *res_out, double *history, int history_len) {
+  Mesh *m = static_cast<Mesh *>(h);
+  const int64_t N = m->n_dofs;
+  std::vector<double> g(N), d(N), hh(N), ones;
+  if (!diag) { ones.assign(N, 1.0); diag = ones.data(); }
+  bool all_zero = true;
+  for (int64_t i = 0; i < N; ++i) if (x[i] != 0.0) { all_zero = false; break; }
+  if (!all_zero) {
+    vmult(*m, kind, 0, true, x, g.data());
+    for (int64_t i = 0; i < N; ++i) g[i] -= b[i];
+  } else
+    for (int64_t i = 0; i < N; ++i) g[i] = -b[i];
+  double res = std::sqrt(dot(N, g.data(), g.data()));
+  int it = 0;
+  if (history && history_len > 0) history[0] = res;
+  auto check = [&](int step, double value) -> int {  // 0 iterate, 1 success, 2 failure
+    if (value <= tol) return 1;
+    if (step >= max_its || std::isnan(value)) return control == 0 ? 1 : 2;
+    return 0;
+  };
+  int conv = check(0, res);
+  if (conv != 0) { *its_out = 0; *res_out = res; return conv == 1 ? 0 : 1; }
+
+  if (variant == 0) {
+    // deal.II SolverCG::solve
+    for (int64_t i = 0; i < N; ++i) { hh[i] = diag[i] * g[i]; d[i] = -hh[i]; }
+    double gh = dot(N, g.data(), hh.data());
+    while (conv == 0) {
+      ++it;
+      vmult(*m, kind, 0, true, d.data(), hh.data());
+      double alpha = dot(N, d.data(), hh.data());
+      alpha = gh / alpha;
+      for (int64_t i = 0; i < N; ++i) { x[i] += alpha * d[i]; g[i] += alpha * hh[i]; }
+      res = std::sqrt(dot(N, g.data(), g.data()));
+      if (history && it < history_len) history[it] = res;
+      conv = check(it, res);
+      if (conv != 0) break;
+      for (int64_t i = 0; i < N; ++i) hh[i] = diag[i] * g[i];
+      double beta = gh;
+      gh = dot(N, g.data(), hh.data());
+      beta = gh / beta;
+      for (int64_t i = 0; i < N; ++i) d[i] = beta * d[i] - hh[i];
+    }
+  } else {
+    double alpha = 0.0, beta = 0.0, alpha_old = 0.0, beta_old = 0.0;
+    while (conv == 0) {
+      ++it;
+      // 1) update region (update_a0 / update_a / update_a1, solver.h:48-140)
+      if (alpha == 0.0) {
+        for (int64_t i = 0; i < N; ++i) { d[i] = -diag[i] * g[i]; hh[i] = 0.0; }
+      } else {
+        bool two_step;
+        if (variant == 2) two_step = (alpha_old != 0.0);          // as shipped (:425)
+        else              two_step = (it % 2 == 1);               // correct parity
+        const bool skip_x = (variant == 2) ? (alpha_old == 0.0) : (it % 2 == 0);
+        const double apa = two_step && beta_old != 0.0 ? alpha + alpha_old / beta_old : 0.0;
+        const double aob = two_step && beta_old != 0.0 ? alpha_old / beta_old : 0.0;
+        for (int64_t i = 0; i < N; ++i) {
+          const double r_old = g[i], r_new = r_old + alpha * hh[i], pst = d[i];
+          if (two_step) x[i] += apa * pst + aob * diag[i] * r_old;
+          else if (!skip_x) x[i] += alpha * pst;
+          g[i] = r_new;
+          d[i] = beta * pst - diag[i] * r_new;
+          hh[i] = 0.0;
+        }
+      }
+      // 2) h = A d with do_zero_out = false (h was zeroed above)
+      vmult(*m, kind, 0, false, d.data(), hh.data());
+      // 3) seven dot products (update_b, solver.h:142-311)
+      double r[7] = {0, 0, 0, 0, 0, 0, 0};
+      {
+        double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0;
+#pragma omp parallel for reduction(+ : r0, r1, r2, r3, r4, r5, r6) schedule(static)
+        for (int64_t i = 0; i < N; ++i) {
+          const double ps = d[i], rs = g[i], vs = hh[i], ds = diag[i];
+          r0 += ps * vs; r1 += vs * vs; r2 += rs * vs; r3 += rs * rs;
+          const double dv = ds * vs;
+          r4 += rs * dv; r5 += vs * dv; r6 += rs * ds * rs;
+        }
+        r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4; r[5] = r5; r[6] = r6;
+      }
+      alpha_old = alpha; beta_old = beta;
+      alpha = r[6] / r[0];
+      res = std::sqrt(r[3] + 2 * alpha * r[2] + alpha * alpha * r[1]);
+      if (history && it < history_len) history[it] = res;
+      conv = check(it, res);
+      if (conv != 0) {
+        if (it % 2 == 1) {
+          for (int64_t i = 0; i < N; ++i) x[i] += alpha * d[i];
+        } else {
+          const double apa = alpha + alpha_old / beta_old, aob = alpha_old / beta_old;
+          for (int64_t i = 0; i < N; ++i) x[i] += apa * d[i] + aob * diag[i] * g[i];
+        }
+        break;
+      }
+      beta = alpha * (r[4] + alpha * r[5]) / r[6];
+    }
+  }
+  *its_out = it; *res_out = res;
+  return conv == 1 ? 0 : 1;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+}  // extern "C"
