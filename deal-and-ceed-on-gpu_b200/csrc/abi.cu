@@ -1,0 +1,456 @@
+// extern "C" entry points declared in include/bp5_b200.h.
+#include <cstring>
+#include <new>
+
+#include "common.h"
+
+namespace bp5 {
+static thread_local char g_error[1024] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+const char *get_error() { return g_error; }
+}  // namespace bp5
+
+using namespace bp5;
+
+#define BP5_ABI_GUARD_BEGIN try {
+#define BP5_ABI_GUARD_END                                     \
+  }                                                           \
+  catch (const std::bad_alloc &) {                            \
+    set_error("out of host memory");                          \
+    return BP5_ERR_INVALID;                                   \
+  }                                                           \
+  catch (...) {                                               \
+    set_error("unexpected C++ exception at the ABI boundary"); \
+    return BP5_ERR_INVALID;                                   \
+  }
+
+extern "C" {
+
+const char *bp5_last_error(void) { return get_error(); }
+const char *bp5_version(void) { return "bp5_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------ context
+int bp5_context_create(int device, bp5_context_t *out) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(out != nullptr, "null output pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return BP5_ERR_CUDA;
+  }
+  BP5_REQUIRE(device >= 0 && device < count, "device index out of range");
+  BP5_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BP5_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return BP5_ERR_UNSUPPORTED;
+  }
+  bp5_context_t ctx = new bp5_context_s;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  BP5_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  BP5_CUDA(cudaMalloc(&ctx->scratch, sizeof(double) * 1024));
+  BP5_CUDA(cudaMallocHost(&ctx->scratch_host, sizeof(double) * 64));
+  *out = ctx;
+  return BP5_OK;
+  BP5_ABI_GUARD_END
+}
+
+int bp5_context_destroy(bp5_context_t ctx) {
+  if (!ctx) return BP5_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  cudaFree(ctx->scratch);
+  cudaFreeHost(ctx->scratch_host);
+  delete ctx;
+  return BP5_OK;
+}
+
+int bp5_context_synchronize(bp5_context_t ctx) {
+  BP5_REQUIRE(ctx, "null context");
+  BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BP5_OK;
+}
+void *bp5_context_stream(bp5_context_t ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int64_t bp5_context_launch_count(bp5_context_t ctx) { return ctx ? ctx->launches : 0; }
+
+// ----------------------------------------------------------------- operator
+int bp5_operator_create(bp5_context_t ctx, const bp5_problem_t *pr, bp5_operator_t *out) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(ctx && pr && out, "null argument");
+  BP5_REQUIRE(pr->degree >= 1 && pr->degree <= kMaxDegree, "degree must be in 1..8");
+  BP5_REQUIRE(pr->quadrature == BP5_QUAD_GAUSS || pr->quadrature == BP5_QUAD_GLL, "unknown quadrature");
+  BP5_REQUIRE(pr->operator_kind == BP5_OP_POISSON || pr->operator_kind == BP5_OP_HELMHOLTZ, "unknown operator");
+  BP5_REQUIRE(pr->geometry_mode == BP5_GEOM_STORED, "only stored-metric geometry is implemented");
+  BP5_REQUIRE(pr->deformation == 0 || pr->deformation == 1, "unknown deformation");
+  for (int d = 0; d < 3; ++d) {
+    BP5_REQUIRE(pr->cells[d] >= 1, "cells must be >= 1");
+    BP5_REQUIRE(pr->upper[d] > pr->lower[d], "upper must exceed lower");
+    BP5_REQUIRE(pr->part_grid[d] >= 1 && pr->part_coord[d] >= 0 && pr->part_coord[d] < pr->part_grid[d],
+                "bad partition");
+    BP5_REQUIRE(pr->part_grid[d] <= pr->cells[d], "more blocks than cells in a direction");
+  }
+  BP5_CUDA(cudaSetDevice(ctx->device));
+  bp5_operator_t op = new bp5_operator_s;
+  op->ctx = ctx;
+  op->prob = *pr;
+  op->p = pr->degree;
+  op->n = pr->degree + 1;
+  make_tables(op->p, pr->quadrature, op->tab);
+  op->metric_planes = pr->operator_kind == BP5_OP_HELMHOLTZ ? 7 : 6;
+  int64_t owned = 1, ncell = 1, nglob = 1;
+  for (int d = 0; d < 3; ++d) {
+    const int64_t G = pr->cells[d], P = pr->part_grid[d], c = pr->part_coord[d];
+    op->c0[d] = (int)(G * c / P);
+    op->lc[d] = (int)(G * (c + 1) / P) - op->c0[d];
+    op->ld[d] = op->lc[d] * op->p + 1;
+    op->has_lo[d] = c > 0;
+    op->has_hi[d] = c < P - 1;
+    op->od[d] = op->ld[d] - op->has_lo[d];
+    owned *= op->od[d];
+    ncell *= op->lc[d];
+    nglob *= G * op->p + 1;
+  }
+  op->n_owned = owned;
+  op->n_cells = ncell;
+  op->n_global = nglob;
+  int64_t goff = 0;
+  for (int m = 1; m < 8; ++m) {
+    bool exists = true;
+    int64_t sz = 1;
+    for (int d = 0; d < 3; ++d) {
+      if (m & (1 << d)) { if (!op->has_lo[d]) exists = false; }
+      else sz *= op->od[d];
+    }
+    op->ghost_offset[m] = goff;
+    op->ghost_size[m] = exists ? sz : 0;
+    goff += op->ghost_size[m];
+  }
+  op->n_ghost = goff;
+  if (op->n_owned + op->n_ghost >= (int64_t)2147483647) {
+    delete op;
+    set_error("block has %lld local DoFs; local indices are 32-bit (types::global_dof_index default)",
+              (long long)(owned + goff));
+    return BP5_ERR_UNSUPPORTED;
+  }
+  int rc = apply_choose(op);
+  if (rc == BP5_OK) rc = operator_setup_device(op);
+  if (rc != BP5_OK) { bp5_operator_destroy(op); return rc; }
+  *out = op;
+  return BP5_OK;
+  BP5_ABI_GUARD_END
+}
+
+int bp5_operator_destroy(bp5_operator_t op) {
+  if (!op) return BP5_OK;
+  cudaSetDevice(op->ctx->device);
+  cudaStreamSynchronize(op->ctx->stream);
+  cudaFree(op->l2g);
+  cudaFree(op->metric);
+  cudaFree(op->constrained);
+  cudaFree(op->cg_scalars);
+  bp5_vector_destroy(op->g);
+  bp5_vector_destroy(op->d);
+  bp5_vector_destroy(op->h);
+  bp5_vector_destroy(op->xh);
+  bp5_vector_destroy(op->bh);
+  delete op;
+  return BP5_OK;
+}
+
+int bp5_operator_sizes(bp5_operator_t op, int64_t *n_owned, int64_t *n_ghost, int64_t *n_global, int64_t *n_cells) {
+  BP5_REQUIRE(op, "null operator");
+  if (n_owned) *n_owned = op->n_owned;
+  if (n_ghost) *n_ghost = op->n_ghost;
+  if (n_global) *n_global = op->n_global;
+  if (n_cells) *n_cells = op->n_cells;
+  return BP5_OK;
+}
+
+int bp5_operator_initialize_dof_vector(bp5_operator_t op, bp5_vector_t *vec) {
+  BP5_REQUIRE(op && vec, "null argument");
+  return bp5_vector_create(op->ctx, op->n_owned, op->n_ghost, vec);
+}
+
+int bp5_operator_set_zero_out(bp5_operator_t op, int z) {
+  BP5_REQUIRE(op, "null operator");
+  op->do_zero_out = z != 0;
+  return BP5_OK;
+}
+
+static int check_vec(bp5_operator_t op, bp5_vector_t v) {
+  BP5_REQUIRE(v != nullptr, "null vector");
+  BP5_REQUIRE(v->n_owned == op->n_owned && v->n_ghost == op->n_ghost, "vector layout does not match the operator");
+  return BP5_OK;
+}
+
+int bp5_operator_cell_loop(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op, "null operator");
+  int rc;
+  if ((rc = check_vec(op, dst)) || (rc = check_vec(op, src))) return rc;
+  BP5_REQUIRE(dst != src, "dst and src must differ");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return apply_cell_loop(op, dst->d, src->d);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_operator_copy_constrained_values(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
+  BP5_REQUIRE(op, "null operator");
+  int rc;
+  if ((rc = check_vec(op, dst)) || (rc = check_vec(op, src))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return apply_copy_constrained(op, dst->d, src->d);
+}
+
+int bp5_operator_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op, "null operator");
+  int rc;
+  if ((rc = check_vec(op, dst)) || (rc = check_vec(op, src))) return rc;
+  BP5_REQUIRE(dst != src, "dst and src must differ");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  // bp5/step-64.cu:270-275.  With ghosts, the halo exchange is driven by the
+  // host that owns the communicator; this entry point
+  // does the local part: src ghosts must be up to date, dst ghosts receive the
+  // contributions for the neighbouring owners.
+  if (op->do_zero_out)
+    BP5_CUDA(cudaMemsetAsync(dst->d, 0, sizeof(double) * (dst->n_owned + dst->n_ghost), op->ctx->stream));
+  if ((rc = apply_cell_loop(op, dst->d, src->d))) return rc;
+  return apply_copy_constrained(op, dst->d, src->d);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_operator_vmult_ptr(bp5_operator_t op, double *dst, const double *src, int zero_dst) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && dst && src && dst != src, "bad argument");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  if (zero_dst) BP5_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (op->n_owned + op->n_ghost), op->ctx->stream));
+  int rc;
+  if ((rc = apply_cell_loop(op, dst, src))) return rc;
+  return apply_copy_constrained(op, dst, src);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_operator_assemble_rhs(bp5_operator_t op, bp5_vector_t b) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op, "null operator");
+  int rc;
+  if ((rc = check_vec(op, b))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return operator_assemble_rhs(op, b->d);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_operator_export_coefficients(bp5_operator_t op, double *host_out) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && host_out, "null argument");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  BP5_CUDA(cudaStreamSynchronize(op->ctx->stream));
+  return operator_export_coefficients(op, host_out);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_operator_export_dof_coordinates(bp5_operator_t op, double *host_out) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && host_out, "null argument");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return operator_export_coords(op, host_out);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_operator_export_global_indices(bp5_operator_t op, int64_t *host_out) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && host_out, "null argument");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return operator_export_global_indices(op, host_out);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_operator_l2_norm_sqr(bp5_operator_t op, bp5_vector_t u, double *out) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && out, "null argument");
+  int rc;
+  if ((rc = check_vec(op, u))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return operator_l2_norm_sqr(op, u->d, out);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *per_vmult, double *per_cg_it) {
+  BP5_REQUIRE(op, "null operator");
+  // per DoF 8 (read src) + 8 (write dst) + 8*planes per q-point;
+  // CG: read {x,r,p,h,diag} + write {x,r,p,h} = 72, plus the metric.
+  const double n3 = (double)op->n * op->n * op->n;
+  const double metric = 8.0 * op->metric_planes * n3 * (double)op->n_cells;
+  if (per_vmult) *per_vmult = 16.0 * (double)op->n_owned + metric;
+  if (per_cg_it) *per_cg_it = 72.0 * (double)op->n_owned + metric;
+  return BP5_OK;
+}
+
+const char *bp5_operator_kernel_name(bp5_operator_t op) { return op ? op->kernel_name.c_str() : ""; }
+
+// ------------------------------------------------------------------- vector
+int bp5_vector_create(bp5_context_t ctx, int64_t n_owned, int64_t n_ghost, bp5_vector_t *out) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(ctx && out, "null argument");
+  BP5_REQUIRE(n_owned >= 0 && n_ghost >= 0, "negative size");
+  BP5_CUDA(cudaSetDevice(ctx->device));
+  bp5_vector_t v = new bp5_vector_s;
+  v->ctx = ctx; v->n_owned = n_owned; v->n_ghost = n_ghost;
+  const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(n_owned + n_ghost, 1);
+  cudaError_t e = cudaMalloc(&v->d, bytes);
+  if (e != cudaSuccess) {
+    delete v;
+    set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return BP5_ERR_CUDA;
+  }
+  // reinit() zero-initialises (solver.h:369-371)
+  BP5_CUDA(cudaMemsetAsync(v->d, 0, bytes, ctx->stream));
+  *out = v;
+  return BP5_OK;
+  BP5_ABI_GUARD_END
+}
+
+int bp5_vector_create_like(bp5_vector_t other, bp5_vector_t *out) {
+  BP5_REQUIRE(other, "null vector");
+  return bp5_vector_create(other->ctx, other->n_owned, other->n_ghost, out);
+}
+
+int bp5_vector_destroy(bp5_vector_t v) {
+  if (!v) return BP5_OK;
+  cudaSetDevice(v->ctx->device);
+  cudaStreamSynchronize(v->ctx->stream);
+  cudaFree(v->d);
+  delete v;
+  return BP5_OK;
+}
+
+int bp5_vector_local_size(bp5_vector_t v, int64_t *n_owned, int64_t *n_ghost) {
+  BP5_REQUIRE(v, "null vector");
+  if (n_owned) *n_owned = v->n_owned;
+  if (n_ghost) *n_ghost = v->n_ghost;
+  return BP5_OK;
+}
+
+double *bp5_vector_get_values(bp5_vector_t v) { return v ? v->d : nullptr; }
+
+int bp5_vector_set(bp5_vector_t v, double value) {
+  BP5_REQUIRE(v, "null vector");
+  BP5_CUDA(cudaSetDevice(v->ctx->device));
+  return vec_fill(v->ctx, v->d, v->n_owned + v->n_ghost, value);
+}
+
+int bp5_vector_import_host(bp5_vector_t v, const double *host, int64_t n) {
+  BP5_REQUIRE(v && host, "null argument");
+  BP5_REQUIRE(n >= 0 && n <= v->n_owned + v->n_ghost, "bad length");
+  BP5_CUDA(cudaSetDevice(v->ctx->device));
+  BP5_CUDA(cudaMemcpyAsync(v->d, host, sizeof(double) * n, cudaMemcpyHostToDevice, v->ctx->stream));
+  BP5_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return BP5_OK;
+}
+
+int bp5_vector_export_host(bp5_vector_t v, double *host, int64_t n) {
+  BP5_REQUIRE(v && host, "null argument");
+  BP5_REQUIRE(n >= 0 && n <= v->n_owned + v->n_ghost, "bad length");
+  BP5_CUDA(cudaSetDevice(v->ctx->device));
+  BP5_CUDA(cudaMemcpyAsync(host, v->d, sizeof(double) * n, cudaMemcpyDeviceToHost, v->ctx->stream));
+  BP5_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return BP5_OK;
+}
+
+static int same_layout(bp5_vector_t a, bp5_vector_t b) {
+  BP5_REQUIRE(a && b, "null vector");
+  BP5_REQUIRE(a->n_owned == b->n_owned && a->n_ghost == b->n_ghost, "vector layouts differ");
+  return BP5_OK;
+}
+
+int bp5_vector_copy(bp5_vector_t dst, bp5_vector_t src) {
+  int rc;
+  if ((rc = same_layout(dst, src))) return rc;
+  BP5_CUDA(cudaSetDevice(dst->ctx->device));
+  BP5_CUDA(cudaMemcpyAsync(dst->d, src->d, sizeof(double) * (src->n_owned + src->n_ghost), cudaMemcpyDeviceToDevice,
+                           dst->ctx->stream));
+  return BP5_OK;
+}
+
+int bp5_vector_add(bp5_vector_t y, double a, bp5_vector_t x) {
+  int rc;
+  if ((rc = same_layout(y, x))) return rc;
+  BP5_CUDA(cudaSetDevice(y->ctx->device));
+  return vec_axpy(y->ctx, y->d, 1.0, a, x->d, y->n_owned, 0);
+}
+int bp5_vector_equ(bp5_vector_t y, double a, bp5_vector_t x) {
+  int rc;
+  if ((rc = same_layout(y, x))) return rc;
+  BP5_CUDA(cudaSetDevice(y->ctx->device));
+  return vec_axpy(y->ctx, y->d, 0.0, a, x->d, y->n_owned, 1);
+}
+int bp5_vector_sadd(bp5_vector_t y, double s, double a, bp5_vector_t x) {
+  int rc;
+  if ((rc = same_layout(y, x))) return rc;
+  BP5_CUDA(cudaSetDevice(y->ctx->device));
+  return vec_axpy(y->ctx, y->d, s, a, x->d, y->n_owned, 2);
+}
+int bp5_vector_dot_local(bp5_vector_t x, bp5_vector_t y, double *out) {
+  int rc;
+  if ((rc = same_layout(x, y))) return rc;
+  BP5_REQUIRE(out, "null output");
+  BP5_CUDA(cudaSetDevice(x->ctx->device));
+  return vec_dot(x->ctx, x->d, y->d, x->n_owned, out);
+}
+int bp5_vector_norm_sqr_local(bp5_vector_t x, double *out) { return bp5_vector_dot_local(x, x, out); }
+int bp5_vector_all_zero_local(bp5_vector_t x, int *out) {
+  BP5_REQUIRE(x && out, "null argument");
+  BP5_CUDA(cudaSetDevice(x->ctx->device));
+  return vec_all_zero(x->ctx, x->d, x->n_owned, out);
+}
+int bp5_vector_zero_out_ghosts(bp5_vector_t v) {
+  BP5_REQUIRE(v, "null vector");
+  if (v->n_ghost == 0) return BP5_OK;
+  BP5_CUDA(cudaSetDevice(v->ctx->device));
+  BP5_CUDA(cudaMemsetAsync(v->d + v->n_owned, 0, sizeof(double) * v->n_ghost, v->ctx->stream));
+  return BP5_OK;
+}
+
+// ------------------------------------------------------------------- solver
+int bp5_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int variant, int control,
+                 double tol, int max_its, int *last_step, double *last_value, double *history, int history_len) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && x && b, "null argument");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return cg_solve(op, x, b, diag, variant, control, tol, max_its, last_step, last_value, history, history_len);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, int64_t n, int variant, int control,
+                      double tol, int max_its, int *last_step, double *last_value) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && x_host && b_host, "null argument");
+  BP5_REQUIRE(n == op->n_owned && op->n_ghost == 0, "host solve needs a single block and n == n_dofs");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  bp5_context_t ctx = op->ctx;
+  if (!op->xh) {
+    int rc;
+    if ((rc = bp5_vector_create(ctx, n, 0, &op->xh))) return rc;
+    if ((rc = bp5_vector_create(ctx, n, 0, &op->bh))) return rc;
+  }
+  BP5_CUDA(cudaMemcpyAsync(op->bh->d, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  BP5_CUDA(cudaMemcpyAsync(op->xh->d, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = cg_solve(op, op->xh, op->bh, nullptr, variant, control, tol, max_its, last_step, last_value, nullptr, 0);
+  if (rc != BP5_OK && rc != BP5_ERR_NO_CONVERGENCE) return rc;
+  BP5_CUDA(cudaMemcpyAsync(x_host, op->xh->d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  return rc;
+  BP5_ABI_GUARD_END
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// Host side of the cell loop: kernel selection per (degree, quadrature,
+// operator), persistent-grid sizing, and the Dirichlet copy
+// (MatrixFree::cell_loop / copy_constrained_values, bp5/step-64.cu:274-275).
+#include "apply.cuh"
+
+namespace bp5 {
+
+// cells per tile for each degree: fills the CTA's warps ((p+1)^2 threads per
+// cell) while keeping >= 2-4 CTAs resident per SM.
+template <int P> struct TileCells;
+template <> struct TileCells<1> { static constexpr int value = 32; };
+template <> struct TileCells<2> { static constexpr int value = 14; };
+template <> struct TileCells<3> { static constexpr int value = 8; };
+template <> struct TileCells<4> { static constexpr int value = 5; };
+template <> struct TileCells<5> { static constexpr int value = 3; };
+template <> struct TileCells<6> { static constexpr int value = 3; };
+template <> struct TileCells<7> { static constexpr int value = 2; };
+template <> struct TileCells<8> { static constexpr int value = 1; };
+
+static int cells_per_tile_for(int p) {
+  switch (p) {
+    case 1: return TileCells<1>::value; case 2: return TileCells<2>::value;
+    case 3: return TileCells<3>::value; case 4: return TileCells<4>::value;
+    case 5: return TileCells<5>::value; case 6: return TileCells<6>::value;
+    case 7: return TileCells<7>::value; case 8: return TileCells<8>::value;
+  }
+  return 0;
+}
+
+int apply_choose(bp5_operator_t op) {
+  const int cpt = cells_per_tile_for(op->p);
+  BP5_REQUIRE(cpt > 0, "degree must be 1..8");
+  const int n3 = op->n * op->n * op->n;
+  op->cells_per_tile = cpt;
+  op->n_tiles = (op->n_cells + cpt - 1) / cpt;
+  op->tile_doubles = ((int64_t)cpt * op->metric_planes * n3 + 1) & ~(int64_t)1;
+  char name[128];
+  snprintf(name, sizeof(name), "bp5_apply_kernel<p=%d,%s,%s,cells_per_tile=%d>", op->p,
+           op->prob.quadrature == BP5_QUAD_GLL ? "gll-collocation" : "gauss",
+           op->prob.operator_kind == BP5_OP_HELMHOLTZ ? "helmholtz" : "poisson", cpt);
+  op->kernel_name = name;
+  return BP5_OK;
+}
+
+template <int P, int QUAD, int HELM>
+static int launch(bp5_operator_t op, double *dst, const double *src) {
+  constexpr int CPT = TileCells<P>::value;
+  using Cfg = ApplyCfg<P, CPT, 6 + HELM>;
+  constexpr int N = P + 1;
+  auto kernel = bp5_apply_kernel<P, QUAD, HELM, CPT>;
+  static int blocks_per_sm = 0;   // per instantiation
+  if (blocks_per_sm == 0) {
+    BP5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    int nb = 0;
+    BP5_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, Cfg::NT, Cfg::SMEM_BYTES));
+    BP5_REQUIRE(nb > 0, "apply kernel does not fit on an SM");
+    blocks_per_sm = nb;
+  }
+  ApplyParams<N> prm;
+  prm.metric = op->metric; prm.l2g = op->l2g; prm.src = src; prm.dst = dst;
+  prm.n_cells = op->n_cells; prm.n_tiles = op->n_tiles; prm.skip = op->skip_flag;
+  for (int q = 0; q < N; ++q)
+    for (int i = 0; i < N; ++i) {
+      prm.tab.B[q * N + i] = op->tab.B[q * N + i];
+      prm.tab.Dt[q * N + i] = op->tab.Dt[q * N + i];
+    }
+  long long grid = (long long)blocks_per_sm * op->ctx->sm_count;
+  if (grid > op->n_tiles) grid = op->n_tiles;
+  if (grid < 1) grid = 1;
+  kernel<<<(unsigned)grid, Cfg::NT, Cfg::SMEM_BYTES, op->ctx->stream>>>(prm);
+  BP5_CHECK_LAUNCH();
+  op->ctx->launches++;
+  return BP5_OK;
+}
+
+template <int P>
+static int launch_p(bp5_operator_t op, double *dst, const double *src) {
+  const bool gll = op->prob.quadrature == BP5_QUAD_GLL;
+  const bool helm = op->prob.operator_kind == BP5_OP_HELMHOLTZ;
+  if (gll) return helm ? launch<P, 1, 1>(op, dst, src) : launch<P, 1, 0>(op, dst, src);
+  return helm ? launch<P, 0, 1>(op, dst, src) : launch<P, 0, 0>(op, dst, src);
+}
+
+int apply_cell_loop(bp5_operator_t op, double *dst, const double *src) {
+  switch (op->p) {
+    case 1: return launch_p<1>(op, dst, src);
+    case 2: return launch_p<2>(op, dst, src);
+    case 3: return launch_p<3>(op, dst, src);
+    case 4: return launch_p<4>(op, dst, src);
+    case 5: return launch_p<5>(op, dst, src);
+    case 6: return launch_p<6>(op, dst, src);
+    case 7: return launch_p<7>(op, dst, src);
+    case 8: return launch_p<8>(op, dst, src);
+  }
+  set_error("unsupported degree %d", op->p);
+  return BP5_ERR_UNSUPPORTED;
+}
+
+// copy_constrained_values [UPSTREAM], called at bp5/step-64.cu:275:
+// dst[c] = src[c] on Dirichlet dofs.
+__global__ void copy_constrained_kernel(const int *__restrict__ list, long long n, const double *__restrict__ src,
+                                        double *__restrict__ dst) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < n) { const int i = list[t]; dst[i] = src[i]; }
+}
+
+int apply_copy_constrained(bp5_operator_t op, double *dst, const double *src) {
+  if (op->n_constrained == 0) return BP5_OK;
+  const long long n = op->n_constrained;
+  copy_constrained_kernel<<<(unsigned)((n + 255) / 256), 256, 0, op->ctx->stream>>>(op->constrained, n, src, dst);
+  BP5_CHECK_LAUNCH();
+  op->ctx->launches++;
+  return BP5_OK;
+}
+
+}  // namespace bp5

@@ -1,0 +1,455 @@
+// Conjugate gradients around the operator: SolverCGFullMerge::solve
+// (bp5/solver.h:343-542) and dealii::SolverCG::solve as the driver uses it
+// (bp5/step-64.cu:446-453) [UPSTREAM].
+//
+// What changed relative to the reference, and why:
+//  * alpha, beta, the residual and the stopping decision live in a small device
+//    struct; the update kernels read them from memory.  The reference copies
+//    seven doubles to the host with a blocking cudaMemcpy and runs
+//    MPI_Allreduce every iteration (solver.h:489-494); here nothing crosses
+//    PCIe inside the loop, the host only polls an "are we done" word every few
+//    iterations, asynchronously.
+//  * the seven dot products (update_b, solver.h:142-311) are reduced with warp
+//    shuffles and per-block partials summed in a fixed order by the last block
+//    to arrive (deterministic; the reference's shared-memory tree relies on
+//    warp-synchronous execution, unsafe since sm_70), and the same block then
+//    evaluates the scalar recurrences of solver.h:497-533.
+//  * after convergence every kernel of the iteration turns into a no-op, so an
+//    asynchronous host never changes the result or last_step().
+//  * the two-step x update (update_a1, solver.h:106-140) is applied on odd
+//    iterations only; as shipped (test at solver.h:425) it runs on every
+//    iteration >= 3 and returns a wrong x (SURVEY.md finding 4).  Residual
+//    history and iteration count are identical either way.
+#include "apply.cuh"
+#include "common.h"
+
+namespace bp5 {
+
+constexpr int kCgBlocks = 592;
+constexpr int kCgThreads = 256;
+
+struct CgState {
+  double alpha, beta, alpha_old, beta_old;
+  double res, tol, gh;
+  int it;          // iterations completed == SolverControl::last_step()
+  int state;       // 0 iterate, 1 success, 2 failure (max its / nan), 3 divide by zero
+  int max_its, control;
+  unsigned ticket;
+  int history_len;
+};
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sums of K values; result valid in thread 0
+template <int K>
+__device__ __forceinline__ void block_sum_k(double (&v)[K], double *sh /*[K*32]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int j = 0; j < K; ++j) v[j] = warp_sum_d(v[j]);
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < K; ++j) sh[j * 32 + w] = v[j];
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      double r = lane < nw ? sh[j * 32 + lane] : 0.0;
+      v[j] = warp_sum_d(r);
+    }
+  }
+  __syncthreads();
+}
+
+// SolverControl::check / IterationNumberControl::check [UPSTREAM]
+__device__ __forceinline__ int control_check(int control, int step, int max_its, double value, double tol) {
+  if (control == BP5_CONTROL_ITERATION_NUMBER && step >= max_its) return 1;
+  if (value <= tol) return 1;
+  if (step >= max_its || isnan(value)) return 2;
+  return 0;
+}
+
+// ---------------------------------------------------------------- merged CG
+// MODE 0: update_a0 (solver.h:48-72)  1: update_a<false> (:74-104)  3: update_a1 (:106-140)
+template <int MODE, bool DIAG>
+__global__ void __launch_bounds__(256) cg_update_kernel(const CgState *__restrict__ st, double *__restrict__ p,
+                                                        double *__restrict__ r, double *__restrict__ v,
+                                                        double *__restrict__ x, const double *__restrict__ diag,
+                                                        long long n) {
+  if (st->state != 0) return;
+  const double alpha = st->alpha, beta = st->beta;
+  double apa = 0.0, aob = 0.0;
+  if (MODE == 3) { aob = st->alpha_old / st->beta_old; apa = alpha + aob; }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double dg = DIAG ? diag[i] : 1.0;
+    if (MODE == 0) {
+      p[i] = -dg * r[i];
+    } else {
+      const double r_old = r[i];
+      const double r_new = r_old + alpha * v[i];
+      const double p_old = p[i];
+      if (MODE == 3) x[i] += apa * p_old + aob * dg * r_old;
+      r[i] = r_new;
+      p[i] = beta * p_old - dg * r_new;
+    }
+    v[i] = 0.0;
+  }
+}
+
+template <bool DIAG>
+__global__ void __launch_bounds__(kCgThreads) cg_dots_kernel(CgState *st, const double *__restrict__ p,
+                                                             const double *__restrict__ r,
+                                                             const double *__restrict__ v,
+                                                             const double *__restrict__ diag, long long n,
+                                                             double *partials, double *history) {
+  if (st->state != 0) return;
+  __shared__ double sh[7 * 32];
+  __shared__ bool is_last;
+  constexpr int K = DIAG ? 7 : 4;
+  double s[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) s[j] = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double ps = p[i], rs = r[i], vs = v[i];
+    s[0] += ps * vs; s[1] += vs * vs; s[2] += rs * vs; s[3] += rs * rs;
+    if (DIAG) {
+      const double ds = diag[i], dv = ds * vs;
+      s[4] += rs * dv; s[5] += vs * dv; s[6] += rs * ds * rs;
+    }
+  }
+  block_sum_k<K>(s, sh);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) partials[blockIdx.x * 7 + j] = s[j];
+    __threadfence();
+    const unsigned t = atomicAdd(&st->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last block: fixed-order sum of the partials, then the scalar recurrences
+#pragma unroll
+  for (int j = 0; j < K; ++j) s[j] = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+#pragma unroll
+    for (int j = 0; j < K; ++j) s[j] += __ldcg(&partials[b * 7 + j]);
+  block_sum_k<K>(s, sh);
+  if (threadIdx.x == 0) {
+    double rr[7];
+#pragma unroll
+    for (int j = 0; j < K; ++j) rr[j] = s[j];
+    if (!DIAG) { rr[4] = rr[2]; rr[5] = rr[1]; rr[6] = rr[3]; }
+    const int it = st->it + 1;
+    st->alpha_old = st->alpha;
+    st->beta_old = st->beta;
+    st->ticket = 0;
+    st->it = it;
+    if (rr[0] == 0.0) { st->state = 3; return; }                 // ExcDivideByZero, solver.h:501
+    const double alpha = rr[6] / rr[0];                         // solver.h:502
+    const double res = sqrt(rr[3] + 2 * alpha * rr[2] + alpha * alpha * rr[1]);   // solver.h:504-505
+    st->alpha = alpha;
+    st->res = res;
+    if (history && it < st->history_len) history[it] = res;
+    const int conv = control_check(st->control, it, st->max_its, res, st->tol);
+    if (conv != 0) { st->state = conv; return; }
+    st->beta = alpha * (rr[4] + alpha * rr[5]) / rr[6];         // solver.h:533
+  }
+}
+
+// x update owed at termination (solver.h:509-526)
+template <bool DIAG>
+__global__ void cg_finish_kernel(const CgState *__restrict__ st, double *__restrict__ x,
+                                 const double *__restrict__ d, const double *__restrict__ g,
+                                 const double *__restrict__ diag, long long n) {
+  if (st->state == 0 || st->state == 3 || st->it == 0) return;
+  const double alpha = st->alpha;
+  const bool odd = (st->it % 2) == 1;
+  double apa = 0.0, aob = 0.0;
+  if (!odd) { aob = st->alpha_old / st->beta_old; apa = alpha + aob; }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (odd) x[i] += alpha * d[i];
+    else x[i] += apa * d[i] + aob * (DIAG ? diag[i] : 1.0) * g[i];
+  }
+}
+
+// -------------------------------------------------------------- standard CG
+// d = -D g, h = D g
+template <bool DIAG>
+__global__ void std_init_kernel(double *__restrict__ d, double *__restrict__ h, const double *__restrict__ g,
+                                const double *__restrict__ diag, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double hv = (DIAG ? diag[i] : 1.0) * g[i];
+    h[i] = hv; d[i] = -hv;
+  }
+}
+
+// alpha = gh / (d.h)
+__global__ void __launch_bounds__(kCgThreads) std_dh_kernel(CgState *st, const double *__restrict__ d,
+                                                            const double *__restrict__ h, long long n,
+                                                            double *partials) {
+  if (st->state != 0) return;
+  __shared__ double sh[32];
+  __shared__ bool is_last;
+  double s[1] = {0.0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s[0] += d[i] * h[i];
+  block_sum_k<1>(s, sh);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 7] = s[0];
+    __threadfence();
+    is_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  s[0] = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s[0] += __ldcg(&partials[b * 7]);
+  block_sum_k<1>(s, sh);
+  if (threadIdx.x == 0) {
+    st->ticket = 0;
+    if (s[0] == 0.0) { st->state = 3; return; }
+    st->alpha = st->gh / s[0];
+  }
+}
+
+// x += alpha d ; g += alpha h ; res = |g| ; check ; beta = (g.Dg)/gh ; gh = g.Dg
+template <bool DIAG>
+__global__ void __launch_bounds__(kCgThreads) std_xg_kernel(CgState *st, double *__restrict__ x,
+                                                            double *__restrict__ g, const double *__restrict__ d,
+                                                            const double *__restrict__ h,
+                                                            const double *__restrict__ diag, long long n,
+                                                            double *partials, double *history) {
+  if (st->state != 0) return;
+  __shared__ double sh[2 * 32];
+  __shared__ bool is_last;
+  const double alpha = st->alpha;
+  double s[2] = {0.0, 0.0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] += alpha * d[i];
+    const double gn = g[i] + alpha * h[i];
+    g[i] = gn;
+    s[0] += gn * gn;
+    s[1] += gn * (DIAG ? diag[i] : 1.0) * gn;
+  }
+  block_sum_k<2>(s, sh);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 7] = s[0];
+    partials[blockIdx.x * 7 + 1] = s[1];
+    __threadfence();
+    is_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  s[0] = s[1] = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    s[0] += __ldcg(&partials[b * 7]);
+    s[1] += __ldcg(&partials[b * 7 + 1]);
+  }
+  block_sum_k<2>(s, sh);
+  if (threadIdx.x == 0) {
+    st->ticket = 0;
+    const int it = st->it + 1;
+    st->it = it;
+    const double res = sqrt(s[0]);
+    st->res = res;
+    if (history && it < st->history_len) history[it] = res;
+    const int conv = control_check(st->control, it, st->max_its, res, st->tol);
+    if (conv != 0) { st->state = conv; return; }
+    st->beta = s[1] / st->gh;
+    st->gh = s[1];
+  }
+}
+
+// d = beta d - D g
+template <bool DIAG>
+__global__ void std_d_kernel(const CgState *__restrict__ st, double *__restrict__ d, const double *__restrict__ g,
+                             const double *__restrict__ diag, long long n) {
+  if (st->state != 0) return;
+  const double beta = st->beta;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = beta * d[i] - (DIAG ? diag[i] : 1.0) * g[i];
+}
+
+static unsigned stream_grid(long long n, int sm_count) {
+  long long g = (n + 255) / 256;
+  const long long cap = (long long)sm_count * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+template <int MODE>
+static void launch_update(bool has_diag, unsigned grid, cudaStream_t s, const CgState *st, double *p, double *r,
+                          double *v, double *x, const double *diag, long long n) {
+  if (has_diag) cg_update_kernel<MODE, true><<<grid, 256, 0, s>>>(st, p, r, v, x, diag, n);
+  else cg_update_kernel<MODE, false><<<grid, 256, 0, s>>>(st, p, r, v, x, diag, n);
+}
+
+int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diagv, int variant, int control,
+             double tol, int max_its, int *last_step, double *last_value, double *history, int history_len) {
+  bp5_context_t ctx = op->ctx;
+  cudaStream_t s = ctx->stream;
+  const long long n = op->n_owned;
+  BP5_REQUIRE(x->n_owned == n && b->n_owned == n, "vector size does not match the operator");
+  BP5_REQUIRE(op->n_ghost == 0, "bp5_cg_solve handles a single block; partitioned meshes use the stepwise API");
+  BP5_REQUIRE(max_its >= 0, "max_its must be >= 0");
+  BP5_REQUIRE(variant == BP5_CG_MERGED || variant == BP5_CG_STANDARD, "unknown CG variant");
+  const double *diag = diagv ? diagv->d : nullptr;
+  const bool has_diag = diag != nullptr;
+  int rc;
+  // temporary vectors g, d, h (VectorMemory pool in the reference, solver.h:355-371); kept with the operator
+  if (!op->g) {
+    if ((rc = bp5_vector_create(ctx, op->n_owned, op->n_ghost, &op->g))) return rc;
+    if ((rc = bp5_vector_create(ctx, op->n_owned, op->n_ghost, &op->d))) return rc;
+    if ((rc = bp5_vector_create(ctx, op->n_owned, op->n_ghost, &op->h))) return rc;
+  }
+  double *g = op->g->d, *d = op->d->d, *h = op->h->d;
+  const int hist_len = history ? history_len : 0;
+  const size_t state_bytes = 256;
+  const size_t partial_bytes = sizeof(double) * kCgBlocks * 7;
+  const size_t need = state_bytes + partial_bytes + sizeof(double) * (hist_len > 0 ? hist_len : 1);
+  if (!op->cg_scalars || op->cg_scalars_bytes < need) {
+    if (op->cg_scalars) cudaFree(op->cg_scalars);
+    op->cg_scalars = nullptr;
+    BP5_CUDA(cudaMalloc(&op->cg_scalars, need));
+    op->cg_scalars_bytes = need;
+  }
+  CgState *st = reinterpret_cast<CgState *>(op->cg_scalars);
+  double *partials = reinterpret_cast<double *>(reinterpret_cast<char *>(op->cg_scalars) + state_bytes);
+  double *hist_dev = hist_len > 0 ? partials + kCgBlocks * 7 : nullptr;
+
+  // g = A x - b, or -b if x == 0 (solver.h:375-381)
+  int x_zero = 0;
+  if ((rc = vec_all_zero(ctx, x->d, n, &x_zero))) return rc;
+  if (!x_zero) {
+    BP5_CUDA(cudaMemsetAsync(g, 0, sizeof(double) * n, s));
+    if ((rc = apply_cell_loop(op, g, x->d))) return rc;
+    if ((rc = apply_copy_constrained(op, g, x->d))) return rc;
+    if ((rc = vec_axpy(ctx, g, 1.0, -1.0, b->d, n, 0))) return rc;
+  } else if ((rc = vec_axpy(ctx, g, 0.0, -1.0, b->d, n, 1)))
+    return rc;
+  double gg = 0.0;
+  if ((rc = vec_dot(ctx, g, g, n, &gg))) return rc;
+  double res = std::sqrt(gg);
+  if (history && history_len > 0) history[0] = res;
+
+  auto host_check = [&](int step, double value) {
+    if (control == BP5_CONTROL_ITERATION_NUMBER && step >= max_its) return 1;
+    if (value <= tol) return 1;
+    if (step >= max_its || std::isnan(value)) return 2;
+    return 0;
+  };
+  int conv = host_check(0, res);   // iteration_status(0, res_norm, x), solver.h:384
+  if (conv != 0) {
+    if (last_step) *last_step = 0;
+    if (last_value) *last_value = res;
+    if (conv == 2) { set_error("NoConvergence: step 0, residual %.17g", res); return BP5_ERR_NO_CONVERGENCE; }
+    return BP5_OK;
+  }
+
+  CgState init{};
+  init.tol = tol; init.res = res; init.max_its = max_its; init.control = control; init.history_len = hist_len;
+  const unsigned grid = stream_grid(n, ctx->sm_count);
+  if (variant == BP5_CG_STANDARD) {
+    if (has_diag) std_init_kernel<true><<<grid, 256, 0, s>>>(d, h, g, diag, n);
+    else std_init_kernel<false><<<grid, 256, 0, s>>>(d, h, g, diag, n);
+    BP5_CHECK_LAUNCH();
+    ctx->launches++;
+    double gh = 0.0;
+    if ((rc = vec_dot(ctx, g, h, n, &gh))) return rc;
+    init.gh = gh;
+  }
+  BP5_CUDA(cudaMemcpyAsync(st, &init, sizeof(CgState), cudaMemcpyHostToDevice, s));
+
+  // Iteration loop.  The host enqueues batches of iterations and looks at the
+  // state word of the batch before last, so the GPU never waits for the host.
+  constexpr int kBatch = 8;
+  volatile int *poll_host = reinterpret_cast<volatile int *>(ctx->scratch_host + 8);   // two slots
+  cudaEvent_t ev[2];
+  BP5_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  BP5_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  poll_host[0] = poll_host[1] = 0;
+  op->skip_flag = &st->state;
+  int it = 0, nbatch = 0;
+  bool done = false;
+  rc = BP5_OK;
+  while (!done && it < max_its && rc == BP5_OK) {
+    const int upto = std::min(max_its, it + kBatch);
+    for (; it < upto && rc == BP5_OK; ++it) {
+      const int cur = it + 1;
+      if (variant == BP5_CG_MERGED) {
+        // 1) update region (solver.h:413-448), with the parity-correct x update
+        if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x->d, diag, n);
+        else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x->d, diag, n);
+        else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, n);
+        ctx->launches++;
+        // 2) h = A d with do_zero_out = false (solver.h:475; h zeroed by the update kernel)
+        if ((rc = apply_cell_loop(op, h, d))) break;
+        if ((rc = apply_copy_constrained(op, h, d))) break;
+        // 3)+4) dots and scalars (solver.h:478-533)
+        if (has_diag) cg_dots_kernel<true><<<kCgBlocks, kCgThreads, 0, s>>>(st, d, g, h, diag, n, partials, hist_dev);
+        else cg_dots_kernel<false><<<kCgBlocks, kCgThreads, 0, s>>>(st, d, g, h, diag, n, partials, hist_dev);
+        ctx->launches++;
+      } else {
+        if (cudaMemsetAsync(h, 0, sizeof(double) * n, s) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
+        if ((rc = apply_cell_loop(op, h, d))) break;
+        if ((rc = apply_copy_constrained(op, h, d))) break;
+        std_dh_kernel<<<kCgBlocks, kCgThreads, 0, s>>>(st, d, h, n, partials);
+        if (has_diag) {
+          std_xg_kernel<true><<<kCgBlocks, kCgThreads, 0, s>>>(st, x->d, g, d, h, diag, n, partials, hist_dev);
+          std_d_kernel<true><<<grid, 256, 0, s>>>(st, d, g, diag, n);
+        } else {
+          std_xg_kernel<false><<<kCgBlocks, kCgThreads, 0, s>>>(st, x->d, g, d, h, diag, n, partials, hist_dev);
+          std_d_kernel<false><<<grid, 256, 0, s>>>(st, d, g, diag, n);
+        }
+        ctx->launches += 3;
+      }
+    }
+    if (rc != BP5_OK) break;
+    const int slot = nbatch & 1;
+    if (cudaMemcpyAsync((void *)&poll_host[slot], &st->state, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaEventRecord(ev[slot], s) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
+    if (nbatch >= 1) {
+      if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
+      if (poll_host[slot ^ 1] != 0) done = true;
+    }
+    ++nbatch;
+  }
+  op->skip_flag = nullptr;
+  if (rc == BP5_OK && variant == BP5_CG_MERGED) {
+    if (has_diag) cg_finish_kernel<true><<<grid, 256, 0, s>>>(st, x->d, d, g, diag, n);
+    else cg_finish_kernel<false><<<grid, 256, 0, s>>>(st, x->d, d, g, diag, n);
+    ctx->launches++;
+  }
+  CgState fin{};
+  cudaError_t e1 = cudaMemcpyAsync(&fin, st, sizeof(CgState), cudaMemcpyDeviceToHost, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  if (rc != BP5_OK) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("CG loop failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return BP5_ERR_CUDA;
+  }
+  BP5_CHECK_LAUNCH();
+  if (history && hist_len > 1) {
+    const int cnt = std::min(hist_len, fin.it + 1) - 1;
+    if (cnt > 0) BP5_CUDA(cudaMemcpy(history + 1, hist_dev + 1, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+  }
+  if (last_step) *last_step = fin.it;
+  if (last_value) *last_value = fin.res;
+  if (fin.state == 3) { set_error("ExcDivideByZero: d.Ad == 0 at iteration %d", fin.it); return BP5_ERR_DIVIDE_BY_ZERO; }
+  if (fin.state == 2) {
+    set_error("NoConvergence: step %d, residual %.17g", fin.it, fin.res);
+    return BP5_ERR_NO_CONVERGENCE;
+  }
+  if (fin.state != 1) { set_error("CG ended in unexpected state %d", fin.state); return BP5_ERR_INVALID; }
+  return BP5_OK;
+}
+
+}  // namespace bp5

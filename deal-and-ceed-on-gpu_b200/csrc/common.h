@@ -1,0 +1,146 @@
+// Internal types shared by the translation units of libbp5b200.so.
+// Product code: sm_100a only, no CPU fallback.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/bp5_b200.h"
+
+namespace bp5 {
+
+constexpr int kMaxDegree = 8;
+constexpr int kMaxN = kMaxDegree + 1;
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const char *fmt, ...);
+const char *get_error();
+
+#define BP5_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t err__ = (call);                                                         \
+    if (err__ != cudaSuccess) {                                                         \
+      ::bp5::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                       cudaGetErrorString(err__));                                      \
+      return BP5_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define BP5_CHECK_LAUNCH()                                                              \
+  do {                                                                                  \
+    cudaError_t err__ = cudaGetLastError();                                             \
+    if (err__ != cudaSuccess) {                                                         \
+      ::bp5::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,         \
+                       cudaGetErrorString(err__));                                      \
+      return BP5_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define BP5_REQUIRE(cond, msg)                                                          \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      ::bp5::set_error("%s (%s:%d)", msg, __FILE__, __LINE__);                          \
+      return BP5_ERR_INVALID;                                                           \
+    }                                                                                   \
+  } while (0)
+
+// ---- 1D tables (host) ------------------------------------------------------
+// n = p+1.  All matrices row-major [row*n + col].
+struct Tables1D {
+  int n;                       // POD: lives in __constant__ memory too
+  double xi[kMaxN];           // FE_Q support points: Gauss-Lobatto on [0,1]
+  double xq[kMaxN], wq[kMaxN]; // quadrature points / weights on [0,1]
+  double B[kMaxN * kMaxN];     // B[q][i]  = phi_i(xq_q)       (identity for GLL quadrature)
+  double Dg[kMaxN * kMaxN];    // Dg[q][i] = phi_i'(xq_q)
+  double Dt[kMaxN * kMaxN];    // Dt[q][r] = l_r'(xq_q), l_r = Lagrange basis through the QUADRATURE points
+};
+void make_tables(int degree, int quadrature, Tables1D &t);
+void gauss_rule01(int n, double *x, double *w);
+void lobatto_rule01(int n, double *x, double *w);
+void lagrange_eval(int n, const double *nodes, double x, double *val, double *der);
+
+// Shape tables as they travel to a kernel (by value, in the parameter constant
+// bank, so that fully unrolled loops read them as immediate constant operands).
+template <int N>
+struct ShapeTables {
+  double B[N * N];
+  double Dt[N * N];
+};
+
+// ---- handles ---------------------------------------------------------------
+}  // namespace bp5
+
+struct bp5_context_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  int64_t launches = 0;
+  double *scratch = nullptr;      // small device scratch for reductions
+  double *scratch_host = nullptr; // pinned
+};
+
+struct bp5_vector_s {
+  bp5_context_t ctx = nullptr;
+  int64_t n_owned = 0, n_ghost = 0;
+  double *d = nullptr;
+};
+
+struct bp5_operator_s {
+  bp5_context_t ctx = nullptr;
+  bp5_problem_t prob{};
+  bp5::Tables1D tab;
+  int p = 0, n = 0;
+  // this block
+  int lc[3] = {0, 0, 0};        // local cells per direction
+  int c0[3] = {0, 0, 0};        // first global cell
+  int ld[3] = {0, 0, 0};        // local dofs per direction (owned + lower ghost layer)
+  int has_lo[3] = {0, 0, 0};    // a lower neighbour owns the lower face
+  int has_hi[3] = {0, 0, 0};
+  int od[3] = {0, 0, 0};        // owned dofs per direction
+  int64_t n_owned = 0, n_ghost = 0, n_global = 0, n_cells = 0;
+  int64_t ghost_offset[8] = {0}; // start of ghost group m (1..7) relative to n_owned
+  int64_t ghost_size[8] = {0};
+  int cells_per_tile = 1;
+  int64_t n_tiles = 0;
+  int64_t tile_doubles = 0;     // metric doubles per tile (padded to a multiple of 2)
+  // device data
+  int *l2g = nullptr;           // [n_tiles*cpt][n^3] local dof index, x fastest
+  double *metric = nullptr;     // Poisson: [cell][6][n^3]; Helmholtz: [cell][7][n^3] (6 + a*JxW)
+  int metric_planes = 6;
+  int *constrained = nullptr;   // local owned indices of Dirichlet dofs
+  int64_t n_constrained = 0;
+  bool do_zero_out = true;
+  std::string kernel_name;
+  // CG work vectors (allocated on first solve)
+  bp5_vector_t g = nullptr, d = nullptr, h = nullptr;
+  bp5_vector_t xh = nullptr, bh = nullptr;  // device staging of bp5_cg_solve_host
+  double *cg_scalars = nullptr; // device
+  size_t cg_scalars_bytes = 0;
+  const int *skip_flag = nullptr; // device word: when non-zero the cell loop is a no-op (CG converged)
+};
+
+namespace bp5 {
+// setup.cu
+int operator_setup_device(bp5_operator_t op);
+int operator_assemble_rhs(bp5_operator_t op, double *b_dev);
+int operator_l2_norm_sqr(bp5_operator_t op, const double *u_dev, double *out);
+int operator_export_coefficients(bp5_operator_t op, double *host_out);
+int operator_export_coords(bp5_operator_t op, double *host_out);
+int operator_export_global_indices(bp5_operator_t op, int64_t *host_out);
+// apply.cu
+int apply_choose(bp5_operator_t op);                 // picks cells_per_tile + kernel name
+int apply_cell_loop(bp5_operator_t op, double *dst, const double *src);
+int apply_copy_constrained(bp5_operator_t op, double *dst, const double *src);
+// vector.cu
+int vec_fill(bp5_context_t ctx, double *d, int64_t n, double v);
+int vec_axpy(bp5_context_t ctx, double *y, double s, double a, const double *x, int64_t n, int mode);
+int vec_dot(bp5_context_t ctx, const double *x, const double *y, int64_t n, double *out);
+int vec_all_zero(bp5_context_t ctx, const double *x, int64_t n, int *out);
+// cg.cu
+int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int variant, int control,
+             double tol, int max_its, int *last_step, double *last_value, double *history, int history_len);
+}  // namespace bp5

@@ -1,0 +1,323 @@
+// Device-side setup of one mesh block: what the reference obtains from
+// CUDAWrappers::MatrixFree::reinit (bp5/step-64.cu:248) [UPSTREAM] and
+// evaluate_coefficients(JacobianFunctor) (bp5/step-64.cu:84-114, 256-258):
+//   local_to_global map, Jacobians of the MappingQGeneric(p) geometry at the
+//   quadrature points, the merged symmetric coefficient G = JxW J^-1 J^-T
+//   (planes xx,yy,zz,xy,xz,yz), the Dirichlet set, and the right-hand side of
+//   assemble_rhs (bp5/step-64.cu:372-418).
+// Everything is generated on the GPU from the analytic mesh description; no
+// O(n_dofs) host arrays are built except the Dirichlet index list.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.h"
+
+namespace bp5 {
+
+struct BlockGeom {
+  int n, p;
+  int lc[3], c0[3], gc[3];      // local cells, first global cell, global cells
+  int ld[3], hlo[3], od[3];     // local dofs/dir, lower-ghost flags, owned dofs/dir
+  long long n_owned;
+  long long goff[8];            // ghost group offsets (relative to n_owned)
+  double lo[3], L[3], h[3];     // domain corner, extent, cell size
+  int deform; double eps;
+  int planes;                   // 6 (Poisson) or 7 (Helmholtz)
+  int cpt; long long tile_doubles; // metric layout [tile][cpt][planes][n3], tile stride padded to 16 B
+};
+
+__constant__ Tables1D c_tab;
+
+__device__ __forceinline__ long long local_dof_index(const BlockGeom &g, int i, int j, int k) {
+  const int bx = i < g.hlo[0], by = j < g.hlo[1], bz = k < g.hlo[2];
+  if (!(bx | by | bz))
+    return (i - g.hlo[0]) + (long long)g.od[0] * ((j - g.hlo[1]) + (long long)g.od[1] * (k - g.hlo[2]));
+  const int m = bx | (by << 1) | (bz << 2);
+  const int e0 = bx ? 1 : g.od[0], e1 = by ? 1 : g.od[1];
+  const int q0 = bx ? 0 : i - g.hlo[0], q1 = by ? 0 : j - g.hlo[1], q2 = bz ? 0 : k - g.hlo[2];
+  return g.n_owned + g.goff[m] + q0 + (long long)e0 * (q1 + (long long)e1 * q2);
+}
+
+__device__ __forceinline__ void map_point(const BlockGeom &g, const double *x, double *y) {
+  if (g.deform == 0) { y[0] = x[0]; y[1] = x[1]; y[2] = x[2]; return; }
+  double s = 1.0;
+  for (int d = 0; d < 3; ++d) s *= sin(M_PI * (x[d] - g.lo[d]) / g.L[d]);
+  for (int d = 0; d < 3; ++d) y[d] = x[d] + g.eps * g.L[d] * s;
+}
+
+// Jacobian of the degree-p mapping at the n^3 points of a 1D rule given by the
+// matrices Bm (values) / Dm (derivatives) [q][i]: three sum-factorised passes
+// per coordinate.  One thread per point.  smem: X[3][n3] + 5 work arrays.
+// On return J[d][e] and xr[d] hold this thread's point.
+__device__ void cell_jacobian(const BlockGeom &g, const double *Bm, const double *Dm, double *sm, int cx, int cy,
+                              int cz, double J[3][3], double xr[3]) {
+  const int n = g.n, n2 = n * n, n3 = n2 * n;
+  const int t = threadIdx.x;
+  const int i = t % n, j = (t / n) % n, k = t / n2;
+  double *X = sm, *tD = sm + 3 * n3, *tB = tD + n3, *tDB = tB + n3, *tBD = tDB + n3, *tBB = tBD + n3;
+  if (t < n3) {
+    const int c[3] = {cx, cy, cz};
+    const int loc[3] = {i, j, k};
+    double x[3], y[3];
+    for (int d = 0; d < 3; ++d) x[d] = g.lo[d] + g.h[d] * (c[d] + c_tab.xi[loc[d]]);
+    map_point(g, x, y);
+    for (int d = 0; d < 3; ++d) X[d * n3 + t] = y[d];
+  }
+  __syncthreads();
+  for (int d = 0; d < 3; ++d) {
+    if (t < n3) {
+      double sD = 0.0, sB = 0.0;
+      for (int m = 0; m < n; ++m) {
+        const double v = X[d * n3 + (k * n + j) * n + m];
+        sD += Dm[i * n + m] * v; sB += Bm[i * n + m] * v;
+      }
+      tD[t] = sD; tB[t] = sB;
+    }
+    __syncthreads();
+    if (t < n3) {
+      double sDB = 0.0, sBD = 0.0, sBB = 0.0;
+      for (int m = 0; m < n; ++m) {
+        const double vD = tD[(k * n + m) * n + i], vB = tB[(k * n + m) * n + i];
+        sDB += Bm[j * n + m] * vD; sBD += Dm[j * n + m] * vB; sBB += Bm[j * n + m] * vB;
+      }
+      tDB[t] = sDB; tBD[t] = sBD; tBB[t] = sBB;
+    }
+    __syncthreads();
+    if (t < n3) {
+      double j0 = 0.0, j1 = 0.0, j2 = 0.0, xv = 0.0;
+      for (int m = 0; m < n; ++m) {
+        const int a = (m * n + j) * n + i;
+        j0 += Bm[k * n + m] * tDB[a]; j1 += Bm[k * n + m] * tBD[a];
+        j2 += Dm[k * n + m] * tBB[a]; xv += Bm[k * n + m] * tBB[a];
+      }
+      J[d][0] = j0; J[d][1] = j1; J[d][2] = j2; xr[d] = xv;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ double det3(const double J[3][3]) {
+  return J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+         J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+}
+
+// One block per local cell.  Writes l2g[cell][n3] and metric[cell][planes][n3].
+__global__ void setup_cells_kernel(BlockGeom g, int *__restrict__ l2g, double *__restrict__ metric) {
+  extern __shared__ double sm[];
+  const int n = g.n, n2 = n * n, n3 = n2 * n;
+  const long long cell = blockIdx.x;
+  const int lcx = cell % g.lc[0], lcy = (cell / g.lc[0]) % g.lc[1], lcz = cell / ((long long)g.lc[0] * g.lc[1]);
+  const int t = threadIdx.x;
+  const int i = t % n, j = (t / n) % n, k = t / n2;
+  if (t < n3)
+    l2g[cell * n3 + t] = (int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
+  double J[3][3], xr[3];
+  cell_jacobian(g, c_tab.B, c_tab.Dg, sm, g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz, J, xr);
+  if (t >= n3) return;
+  const double det = det3(J);
+  const double id = 1.0 / det;
+  double I[3][3];   // I[d][f] = d xi_d / d x_f
+  I[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * id;
+  I[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+  I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+  I[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * id;
+  I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+  I[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+  I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * id;
+  I[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+  I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+  const double jxw = det * c_tab.wq[i] * c_tab.wq[j] * c_tab.wq[k];
+  // JacobianFunctor, bp5/step-64.cu:98-113
+  double G[6];
+  int pl = 3;
+  for (int d = 0; d < 3; ++d) {
+    G[d] = jxw * (I[d][0] * I[d][0] + I[d][1] * I[d][1] + I[d][2] * I[d][2]);
+    for (int e = d + 1; e < 3; ++e, ++pl) G[pl] = jxw * (I[d][0] * I[e][0] + I[d][1] * I[e][1] + I[d][2] * I[e][2]);
+  }
+  double *out = metric + (cell / g.cpt) * g.tile_doubles + (cell % g.cpt) * (long long)g.planes * n3 + t;
+  for (int c = 0; c < 6; ++c) out[(long long)c * n3] = G[c];
+  if (g.planes == 7) {
+    // VaryingCoefficientFunctor (step-64/step-64.cu:100-118) times JxW (submit_value,
+    // bp5/fe_evaluation_gl.h:297-300)
+    const double p2 = xr[0] * xr[0] + xr[1] * xr[1] + xr[2] * xr[2];
+    out[6LL * n3] = 10.0 / (0.05 + 2.0 * p2) * jxw;
+  }
+}
+
+// Right-hand side b_i = int phi_i * 1 with QGauss(p+1) (c_tab must hold the
+// GAUSS tables).  Loops over the local cells plus one halo layer of cells above
+// each upper face that has a neighbour, and adds only into OWNED dofs, so no
+// ghost exchange is needed.  Dirichlet rows stay zero.
+__global__ void rhs_kernel(BlockGeom g, int ex, int ey, int ez, double *__restrict__ b) {
+  extern __shared__ double sm[];
+  const int n = g.n, n2 = n * n, n3 = n2 * n;
+  const long long cell = blockIdx.x;
+  const int lcx = cell % ex, lcy = (cell / ex) % ey, lcz = cell / ((long long)ex * ey);
+  const int t = threadIdx.x;
+  const int i = t % n, j = (t / n) % n, k = t / n2;
+  double J[3][3], xr[3];
+  cell_jacobian(g, c_tab.B, c_tab.Dg, sm, g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz, J, xr);
+  double *w0 = sm, *w1 = sm + n3;
+  if (t < n3) w0[t] = det3(J) * c_tab.wq[i] * c_tab.wq[j] * c_tab.wq[k];
+  __syncthreads();
+  // v_i = sum_q B[q][i] w_q, three transposed passes
+  if (t < n3) { double s = 0; for (int m = 0; m < n; ++m) s += c_tab.B[m * n + i] * w0[(k * n + j) * n + m]; w1[t] = s; }
+  __syncthreads();
+  if (t < n3) { double s = 0; for (int m = 0; m < n; ++m) s += c_tab.B[m * n + j] * w1[(k * n + m) * n + i]; w0[t] = s; }
+  __syncthreads();
+  if (t < n3) {
+    double s = 0; for (int m = 0; m < n; ++m) s += c_tab.B[m * n + k] * w0[(m * n + j) * n + i];
+    const int li = lcx * g.p + i, lj = lcy * g.p + j, lk = lcz * g.p + k;   // local dof coords (may exceed ld)
+    const int gi = g.c0[0] * g.p + li, gj = g.c0[1] * g.p + lj, gk = g.c0[2] * g.p + lk;
+    const bool owned = li >= g.hlo[0] && lj >= g.hlo[1] && lk >= g.hlo[2] && li < g.ld[0] && lj < g.ld[1] && lk < g.ld[2];
+    const bool bdry = gi == 0 || gj == 0 || gk == 0 || gi == g.gc[0] * g.p || gj == g.gc[1] * g.p || gk == g.gc[2] * g.p;
+    if (owned && !bdry) atomicAdd(&b[local_dof_index(g, li, lj, lk)], s);
+  }
+}
+
+// coordinates + global lexicographic index of every local dof (owned, then ghost)
+__global__ void dof_info_kernel(BlockGeom g, double *__restrict__ xyz, long long *__restrict__ gidx) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long tot = (long long)g.ld[0] * g.ld[1] * g.ld[2];
+  if (t >= tot) return;
+  const int i = t % g.ld[0], j = (t / g.ld[0]) % g.ld[1], k = t / ((long long)g.ld[0] * g.ld[1]);
+  const long long li = local_dof_index(g, i, j, k);
+  const int loc[3] = {i, j, k};
+  double x[3], y[3];
+  long long gl[3];
+  for (int d = 0; d < 3; ++d) {
+    int c = loc[d] / g.p, l = loc[d] % g.p;
+    if (c == g.lc[d]) { c -= 1; l = g.p; }
+    x[d] = g.lo[d] + g.h[d] * (g.c0[d] + c + c_tab.xi[l]);
+    gl[d] = (long long)g.c0[d] * g.p + loc[d];
+  }
+  map_point(g, x, y);
+  if (xyz) { xyz[3 * li] = y[0]; xyz[3 * li + 1] = y[1]; xyz[3 * li + 2] = y[2]; }
+  if (gidx) gidx[li] = gl[0] + ((long long)g.gc[0] * g.p + 1) * (gl[1] + ((long long)g.gc[1] * g.p + 1) * gl[2]);
+}
+
+static BlockGeom make_geom(bp5_operator_t op) {
+  BlockGeom g{};
+  g.n = op->n; g.p = op->p;
+  for (int d = 0; d < 3; ++d) {
+    g.lc[d] = op->lc[d]; g.c0[d] = op->c0[d]; g.gc[d] = op->prob.cells[d];
+    g.ld[d] = op->ld[d]; g.hlo[d] = op->has_lo[d]; g.od[d] = op->od[d];
+    g.lo[d] = op->prob.lower[d]; g.L[d] = op->prob.upper[d] - op->prob.lower[d];
+    g.h[d] = g.L[d] / op->prob.cells[d];
+  }
+  g.n_owned = op->n_owned;
+  for (int m = 0; m < 8; ++m) g.goff[m] = op->ghost_offset[m];
+  g.deform = op->prob.deformation; g.eps = op->prob.deformation_eps;
+  g.planes = op->metric_planes;
+  g.cpt = op->cells_per_tile;
+  g.tile_doubles = op->tile_doubles;
+  return g;
+}
+
+int operator_setup_device(bp5_operator_t op) {
+  bp5_context_t ctx = op->ctx;
+  const int n = op->n, n3 = n * n * n;
+  const BlockGeom g = make_geom(op);
+  const int64_t padded_cells = op->n_tiles * op->cells_per_tile;
+  BP5_CUDA(cudaMalloc(&op->l2g, sizeof(int) * padded_cells * n3));
+  BP5_CUDA(cudaMemsetAsync(op->l2g, 0, sizeof(int) * padded_cells * n3, ctx->stream));
+  const size_t mbytes = sizeof(double) * op->n_tiles * op->tile_doubles;
+  BP5_CUDA(cudaMalloc(&op->metric, mbytes));
+  BP5_CUDA(cudaMemsetAsync(op->metric, 0, mbytes, ctx->stream));
+  BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = ((n3 + 31) / 32) * 32;
+  const size_t smem = sizeof(double) * 8 * n3;
+  setup_cells_kernel<<<(unsigned)op->n_cells, threads, smem, ctx->stream>>>(g, op->l2g, op->metric);
+  BP5_CHECK_LAUNCH();
+  ctx->launches++;
+
+  // Dirichlet set: owned dofs on the global boundary (boundary id 0 = whole
+  // boundary, bp5/step-64.cu:354-357), ascending local index.
+  std::vector<int> cons;
+  const long long G[3] = {(long long)op->prob.cells[0] * op->p, (long long)op->prob.cells[1] * op->p,
+                          (long long)op->prob.cells[2] * op->p};
+  for (int k = op->has_lo[2]; k < op->ld[2]; ++k) {
+    const long long gk = (long long)op->c0[2] * op->p + k;
+    for (int j = op->has_lo[1]; j < op->ld[1]; ++j) {
+      const long long gj = (long long)op->c0[1] * op->p + j;
+      const bool plane_b = gk == 0 || gk == G[2] || gj == 0 || gj == G[1];
+      const long long row = (long long)op->od[0] * ((j - op->has_lo[1]) + (long long)op->od[1] * (k - op->has_lo[2]));
+      if (plane_b) {
+        for (int i = op->has_lo[0]; i < op->ld[0]; ++i) cons.push_back((int)(row + i - op->has_lo[0]));
+      } else {
+        if (op->c0[0] == 0 && !op->has_lo[0]) cons.push_back((int)row);
+        if ((long long)op->c0[0] * op->p + op->ld[0] - 1 == G[0]) cons.push_back((int)(row + op->od[0] - 1));
+      }
+    }
+  }
+  op->n_constrained = (int64_t)cons.size();
+  if (!cons.empty()) {
+    BP5_CUDA(cudaMalloc(&op->constrained, sizeof(int) * cons.size()));
+    BP5_CUDA(cudaMemcpyAsync(op->constrained, cons.data(), sizeof(int) * cons.size(), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BP5_OK;
+}
+
+int operator_assemble_rhs(bp5_operator_t op, double *b_dev) {
+  bp5_context_t ctx = op->ctx;
+  const int n = op->n, n3 = n * n * n;
+  const BlockGeom g = make_geom(op);
+  Tables1D tg;
+  make_tables(op->p, BP5_QUAD_GAUSS, tg);   // the reference always assembles with QGauss(p+1), step-64.cu:380
+  BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &tg, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(b_dev, 0, sizeof(double) * (op->n_owned + op->n_ghost), ctx->stream));
+  const int ex = op->lc[0] + op->has_hi[0], ey = op->lc[1] + op->has_hi[1], ez = op->lc[2] + op->has_hi[2];
+  const int threads = ((n3 + 31) / 32) * 32;
+  rhs_kernel<<<(unsigned)((long long)ex * ey * ez), threads, sizeof(double) * 8 * n3, ctx->stream>>>(g, ex, ey, ez, b_dev);
+  BP5_CHECK_LAUNCH();
+  ctx->launches++;
+  // restore the operator's own tables for later setup calls
+  BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BP5_OK;
+}
+
+int operator_export_coefficients(bp5_operator_t op, double *host_out) {
+  // internal layout [cell][plane][q] -> reference layout coef[plane][cell][q]
+  // (bp5/step-64.cu:108,112), first 6 planes.
+  const int n3 = op->n * op->n * op->n;
+  const int P = op->metric_planes;
+  std::vector<double> tmp((size_t)op->n_tiles * op->tile_doubles);
+  BP5_CUDA(cudaMemcpy(tmp.data(), op->metric, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+  for (int64_t c = 0; c < op->n_cells; ++c) {
+    const size_t base = (size_t)(c / op->cells_per_tile) * op->tile_doubles + (size_t)(c % op->cells_per_tile) * P * n3;
+    for (int pl = 0; pl < 6; ++pl)
+      std::copy_n(&tmp[base + (size_t)pl * n3], n3, &host_out[((size_t)pl * op->n_cells + c) * n3]);
+  }
+  return BP5_OK;
+}
+
+static int dof_info(bp5_operator_t op, double *xyz_host, int64_t *gidx_host) {
+  bp5_context_t ctx = op->ctx;
+  const BlockGeom g = make_geom(op);
+  const int64_t nloc = op->n_owned + op->n_ghost;
+  double *xyz = nullptr; long long *gi = nullptr;
+  if (xyz_host) BP5_CUDA(cudaMalloc(&xyz, sizeof(double) * 3 * nloc));
+  if (gidx_host) BP5_CUDA(cudaMalloc(&gi, sizeof(long long) * nloc));
+  BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  const long long tot = (long long)op->ld[0] * op->ld[1] * op->ld[2];
+  dof_info_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(g, xyz, gi);
+  BP5_CHECK_LAUNCH();
+  ctx->launches++;
+  if (xyz_host) BP5_CUDA(cudaMemcpyAsync(xyz_host, xyz, sizeof(double) * 3 * nloc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (gidx_host) BP5_CUDA(cudaMemcpyAsync(gidx_host, gi, sizeof(long long) * nloc, cudaMemcpyDeviceToHost, ctx->stream));
+  BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(xyz); cudaFree(gi);
+  return BP5_OK;
+}
+int operator_export_coords(bp5_operator_t op, double *host_out) { return dof_info(op, host_out, nullptr); }
+int operator_export_global_indices(bp5_operator_t op, int64_t *host_out) { return dof_info(op, nullptr, host_out); }
+
+int operator_l2_norm_sqr(bp5_operator_t, const double *, double *) {
+  set_error("l2 norm with QGauss(p+2) not implemented yet");
+  return BP5_ERR_UNSUPPORTED;
+}
+
+}  // namespace bp5

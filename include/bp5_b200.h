@@ -1,0 +1,173 @@
+/* bp5_b200.h -- C ABI of the B200-native BP5 / step-64 hot path.
+ *
+ * This is the drop-in boundary: a plain C interface (opaque handles, plain
+ * pointers and sizes, int status codes, no C++/torch types) that a host
+ * program written against the reference's deal.II-style classes binds to.
+ * The header-only C++ facade in include/dealii_b200/ re-creates those classes
+ * (PoissonOperator, MatrixFree, distributed::Vector, SolverCGFullMerge,
+ * SolverControl ...) on top of it; INTEGRATION.md shows the binding.
+ *
+ * Every entry point names the reference interface it replaces (file:line in
+ * peterrum/deal-and-ceed-on-gpu).  [UPSTREAM] marks deal.II members that the
+ * reference calls but does not vendor.
+ *
+ * Conventions
+ *   - every function returns BP5_OK (0) or an error code; bp5_last_error()
+ *     gives the message for the calling thread.  No exception crosses the ABI.
+ *   - the caller owns handles and frees them with the matching *_destroy.
+ *   - all device work is enqueued on the context's stream; functions that
+ *     return a value to the host synchronise that stream, the others do not.
+ *   - vectors are [owned | ghost] contiguous in device memory
+ *     (LinearAlgebra::distributed::Vector semantics).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with BP5_ERR_CUDA.
+ */
+#ifndef BP5_B200_H
+#define BP5_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bp5_context_s *bp5_context_t;
+typedef struct bp5_operator_s *bp5_operator_t;
+typedef struct bp5_vector_s *bp5_vector_t;
+
+enum bp5_status {
+  BP5_OK = 0,
+  BP5_ERR_INVALID = 1,        /* bad argument / handle */
+  BP5_ERR_CUDA = 2,           /* CUDA runtime error (message in bp5_last_error) */
+  BP5_ERR_NO_CONVERGENCE = 3, /* SolverControl::NoConvergence, bp5/solver.h:540 */
+  BP5_ERR_DIVIDE_BY_ZERO = 4, /* ExcDivideByZero, bp5/solver.h:501 */
+  BP5_ERR_UNSUPPORTED = 5
+};
+
+enum { BP5_QUAD_GAUSS = 0, BP5_QUAD_GLL = 1 };     /* bp5/step-64.cu:243-247 (COLLOCATION) */
+enum { BP5_OP_POISSON = 0, BP5_OP_HELMHOLTZ = 1 }; /* bp5/step-64.cu:147 ; step-64/step-64.cu:201 */
+enum { BP5_GEOM_STORED = 0, BP5_GEOM_ON_THE_FLY = 1 };
+enum { BP5_CONTROL_ITERATION_NUMBER = 0, /* IterationNumberControl, bp5/step-64.cu:443 */
+       BP5_CONTROL_SOLVER = 1 };         /* SolverControl, step-64/step-64.cu:513 */
+enum { BP5_CG_STANDARD = 0,              /* dealii::SolverCG ("pcg-standard"), bp5/step-64.cu:446 */
+       BP5_CG_MERGED = 1 };              /* SolverCGFullMerge ("pcg-merged"), bp5/solver.h:343 */
+
+/* What the reference builds from GridGenerator::subdivided_hyper_rectangle +
+ * refine_global + DoFHandler/FE_Q + MappingQGeneric + QGauss + zero Dirichlet
+ * constraints (bp5/step-64.cu:228-259, 341-368, 656-663): a structured hex
+ * mesh, optionally smoothly deformed, optionally one block of a Cartesian
+ * partition (one block per GPU, replacing the p4est partition). */
+typedef struct bp5_problem {
+  int32_t degree;          /* fe_degree p, 1..8 */
+  int32_t quadrature;      /* BP5_QUAD_* with p+1 points per direction */
+  int32_t operator_kind;   /* BP5_OP_* */
+  int32_t geometry_mode;   /* BP5_GEOM_* */
+  int32_t cells[3];        /* global number of cells per direction */
+  double lower[3];         /* domain corner */
+  double upper[3];
+  int32_t deformation;     /* 0 none; 1: x -> x + eps*L*prod_d sin(pi (x_d-lo_d)/L_d) */
+  double deformation_eps;
+  int32_t part_grid[3];    /* process grid (1,1,1 for one GPU) */
+  int32_t part_coord[3];   /* this block's coordinates in the grid */
+  int32_t reserved[8];     /* must be zero */
+} bp5_problem_t;
+
+/* ---- context ---------------------------------------------------------- */
+/* replaces print_hardware_specs()/cudaSetDevice, bp5/step-64.cu:683-709 */
+int bp5_context_create(int device, bp5_context_t *ctx);
+int bp5_context_destroy(bp5_context_t ctx);
+int bp5_context_synchronize(bp5_context_t ctx);
+/* raw cudaStream_t of the context (for callers that interleave their own work) */
+void *bp5_context_stream(bp5_context_t ctx);
+const char *bp5_last_error(void);
+const char *bp5_version(void);
+
+/* ---- operator: PoissonOperator / HelmholtzOperator --------------------- */
+/* ctor: PoissonOperator(dof_handler, constraints) bp5/step-64.cu:228-259
+ * (MatrixFree::reinit :248, evaluate_coefficients(JacobianFunctor) :256-258);
+ * HelmholtzOperator ctor step-64/step-64.cu:276-302. */
+int bp5_operator_create(bp5_context_t ctx, const bp5_problem_t *problem, bp5_operator_t *op);
+int bp5_operator_destroy(bp5_operator_t op);
+/* sizes of a vector this operator works on: locally owned, ghost, global */
+int bp5_operator_sizes(bp5_operator_t op, int64_t *n_owned, int64_t *n_ghost, int64_t *n_global,
+                       int64_t *n_local_cells);
+/* initialize_dof_vector, bp5/step-64.cu:210-215 */
+int bp5_operator_initialize_dof_vector(bp5_operator_t op, bp5_vector_t *vec);
+/* public member do_zero_out, bp5/step-64.cu:223 */
+int bp5_operator_set_zero_out(bp5_operator_t op, int do_zero_out);
+/* vmult(dst, src), bp5/step-64.cu:263-276: optional dst=0, cell loop
+ * (ghost update, kernel, compress), copy_constrained_values. */
+int bp5_operator_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src);
+/* the two halves of vmult separately [UPSTREAM MatrixFree::cell_loop /
+ * copy_constrained_values], called at bp5/step-64.cu:274-275 */
+int bp5_operator_cell_loop(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src);
+int bp5_operator_copy_constrained_values(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src);
+/* raw device pointers, single block only (no ghosts): dst[n], src[n] */
+int bp5_operator_vmult_ptr(bp5_operator_t op, double *dst_dev, const double *src_dev, int zero_dst);
+/* assemble_rhs, bp5/step-64.cu:372-418: b_i = int phi_i, QGauss(p+1),
+ * constrained rows zero; written to the owned range of b. */
+int bp5_operator_assemble_rhs(bp5_operator_t op, bp5_vector_t b);
+/* the merged coefficient in the REFERENCE layout coef[plane][cell][q],
+ * planes xx,yy,zz,xy,xz,yz (bp5/step-64.cu:107-113), cells in this block's
+ * lexicographic order, copied to host (for inspection/parity). 6*cells*n^3 doubles. */
+int bp5_operator_export_coefficients(bp5_operator_t op, double *host_out);
+/* coordinates (x,y,z) of the locally owned + ghost DoFs, host, 3 doubles each */
+int bp5_operator_export_dof_coordinates(bp5_operator_t op, double *host_out);
+/* global lexicographic index of each local (owned, then ghost) DoF, host */
+int bp5_operator_export_global_indices(bp5_operator_t op, int64_t *host_out);
+/* ||u||_L2 with QGauss(p+2), this block's contribution squared
+ * (output_results, bp5/step-64.cu:604-615) */
+int bp5_operator_l2_norm_sqr(bp5_operator_t op, bp5_vector_t u, double *out);
+/* algorithmic bytes of one vmult over this block (16 + 48 r per DoF) */
+int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *bytes_per_vmult, double *bytes_per_cg_it);
+/* name of the hand-written kernel variant chosen for this operator */
+const char *bp5_operator_kernel_name(bp5_operator_t op);
+/* number of kernels this library has launched on the context since creation */
+int64_t bp5_context_launch_count(bp5_context_t ctx);
+
+/* ---- vector: LinearAlgebra::distributed::Vector<double, CUDA> ---------- */
+/* [UPSTREAM] used at bp5/step-64.cu:321-323,349,363-367 ; solver.h:369-382 */
+int bp5_vector_create(bp5_context_t ctx, int64_t n_owned, int64_t n_ghost, bp5_vector_t *vec);
+int bp5_vector_create_like(bp5_vector_t other, bp5_vector_t *vec); /* reinit(other) */
+int bp5_vector_destroy(bp5_vector_t vec);
+int bp5_vector_local_size(bp5_vector_t vec, int64_t *n_owned, int64_t *n_ghost);
+double *bp5_vector_get_values(bp5_vector_t vec);                   /* get_values(): device pointer */
+int bp5_vector_set(bp5_vector_t vec, double value);                /* operator=(double): owned and ghost */
+int bp5_vector_import_host(bp5_vector_t vec, const double *host, int64_t n); /* import(rw, insert) */
+int bp5_vector_export_host(bp5_vector_t vec, double *host, int64_t n);
+int bp5_vector_copy(bp5_vector_t dst, bp5_vector_t src);
+int bp5_vector_add(bp5_vector_t y, double a, bp5_vector_t x);      /* y.add(a, x) */
+int bp5_vector_equ(bp5_vector_t y, double a, bp5_vector_t x);      /* y.equ(a, x) */
+int bp5_vector_sadd(bp5_vector_t y, double s, double a, bp5_vector_t x); /* y = s*y + a*x */
+/* local (this block's owned range) parts of the reductions; the caller sums
+ * over blocks (MPI_Allreduce in the reference, bp5/solver.h:493) */
+int bp5_vector_dot_local(bp5_vector_t x, bp5_vector_t y, double *out);
+int bp5_vector_norm_sqr_local(bp5_vector_t x, double *out);        /* l2_norm()^2 */
+int bp5_vector_all_zero_local(bp5_vector_t x, int *out);           /* all_zero() */
+int bp5_vector_zero_out_ghosts(bp5_vector_t vec);                  /* zero_out_ghosts() */
+
+/* ---- solver ------------------------------------------------------------ */
+/* SolverCGFullMerge::solve(A, x, b, preconditioner) bp5/solver.h:343-542 and
+ * dealii::SolverCG::solve as used at bp5/step-64.cu:446-453.
+ *   diag          DiagonalMatrix::get_vector() (solver.h:421) or NULL for the
+ *                 identity (the reference passes a vector of ones, step-64.cu:432)
+ *   tol           absolute tolerance on the residual l2 norm
+ *   control       BP5_CONTROL_*; max_its its step limit
+ *   last_step     SolverControl::last_step(); last_value its last_value()
+ *   history       optional host array, history[it] = residual after it iterations
+ * returns BP5_OK, BP5_ERR_NO_CONVERGENCE (x holds the last iterate) or an error.
+ * Single block only; multi-block solves go through bp5_cg_* stepwise API below
+ * driven by the host that owns the communicator. */
+int bp5_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int variant,
+                 int control, double tol, int max_its, int *last_step, double *last_value,
+                 double *history, int history_len);
+/* same, with HOST buffers: copies b (and x0) to the device, solves, copies x
+ * back -- the end-to-end entry point a host-side caller uses. */
+int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, int64_t n, int variant,
+                      int control, double tol, int max_its, int *last_step, double *last_value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BP5_B200_H */
