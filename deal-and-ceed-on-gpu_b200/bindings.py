@@ -74,6 +74,8 @@ ABI = [
     ("bp5_operator_export_global_indices", C.c_int, [_vp, C.POINTER(C.c_int64)]),
     ("bp5_operator_l2_norm_sqr", C.c_int, [_vp, _vp, _dp]),
     ("bp5_operator_algorithmic_bytes", C.c_int, [_vp, _dp, _dp]),
+    ("bp5_operator_profile", C.c_int, [_vp, C.c_int]),
+    ("bp5_operator_profile_result", C.c_int, [_vp, C.POINTER(C.c_int64), _dp]),
     ("bp5_operator_kernel_name", C.c_char_p, [_vp]),
     ("bp5_context_launch_count", C.c_int64, [_vp]),
     ("bp5_vector_create", C.c_int, [_vp, C.c_int64, C.c_int64, C.POINTER(_vp)]),
@@ -292,6 +294,14 @@ class PoissonOperator:
         a, b = C.c_double(), C.c_double()
         _check(lib().bp5_operator_algorithmic_bytes(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def profile(self, enable=True):
+        _check(lib().bp5_operator_profile(self.h, int(enable)))
+
+    def profile_result(self):
+        n, ms = C.c_int64(), C.c_double()
+        _check(lib().bp5_operator_profile_result(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
 
     @property
     def kernel_name(self):

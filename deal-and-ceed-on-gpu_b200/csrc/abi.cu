@@ -157,6 +157,7 @@ int bp5_operator_destroy(bp5_operator_t op) {
   cudaFree(op->metric);
   cudaFree(op->constrained);
   cudaFree(op->cg_scalars);
+  for (cudaEvent_t e : op->prof_events) cudaEventDestroy(e);
   bp5_vector_destroy(op->g);
   bp5_vector_destroy(op->d);
   bp5_vector_destroy(op->h);
@@ -293,6 +294,29 @@ int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *per_vmult, double 
   const double metric = 8.0 * op->metric_planes * n3 * (double)op->n_cells;
   if (per_vmult) *per_vmult = 16.0 * (double)op->n_owned + metric;
   if (per_cg_it) *per_cg_it = 72.0 * (double)op->n_owned + metric;
+  return BP5_OK;
+}
+
+int bp5_operator_profile(bp5_operator_t op, int enable) {
+  BP5_REQUIRE(op, "null operator");
+  op->profile = enable != 0;
+  op->prof_used = 0;
+  return BP5_OK;
+}
+
+int bp5_operator_profile_result(bp5_operator_t op, int64_t *launches, double *total_ms) {
+  BP5_REQUIRE(op && launches && total_ms, "null argument");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  BP5_CUDA(cudaStreamSynchronize(op->ctx->stream));
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < op->prof_used; i += 2) {
+    float t = 0.f;
+    BP5_CUDA(cudaEventElapsedTime(&t, op->prof_events[i], op->prof_events[i + 1]));
+    ms += t;
+  }
+  *launches = (int64_t)(op->prof_used / 2);
+  *total_ms = ms;
+  op->prof_used = 0;
   return BP5_OK;
 }
 

@@ -67,8 +67,17 @@ static int launch(bp5_operator_t op, double *dst, const double *src) {
   long long grid = (long long)blocks_per_sm * op->ctx->sm_count;
   if (grid > op->n_tiles) grid = op->n_tiles;
   if (grid < 1) grid = 1;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (op->profile) {
+    if (op->prof_used + 2 > op->prof_events.size()) {
+      for (int i = 0; i < 64; ++i) { cudaEvent_t e; BP5_CUDA(cudaEventCreate(&e)); op->prof_events.push_back(e); }
+    }
+    e0 = op->prof_events[op->prof_used++]; e1 = op->prof_events[op->prof_used++];
+    BP5_CUDA(cudaEventRecord(e0, op->ctx->stream));
+  }
   kernel<<<(unsigned)grid, Cfg::NT, Cfg::SMEM_BYTES, op->ctx->stream>>>(prm);
   BP5_CHECK_LAUNCH();
+  if (e1) BP5_CUDA(cudaEventRecord(e1, op->ctx->stream));
   op->ctx->launches++;
   return BP5_OK;
 }

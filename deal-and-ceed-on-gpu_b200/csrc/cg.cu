@@ -150,7 +150,9 @@ __global__ void __launch_bounds__(kCgThreads) cg_dots_kernel(CgState *st, const 
     st->it = it;
     if (rr[0] == 0.0) { st->state = 3; return; }                 // ExcDivideByZero, solver.h:501
     const double alpha = rr[6] / rr[0];                         // solver.h:502
-    const double res = sqrt(rr[3] + 2 * alpha * rr[2] + alpha * alpha * rr[1]);   // solver.h:504-505
+    // solver.h:504-505; clamped at 0 (deviation): at exact convergence the three-term
+    // expression can round slightly negative and the unguarded sqrt would report NaN.
+    const double res = sqrt(fmax(0.0, rr[3] + 2 * alpha * rr[2] + alpha * alpha * rr[1]));
     st->alpha = alpha;
     st->res = res;
     if (history && it < st->history_len) history[it] = res;

@@ -120,6 +120,10 @@ struct bp5_operator_s {
   bp5_vector_t xh = nullptr, bh = nullptr;  // device staging of bp5_cg_solve_host
   double *cg_scalars = nullptr; // device
   size_t cg_scalars_bytes = 0;
+  // live per-launch timing of the cell kernel (bench.py roofline): events around every launch
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;   // start/stop pairs
+  size_t prof_used = 0;
   const int *skip_flag = nullptr; // device word: when non-zero the cell loop is a no-op (CG converged)
 };
 

@@ -121,6 +121,12 @@ int bp5_operator_export_global_indices(bp5_operator_t op, int64_t *host_out);
 int bp5_operator_l2_norm_sqr(bp5_operator_t op, bp5_vector_t u, double *out);
 /* algorithmic bytes of one vmult over this block (16 + 48 r per DoF) */
 int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *bytes_per_vmult, double *bytes_per_cg_it);
+/* live timing of the cell kernel: when enabled, every launch of the hot kernel
+ * is bracketed by CUDA events on the context's stream; profile_result
+ * synchronises, returns the number of launches and their summed device time
+ * since the last call, and resets the counters. */
+int bp5_operator_profile(bp5_operator_t op, int enable);
+int bp5_operator_profile_result(bp5_operator_t op, int64_t *launches, double *total_ms);
 /* name of the hand-written kernel variant chosen for this operator */
 const char *bp5_operator_kernel_name(bp5_operator_t op);
 /* number of kernels this library has launched on the context since creation */

@@ -689,7 +689,10 @@ int orc_cg(void *h, int kind, int variant, int control, double tol, int max_its,
       }
       alpha_old = alpha; beta_old = beta;
       alpha = r[6] / r[0];
-      res = std::sqrt(r[3] + 2 * alpha * r[2] + alpha * alpha * r[1]);
+      // solver.h:504-505.  Deviation: clamped at 0 -- at exact (finite-termination)
+      // convergence the three-term expression can round to -1e-30 and the
+      // unguarded sqrt would turn a converged solve into NaN / NoConvergence.
+      res = std::sqrt(std::max(0.0, r[3] + 2 * alpha * r[2] + alpha * alpha * r[1]));
       if (history && it < history_len) history[it] = res;
       conv = check(it, res);
       if (conv != 0) {

@@ -1,0 +1,17 @@
+"""Small fixed workload for ncu: a few vmults (zero + cell kernel + constrained copy) of one configuration.
+usage: python scripts/ncu_target.py <degree> <gll|gauss> <cells_per_dir> [n_vmults]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import dealceed_b200 as dc
+p, quad, cells = int(sys.argv[1]), sys.argv[2], int(sys.argv[3])
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+ctx = dc.Context(0)
+op = dc.PoissonOperator(ctx, dc.make_problem(p, (cells,) * 3, quadrature=dc.QUAD_GLL if quad == "gll" else dc.QUAD_GAUSS))
+src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+src.import_host(np.random.default_rng(0).standard_normal(op.n_owned))
+for _ in range(reps):
+    op.vmult(dst, src)
+ctx.synchronize()
+print("done", op.kernel_name, op.n_owned, "algorithmic bytes per vmult", op.algorithmic_bytes()[0])

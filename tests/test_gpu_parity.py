@@ -1,0 +1,268 @@
+"""-m gpu: the CUDA path (through the C ABI) against the oracle and the committed golden
+fixtures.  Tolerance: fp64 operator application <= 1e-12 relative L2 error (north star);
+CG: same iteration count +-1 to the same tolerance, solution to 1e-8."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ladder
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-12
+
+
+def _dc():
+    import dealceed_b200 as dc
+    return dc
+
+
+def _vmult(ctx, op, u):
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.import_host(u)
+    op.vmult(dst, src)
+    out = dst.to_host()
+    src.close(); dst.close()
+    return out
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("p", range(1, 9))
+def test_vmult_matches_golden_fixture_and_oracle(gpu_ctx, p):
+    """every degree x quadrature x operator x (affine|deformed): committed fixture AND live oracle"""
+    dc = _dc()
+    import oracle as O
+    gold = np.load(os.path.join(GOLD, "vmult_cases.npz"))
+    for quad in (0, 1):
+        for kind in (0, 1):
+            for deform in (0, 1):
+                key = f"p{p}_q{quad}_k{kind}_d{deform}"
+                cells = tuple(int(c) for c in gold[key + "_cells"])
+                op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=quad, operator_kind=kind,
+                                                                 deformation=deform, eps=0.1))
+                u = np.random.default_rng(p).standard_normal(op.n_owned)
+                got = _vmult(gpu_ctx, op, u)
+                assert relerr(got, gold[key + "_out"]) <= TOL, key
+                m = O.OracleMesh(p, cells, quad=quad, deform=deform, eps=0.1)
+                assert relerr(got, m.vmult(u, kind=kind)) <= TOL, key
+                assert np.abs(op.coefficients() - m.metric()).max() <= 1e-12 * np.abs(m.metric()).max(), key
+                op.close()
+
+
+@pytest.mark.parametrize("p,cells", [(2, (1, 1, 1)), (4, (1, 1, 1)), (8, (1, 1, 1)), (3, (7, 1, 1)), (2, (5, 3, 1)),
+                                     (4, (3, 2, 1)), (5, (2, 2, 1)), (6, (4, 1, 1)), (7, (3, 1, 1)), (1, (33, 1, 1))])
+def test_ragged_and_minimal_meshes(gpu_ctx, p, cells):
+    """cell counts that do not fill the last tile, single cells, one-cell-thick slabs"""
+    dc = _dc()
+    import oracle as O
+    for quad in (0, 1):
+        op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=quad))
+        m = O.OracleMesh(p, cells, quad=quad)
+        u = np.random.default_rng(7).standard_normal(m.n_dofs)
+        assert relerr(_vmult(gpu_ctx, op, u), m.vmult(u)) <= TOL
+        op.close()
+
+
+def test_vmult_semantics_zero_out_and_constrained_copy(gpu_ctx):
+    """do_zero_out=false accumulates (bp5/step-64.cu:270-271); Dirichlet rows copy src (:275)"""
+    dc = _dc()
+    import oracle as O
+    p, cells = 3, (3, 3, 2)
+    op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells))
+    m = O.OracleMesh(p, cells)
+    rng = np.random.default_rng(3)
+    u, w = rng.standard_normal(m.n_dofs), rng.standard_normal(m.n_dofs)
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.import_host(u); dst.import_host(w)
+    op.do_zero_out = False
+    op.vmult(dst, src)
+    got = dst.to_host()
+    ref = m.vmult(u, dst=w.copy())
+    assert relerr(got, ref) <= TOL
+    bm = m.boundary_mask()
+    assert np.array_equal(got[bm], u[bm])
+    op.do_zero_out = True
+    op.vmult(dst, src)
+    assert relerr(dst.to_host(), m.vmult(u)) <= TOL
+    # the two halves separately
+    dst.set(0.0)
+    op.cell_loop(dst, src)
+    half = dst.to_host()
+    op.copy_constrained_values(dst, src)
+    assert relerr(dst.to_host(), m.vmult(u)) <= TOL and not np.array_equal(half[bm], u[bm])
+    for v in (src, dst):
+        v.close()
+    op.close()
+
+
+def test_config1_p4_32cubed(gpu_ctx):
+    """BASELINE config 1 (p=4, 32^3 cells, 2,146,689 DoFs): operator and 200-iteration CG vs fixture"""
+    dc = _dc()
+    g = json.load(open(os.path.join(GOLD, "config1_p4_32.json")))
+    op = dc.PoissonOperator(gpu_ctx, dc.make_problem(4, (32, 32, 32), upper=(1., 1., 1.)))
+    assert op.n_owned == g["n_dofs"]
+    n = op.n_owned
+    # boundary mask from coordinates
+    xyz = op.dof_coordinates()
+    bm = np.any((xyz == 0.0) | (xyz == 1.0), axis=1)
+    u = np.random.default_rng(4).standard_normal(n); u[bm] = 0
+    v = _vmult(gpu_ctx, op, u)
+    assert np.linalg.norm(v) == pytest.approx(g["vmult_seed4_l2"], rel=1e-12)
+    np.testing.assert_allclose(v[:: n // 16][:16], g["vmult_seed4_sample"], rtol=1e-10, atol=1e-12 * np.abs(v).max())
+    b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+    op.assemble_rhs(b)
+    assert b.l2_norm() == pytest.approx(g["b_l2"], rel=1e-12)
+    ctl = dc.IterationNumberControl(200, 1e-6 * b.l2_norm())
+    op.do_zero_out = False
+    dc.SolverCGFullMerge(ctl).solve(op, x, b)
+    assert ctl.last_step() == g["its"] == 200          # terminates at the cap
+    np.testing.assert_allclose(ctl.history[::20], g["history_every_20"], rtol=1e-6)
+    assert x.l2_norm() == pytest.approx(g["x_l2"], rel=1e-8)
+    for v_ in (b, x):
+        v_.close()
+    op.close()
+
+
+@pytest.mark.parametrize("cycle", [7, 8, 12, 13])
+@pytest.mark.parametrize("quad", ["gauss", "gll"])
+def test_bp5_ladder_cg_iteration_parity(gpu_ctx, cycle, quad):
+    """reference mesh ladder, degree 5, tol 1e-6 (bp5/step-64.cu:443-445,724-730): merged and standard CG"""
+    dc = _dc()
+    g = json.load(open(os.path.join(GOLD, "bp5_ladder_p5.json")))[f"cycle{cycle}_{quad}"]
+    cells, upper = ladder(cycle)
+    op = dc.PoissonOperator(gpu_ctx, dc.make_problem(5, cells, quadrature=0 if quad == "gauss" else 1, upper=upper))
+    assert op.n_owned == g["n_dofs"]
+    b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+    op.assemble_rhs(b)
+    assert b.l2_norm() == pytest.approx(g["b_l2"], rel=1e-12)
+    tol = 1e-6 * b.l2_norm()
+    for Solver, key, zero in ((dc.SolverCGFullMerge, "its_merged", False), (dc.SolverCG, "its_standard", True)):
+        ctl = dc.IterationNumberControl(200, tol)
+        op.do_zero_out = zero
+        x.set(0.0)
+        Solver(ctl).solve(op, x, b)
+        assert abs(ctl.last_step() - g[key]) <= 1
+        assert x.l2_norm() == pytest.approx(g["x_l2"], rel=1e-6)
+        if key == "its_merged" and ctl.last_step() == g[key]:
+            # residual history: tight while the residual is large, loose in the last digits
+            # before convergence (rounding-sensitive; the iteration count is the parity criterion)
+            h, hg = np.asarray(ctl.history), np.asarray(g["history"])
+            big = hg > 1e-3 * hg[0]
+            np.testing.assert_allclose(h[big], hg[big], rtol=1e-6)
+            np.testing.assert_allclose(h[~big], hg[~big], rtol=0.25)
+    b.close(); x.close(); op.close()
+
+
+@pytest.mark.parametrize("refine,its_ref,norm_ref", [(1, 27, 0.0205439), (2, 60, 0.0205269), (3, 114, 0.0205261)])
+def test_step64_helmholtz_known_answers_on_gpu(gpu_ctx, refine, its_ref, norm_ref):
+    """upstream deal.II step-64 tutorial output reproduced by the CUDA path (Q3, tol 1e-12|b|, SolverControl)"""
+    dc = _dc()
+    import oracle as O
+    c = 2 ** refine
+    op = dc.PoissonOperator(gpu_ctx, dc.make_problem(3, (c, c, c), operator_kind=dc.OP_HELMHOLTZ, upper=(1., 1., 1.)))
+    b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+    op.assemble_rhs(b)
+    for Solver, zero in ((dc.SolverCG, True), (dc.SolverCGFullMerge, False)):
+        ctl = dc.SolverControl(op.n_owned, 1e-12 * b.l2_norm())
+        op.do_zero_out = zero
+        x.set(0.0)
+        Solver(ctl).solve(op, x, b)
+        assert abs(ctl.last_step() - its_ref) <= 1
+        m = O.OracleMesh(3, (c, c, c), quad=O.GAUSS, upper=(1., 1., 1.))
+        assert f"{m.l2_norm(x.to_host()):.6g}" == f"{norm_ref:.6g}"
+    b.close(); x.close(); op.close()
+
+
+def test_solver_control_failure_and_diag_preconditioner(gpu_ctx):
+    dc = _dc()
+    import oracle as O
+    p, cells = 3, (3, 2, 2)
+    op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells))
+    m = O.OracleMesh(p, cells)
+    b, x, diag = op.initialize_dof_vector(), op.initialize_dof_vector(), op.initialize_dof_vector()
+    op.assemble_rhs(b)
+    op.do_zero_out = False
+    ctl = dc.SolverControl(3, 0.0)
+    with pytest.raises(dc.NoConvergence):
+        dc.SolverCGFullMerge(ctl).solve(op, x, b)
+    assert ctl.last_step() == 3
+    # zero right-hand side: converged at step 0, x untouched
+    z = op.initialize_dof_vector()
+    ctl = dc.SolverControl(10, 0.0)
+    x.set(0.0)
+    dc.SolverCGFullMerge(ctl).solve(op, x, z)
+    assert ctl.last_step() == 0 and x.all_zero()
+    # non-trivial diagonal in the preconditioner slot (solver.h:421), non-zero start vector
+    d = 1.0 / (1.0 + np.arange(m.n_dofs) % 3)
+    diag.import_host(d)
+    bh = b.to_host()
+    tol = 1e-8 * np.linalg.norm(bh)
+    x0 = np.random.default_rng(5).standard_normal(m.n_dofs); x0[m.boundary_mask()] = 0
+    xo, its, *_ = m.cg(bh, x0=x0, variant=1, control=1, tol=tol, max_its=500, diag=d)
+    for Solver, zero in ((dc.SolverCGFullMerge, False), (dc.SolverCG, True)):
+        ctl = dc.SolverControl(500, tol)
+        op.do_zero_out = zero
+        x.import_host(x0)
+        Solver(ctl).solve(op, x, b, preconditioner=diag)
+        assert abs(ctl.last_step() - its) <= 1
+        assert relerr(x.to_host(), xo) <= 1e-7
+    for v in (b, x, diag, z):
+        v.close()
+    op.close()
+
+
+def test_full_size_properties(gpu_ctx):
+    """size-independent properties at a BASELINE-scale mesh (p=6, 40^3 cells, 13.9M DoFs):
+    linearity, symmetry u.Av = v.Au, A*1 = 0 off the boundary, positive definiteness"""
+    dc = _dc()
+    p, c = 6, 40
+    for quad in (0, 1):
+        op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, (c, c, c), quadrature=quad, deformation=1, eps=0.1))
+        n = op.n_owned
+        xyz = op.dof_coordinates()
+        bm = np.any((xyz == 0.0) | (xyz == float(c)), axis=1)
+        rng = np.random.default_rng(11)
+        u, v = rng.standard_normal(n), rng.standard_normal(n)
+        u[bm] = 0; v[bm] = 0
+        U, V, W, AU, AV, AW = [op.initialize_dof_vector() for _ in range(6)]
+        U.import_host(u); V.import_host(v); W.import_host(2.0 * u - 3.0 * v)
+        op.vmult(AU, U); op.vmult(AV, V); op.vmult(AW, W)
+        uav, vau, uau = U.dot_local(AV), V.dot_local(AU), U.dot_local(AU)
+        assert abs(uav - vau) <= 1e-11 * abs(uav)
+        assert uau > 0
+        lin = AW.to_host() - (2.0 * AU.to_host() - 3.0 * AV.to_host())
+        assert np.linalg.norm(lin) <= 1e-12 * np.linalg.norm(AW.to_host())
+        U.set(1.0)
+        op.vmult(AU, U)
+        r = AU.to_host()
+        assert np.abs(r[~bm]).max() <= 1e-10 and np.all(r[bm] == 1.0)
+        for t in (U, V, W, AU, AV, AW):
+            t.close()
+        op.close()
+
+
+def test_vector_ops(gpu_ctx):
+    dc = _dc()
+    n = 100003
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    A, B = dc.Vector(gpu_ctx, n), dc.Vector(gpu_ctx, n)
+    assert A.all_zero()
+    A.import_host(a); B.import_host(b)
+    assert not A.all_zero()
+    assert A.dot_local(B) == pytest.approx(a @ b, rel=1e-12)
+    assert A.l2_norm() == pytest.approx(np.linalg.norm(a), rel=1e-13)
+    A.add(2.5, B); a = a + 2.5 * b
+    np.testing.assert_allclose(A.to_host(), a, rtol=1e-14, atol=1e-14)   # FMA contraction on the device
+    A.sadd(0.5, -1.0, B); a = 0.5 * a - b
+    np.testing.assert_allclose(A.to_host(), a, rtol=1e-14, atol=1e-14)
+    A.equ(-1.0, B)
+    np.testing.assert_array_equal(A.to_host(), -b)
+    A.set(3.0)
+    assert np.all(A.to_host() == 3.0)
+    A.close(); B.close()
