@@ -153,7 +153,9 @@ int bp5_operator_destroy(bp5_operator_t op) {
   if (!op) return BP5_OK;
   cudaSetDevice(op->ctx->device);
   cudaStreamSynchronize(op->ctx->stream);
-  cudaFree(op->l2g);
+  cudaFree(op->cell_base);
+  cudaFree(op->l2g_irr);
+  cudaFree(op->skel_mask);
   cudaFree(op->metric);
   cudaFree(op->constrained);
   cudaFree(op->cg_scalars);
@@ -200,7 +202,7 @@ int bp5_operator_cell_loop(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src
   if ((rc = check_vec(op, dst)) || (rc = check_vec(op, src))) return rc;
   BP5_REQUIRE(dst != src, "dst and src must differ");
   BP5_CUDA(cudaSetDevice(op->ctx->device));
-  return apply_cell_loop(op, dst->d, src->d);
+  return apply_cell_loop(op, dst->d, src->d, /*overwrite_interior=*/false);   // dst += A src
   BP5_ABI_GUARD_END
 }
 
@@ -223,9 +225,10 @@ int bp5_operator_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
   // host that owns the communicator; this entry point
   // does the local part: src ghosts must be up to date, dst ghosts receive the
   // contributions for the neighbouring owners.
-  if (op->do_zero_out)
-    BP5_CUDA(cudaMemsetAsync(dst->d, 0, sizeof(double) * (dst->n_owned + dst->n_ghost), op->ctx->stream));
-  if ((rc = apply_cell_loop(op, dst->d, src->d))) return rc;
+  // "dst = 0" only has to reach the DoFs shared between cells: cell-interior
+  // DoFs receive exactly one contribution and are stored by the kernel.
+  if (op->do_zero_out && (rc = apply_zero_skeleton(op, dst->d))) return rc;
+  if ((rc = apply_cell_loop(op, dst->d, src->d, /*overwrite_interior=*/op->do_zero_out))) return rc;
   return apply_copy_constrained(op, dst->d, src->d);
   BP5_ABI_GUARD_END
 }
@@ -234,9 +237,9 @@ int bp5_operator_vmult_ptr(bp5_operator_t op, double *dst, const double *src, in
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && dst && src && dst != src, "bad argument");
   BP5_CUDA(cudaSetDevice(op->ctx->device));
-  if (zero_dst) BP5_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (op->n_owned + op->n_ghost), op->ctx->stream));
   int rc;
-  if ((rc = apply_cell_loop(op, dst, src))) return rc;
+  if (zero_dst && (rc = apply_zero_skeleton(op, dst))) return rc;
+  if ((rc = apply_cell_loop(op, dst, src, zero_dst != 0))) return rc;
   return apply_copy_constrained(op, dst, src);
   BP5_ABI_GUARD_END
 }

@@ -1,6 +1,8 @@
 // Host side of the cell loop: kernel selection per (degree, quadrature,
-// operator), persistent-grid sizing, and the Dirichlet copy
+// operator), persistent-grid sizing, skeleton zeroing and the Dirichlet copy
 // (MatrixFree::cell_loop / copy_constrained_values, bp5/step-64.cu:274-275).
+#include <cstdlib>
+
 #include "apply.cuh"
 
 namespace bp5 {
@@ -34,7 +36,7 @@ int apply_choose(bp5_operator_t op) {
   op->cells_per_tile = cpt;
   op->n_tiles = (op->n_cells + cpt - 1) / cpt;
   op->tile_doubles = ((int64_t)cpt * op->metric_planes * n3 + 1) & ~(int64_t)1;
-  char name[128];
+  char name[160];
   snprintf(name, sizeof(name), "bp5_apply_kernel<p=%d,%s,%s,cells_per_tile=%d>", op->p,
            op->prob.quadrature == BP5_QUAD_GLL ? "gll-collocation" : "gauss",
            op->prob.operator_kind == BP5_OP_HELMHOLTZ ? "helmholtz" : "poisson", cpt);
@@ -42,27 +44,33 @@ int apply_choose(bp5_operator_t op) {
   return BP5_OK;
 }
 
-template <int P, int QUAD, int HELM>
+template <int P, int QUAD, int HELM, int OVERWRITE>
 static int launch(bp5_operator_t op, double *dst, const double *src) {
   constexpr int CPT = TileCells<P>::value;
   using Cfg = ApplyCfg<P, CPT, 6 + HELM>;
   constexpr int N = P + 1;
-  auto kernel = bp5_apply_kernel<P, QUAD, HELM, CPT>;
+  auto kernel = bp5_apply_kernel<P, QUAD, HELM, CPT, OVERWRITE>;
   static int blocks_per_sm = 0;   // per instantiation
   if (blocks_per_sm == 0) {
     BP5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    if (const char *cv = getenv("BP5_CARVEOUT"))   // tuning knob: percent of the L1/shared array given to shared
+      BP5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
     int nb = 0;
     BP5_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, Cfg::NT, Cfg::SMEM_BYTES));
     BP5_REQUIRE(nb > 0, "apply kernel does not fit on an SM");
     blocks_per_sm = nb;
   }
   ApplyParams<N> prm;
-  prm.metric = op->metric; prm.l2g = op->l2g; prm.src = src; prm.dst = dst;
-  prm.n_cells = op->n_cells; prm.n_tiles = op->n_tiles; prm.skip = op->skip_flag;
+  prm.metric = op->metric; prm.cell_base = op->cell_base; prm.l2g_irr = op->l2g_irr;
+  prm.src = src; prm.dst = dst;
+  prm.n_tiles = op->n_tiles; prm.sy = op->od[0]; prm.sz = op->od[0] * op->od[1];
+  prm.skip = op->skip_flag;
   for (int q = 0; q < N; ++q)
     for (int i = 0; i < N; ++i) {
-      prm.tab.B[q * N + i] = op->tab.B[q * N + i];
-      prm.tab.Dt[q * N + i] = op->tab.Dt[q * N + i];
+      for (int d = 0; d < 3; ++d) {
+        prm.tab.B[d][q * N + i] = prm.tab.BT[d][i * N + q] = op->tab.B[q * N + i];
+        prm.tab.D[d][q * N + i] = prm.tab.DT[d][i * N + q] = op->tab.Dt[q * N + i];
+      }
     }
   long long grid = (long long)blocks_per_sm * op->ctx->sm_count;
   if (grid > op->n_tiles) grid = op->n_tiles;
@@ -83,26 +91,51 @@ static int launch(bp5_operator_t op, double *dst, const double *src) {
 }
 
 template <int P>
-static int launch_p(bp5_operator_t op, double *dst, const double *src) {
+static int launch_p(bp5_operator_t op, double *dst, const double *src, bool overwrite) {
   const bool gll = op->prob.quadrature == BP5_QUAD_GLL;
   const bool helm = op->prob.operator_kind == BP5_OP_HELMHOLTZ;
-  if (gll) return helm ? launch<P, 1, 1>(op, dst, src) : launch<P, 1, 0>(op, dst, src);
-  return helm ? launch<P, 0, 1>(op, dst, src) : launch<P, 0, 0>(op, dst, src);
+  if (overwrite) {
+    if (gll) return helm ? launch<P, 1, 1, 1>(op, dst, src) : launch<P, 1, 0, 1>(op, dst, src);
+    return helm ? launch<P, 0, 1, 1>(op, dst, src) : launch<P, 0, 0, 1>(op, dst, src);
+  }
+  if (gll) return helm ? launch<P, 1, 1, 0>(op, dst, src) : launch<P, 1, 0, 0>(op, dst, src);
+  return helm ? launch<P, 0, 1, 0>(op, dst, src) : launch<P, 0, 0, 0>(op, dst, src);
 }
 
-int apply_cell_loop(bp5_operator_t op, double *dst, const double *src) {
+// overwrite_interior: dst's skeleton (shared DoFs, see zero_skeleton) must be
+// zero on entry, cell-interior DoFs are overwritten; otherwise dst += A src.
+int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior) {
   switch (op->p) {
-    case 1: return launch_p<1>(op, dst, src);
-    case 2: return launch_p<2>(op, dst, src);
-    case 3: return launch_p<3>(op, dst, src);
-    case 4: return launch_p<4>(op, dst, src);
-    case 5: return launch_p<5>(op, dst, src);
-    case 6: return launch_p<6>(op, dst, src);
-    case 7: return launch_p<7>(op, dst, src);
-    case 8: return launch_p<8>(op, dst, src);
+    case 1: return launch_p<1>(op, dst, src, overwrite_interior);
+    case 2: return launch_p<2>(op, dst, src, overwrite_interior);
+    case 3: return launch_p<3>(op, dst, src, overwrite_interior);
+    case 4: return launch_p<4>(op, dst, src, overwrite_interior);
+    case 5: return launch_p<5>(op, dst, src, overwrite_interior);
+    case 6: return launch_p<6>(op, dst, src, overwrite_interior);
+    case 7: return launch_p<7>(op, dst, src, overwrite_interior);
+    case 8: return launch_p<8>(op, dst, src, overwrite_interior);
   }
   set_error("unsupported degree %d", op->p);
   return BP5_ERR_UNSUPPORTED;
+}
+
+// dst = 0 on the skeleton only: owned DoFs shared by more than one cell (bit set
+// in skel_mask) and all ghost DoFs.  Cell-interior DoFs are left alone; the
+// OVERWRITE kernel stores them.  One 32-bit mask word serves a whole warp.
+__global__ void zero_skeleton_kernel(double *__restrict__ dst, const uint32_t *__restrict__ mask, long long n_owned,
+                                     long long n_total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_total;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i >= n_owned || ((__ldg(mask + (i >> 5)) >> (i & 31)) & 1u)) dst[i] = 0.0;
+  }
+}
+
+// Measured (profiles/r1_v2_notes.md): zeroing only the skeleton through the bit mask is SLOWER
+// than a full memset (scattered partial-sector writes) and saves no DRAM traffic, because L2
+// fills partially written sectors anyway.  So "dst = 0" is a plain memset.
+int apply_zero_skeleton(bp5_operator_t op, double *dst) {
+  BP5_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (op->n_owned + op->n_ghost), op->ctx->stream));
+  return BP5_OK;
 }
 
 // copy_constrained_values [UPSTREAM], called at bp5/step-64.cu:275:

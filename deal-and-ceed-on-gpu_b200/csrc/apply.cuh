@@ -13,34 +13,61 @@
 //    fetched by ONE cp.async.bulk (TMA 1D) per tile into shared memory, signalled
 //    on an mbarrier, and re-issued for the next tile as soon as the quadrature
 //    phase has consumed it: tens of KB in flight per CTA with zero registers;
-//  * gathers for the next tile are issued into registers one tile ahead, their
-//    indices two tiles ahead;
+//  * DoF indices: one int per cell.  base >= 0: the cell's DoFs are affine in the
+//    vector, idx(i,j,k) = base + i + j*sy + k*sz (structured numbering), so no
+//    index stream is read at all; base < 0: explicit n^3-entry table (cells on a
+//    partition's lower faces, whose ghost DoFs break the affine pattern).
+//    Replaces the padded local_to_global array of bp5/fe_evaluation_gl.h:118,144.
+//  * gathers for the next tile are issued into registers one tile ahead;
 //  * contractions: n^2 threads per cell.  Each thread alternates between
 //    "home" (owns the z-column (i,j,*)), "x-line" and "y-line" roles, holding a
 //    whole line in registers, so one 1D contraction costs one shared-memory load
 //    and one store per point instead of n loads; the z direction never leaves
-//    registers.  Shape matrices are kernel parameters (constant bank) and, with
-//    full unrolling, become immediate operands of the DFMAs.
-//  * scatter: fire-and-forget fp64 red.global.add.
+//    registers.  Shape matrices are kernel parameters (constant bank).  Line
+//    contractions whose result goes to shared memory or straight to the scatter
+//    keep their OUTER loop rolled: one matrix row (uniform-indexed LDCU) is live
+//    at a time.  Fully unrolled, ptxas caches matrix entries across contractions
+//    in the 63 uniform registers and spills them (MOV.SPILL / R2UR.FILL per DFMA).
+//  * scatter: DoFs interior to a cell have exactly one contribution: with
+//    OVERWRITE they are written with a plain store (no zero-fill before, no
+//    read-modify-write); only the skeleton (faces/edges/vertices) uses
+//    fire-and-forget fp64 red.global.add into pre-zeroed entries.
 #pragma once
 #include <cuda_runtime.h>
 
+#include <climits>
 #include <cstdint>
 
 #include "common.h"
+#include "smem_layout.h"
 
 namespace bp5 {
+
+constexpr int kNoCell = INT_MIN;
+
+// Shape tables as they travel to the kernel (by value, parameter constant bank).
+template <int N>
+struct KernelTables {
+  // One private copy per coordinate direction (x, y, z): every unrolled contraction
+  // then reads matrix entries nobody else reads, so ptxas has no cross-contraction
+  // reuse to cache in (and spill from) the 63 uniform registers.
+  double B[3][N * N];     // B[q][i]: basis i at quadrature point q (identity for GLL)
+  double BT[3][N * N];    // transpose
+  double D[3][N * N];     // D[q][r]: derivative of the Lagrange basis through the QUADRATURE points
+  double DT[3][N * N];    // transpose
+};
 
 template <int N>
 struct ApplyParams {
   const double *metric;   // [tile][CPT][PLANES][N^3], tile stride padded to 16 bytes
-  const int *l2g;         // [tiles*CPT][N^3]
+  const int *cell_base;   // [tiles*CPT]: >= 0 affine base, < 0: -(slot+1) into l2g_irr, kNoCell: padding
+  const int *l2g_irr;     // [n_irregular][N^3] explicit local dof indices, x fastest
   const double *src;
   double *dst;
-  long long n_cells;
   long long n_tiles;
+  int sy, sz;             // affine strides of the owned box
   const int *skip;        // optional device flag: non-zero => nothing to do (CG already converged)
-  ShapeTables<N> tab;
+  KernelTables<N> tab;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,34 +111,107 @@ __device__ __forceinline__ uint64_t make_evict_first_policy() {
   return pol;
 }
 
+// Local dof indices of the N points of one thread's z-column in a cell with
+// descriptor `base` (>= 0: affine, < 0: explicit table slot, kNoCell: no cell,
+// indices are 0 and the values are never used).  Branch-free on the common path
+// so that the N value loads that follow are issued back to back.
+template <int N>
+__device__ __forceinline__ void column_indices(int (&idx)[N], const int *__restrict__ l2g_irr, int base, int ab_off,
+                                               int ab_irr, int sz) {
+  if (base >= 0 || base == kNoCell) {
+    const int b0 = base >= 0 ? base + ab_off : 0;
+    const int s = base >= 0 ? sz : 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) idx[k] = b0 + k * s;
+  } else {
+    const int *row = l2g_irr + (long long)(-(base + 1)) * (N * N * N) + ab_irr;
+#pragma unroll
+    for (int k = 0; k < N; ++k) idx[k] = __ldg(row + k * N * N);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void gather_column(double (&u)[N], const double *__restrict__ src,
+                                              const int *__restrict__ l2g_irr, int base, int ab_off, int ab_irr, int sz) {
+  int idx[N];
+  column_indices<N>(idx, l2g_irr, base, ab_off, ab_irr, sz);
+#pragma unroll
+  for (int k = 0; k < N; ++k) u[k] = __ldg(src + idx[k]);
+}
+
+// Rows of the outer loop handled per (rolled) iteration: U independent DFMA
+// chains for latency hiding, with U*N matrix entries (2 uniform registers each)
+// live at a time -- must stay well inside the 63-entry uniform register file.
+#ifndef BP5_ROW_CHUNK
+#define BP5_ROW_CHUNK(N) ((N) == 9 ? 3 : (N))
+#endif
+
+// out[i*stride] = sum_m M[i][m] v[m], outer loop ROLLED in chunks of U rows
+// (see header comment).
+template <int N>
+__device__ __forceinline__ void contract_to_smem(double *out, int stride, const double *__restrict__ M,
+                                                 const double (&v)[N]) {
+  constexpr int U = BP5_ROW_CHUNK(N);
+#pragma unroll 1
+  for (int i0 = 0; i0 < N; i0 += U) {
+    const double *row = M + i0 * N;
+    double s[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) s[u] = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; ++m)
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (N % U == 0 || i0 + u < N) s[u] += row[u * N + m] * v[m];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (N % U == 0 || i0 + u < N) out[(i0 + u) * stride] = s[u];
+  }
+}
+
+// w[i] = sum_m M[i][m] v[m] in registers, fully unrolled (result indexed statically)
+template <int N>
+__device__ __forceinline__ void contract_in_regs(double (&w)[N], const double *__restrict__ M, const double (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; ++m) s += M[i * N + m] * v[m];
+    w[i] = s;
+  }
+}
+
 template <int P, int CPT, int PLANES>
 struct ApplyCfg {
   static constexpr int N = P + 1, N2 = N * N, N3 = N2 * N;
-  static constexpr int NP = (N % 2) ? N : N + 1;          // odd x-pitch of the work tiles: conflict-free line access
-  static constexpr int WS = N2 * NP;                       // doubles per work array per cell
+  using L = SmemLayout<N, CPT>;                            // per-array bank-conflict-minimising strides
   static constexpr int ACTIVE = CPT * N2;
   static constexpr int NT = ((ACTIVE + 31) / 32) * 32;
   static constexpr int METRIC_DOUBLES = (CPT * PLANES * N3 + 1) & ~1;  // per tile, padded to 16 bytes
   static constexpr uint32_t METRIC_BYTES = METRIC_DOUBLES * 8;
-  static constexpr int WORK_ARRAYS = 3;
-  static constexpr size_t SMEM_BYTES = (size_t)METRIC_BYTES + (size_t)WORK_ARRAYS * CPT * WS * 8 + 16;
+  static constexpr int WORK_DOUBLES = CPT * (2 * L::A_CS + L::B_CS);   // S0, S1 (layout A) and S2 (layout B)
+  static constexpr size_t SMEM_BYTES = (size_t)METRIC_BYTES + (size_t)WORK_DOUBLES * 8 + 16;
   static_assert(METRIC_BYTES % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
 };
 
 // QUAD: 0 = Gauss (basis nodes != quadrature points: interpolate, then
 // collocation derivative), 1 = Gauss-Lobatto collocation (B = identity).
 // HELM: 0 = Poisson (6 planes), 1 = Helmholtz (7th plane a(x) JxW on the values).
-template <int P, int QUAD, int HELM, int CPT>
+// OVERWRITE: 1 = cell-interior DoFs are stored, not added (dst's skeleton must be
+// zero on entry, its interior may hold anything); 0 = dst += A src everywhere.
+template <int P, int QUAD, int HELM, int CPT, int OVERWRITE>
 __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
     bp5_apply_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
   using Cfg = ApplyCfg<P, CPT, 6 + HELM>;
-  constexpr int N = Cfg::N, N2 = Cfg::N2, N3 = Cfg::N3, NP = Cfg::NP, WS = Cfg::WS, PLANES = 6 + HELM;
+  constexpr int N = Cfg::N, N2 = Cfg::N2, N3 = Cfg::N3, PLANES = 6 + HELM;
+  using L = typename Cfg::L;
+  constexpr int A1 = L::A_S1, A2 = L::A_S2, B1 = L::B_S1, B2 = L::B_S2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *Gs = reinterpret_cast<double *>(smem_raw);                 // [CPT][PLANES][N3]
-  double *S0 = Gs + Cfg::METRIC_DOUBLES;                             // [CPT][WS]
-  double *S1 = S0 + CPT * WS;
-  double *S2 = S1 + CPT * WS;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(S2 + CPT * WS);
+  double *S0 = Gs + Cfg::METRIC_DOUBLES;                             // layout A (home + x-line + y-line readers)
+  double *S1 = S0 + CPT * L::A_CS;                                   // layout A (home + x-line)
+  double *S2 = S1 + CPT * L::A_CS;                                   // layout B (home + y-line)
+  uint64_t *bar = reinterpret_cast<uint64_t *>(S2 + CPT * L::B_CS);
 
   if (prm.skip != nullptr && *prm.skip != 0) return;
   const int tid = threadIdx.x;
@@ -119,56 +219,56 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
   const int c = active ? tid / N2 : 0;      // cell within the tile
   const int r = tid % N2;
   const int a = r % N, b = r / N;           // the two free indices of this thread's line/column
-  double *s0 = S0 + c * WS, *s1 = S1 + c * WS, *s2 = S2 + c * WS;
+  double *s0 = S0 + c * L::A_CS, *s1 = S1 + c * L::A_CS, *s2 = S2 + c * L::B_CS;
   const double *gm = Gs + c * PLANES * N3;
-  const double *__restrict__ Bm = prm.tab.B;
-  const double *__restrict__ Dt = prm.tab.Dt;
+  const double *__restrict__ Bx = prm.tab.B[0], *__restrict__ By = prm.tab.B[1], *__restrict__ Bz = prm.tab.B[2];
+  const double *__restrict__ BTx = prm.tab.BT[0], *__restrict__ BTy = prm.tab.BT[1], *__restrict__ BTz = prm.tab.BT[2];
+  const double *__restrict__ Dx = prm.tab.D[0], *__restrict__ Dy = prm.tab.D[1], *__restrict__ Dz = prm.tab.D[2];
+  const double *__restrict__ DTx = prm.tab.DT[0], *__restrict__ DTy = prm.tab.DT[1], *__restrict__ DTz = prm.tab.DT[2];
+  const int ab_off = a + b * prm.sy;        // affine offset of this thread's column
+  const int ab_irr = b * N + a;
+  // shared-memory offsets of this thread's three roles
+  // address(i,j,k) = k*S2 + j*S1 + i in each array's own strides
+  const int hA = b * A1 + a, hB = b * B1 + a;     // + k * {A2,B2} : home column (i=a, j=b, k)
+  const int xA = b * A2 + a * A1;                 // + i           : x-line (i, j=a, k=b)
+  const int yA = b * A2 + a, yB = b * B2 + a;     // + j * {A1,B1} : y-line (i=a, j, k=b)
 
   const long long tile0 = blockIdx.x;
   const long long tstride = gridDim.x;
+  const long long n_tiles = prm.n_tiles;
+  const int sz = prm.sz;
+  const int *__restrict__ cell_base = prm.cell_base;
+  const int *__restrict__ l2g_irr = prm.l2g_irr;
+  const double *__restrict__ src = prm.src;
+  double *__restrict__ dst = prm.dst;
+  const double *__restrict__ metric = prm.metric;
   uint64_t policy = 0;
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
     policy = make_evict_first_policy();
-    if (tile0 < prm.n_tiles) {
+    if (tile0 < n_tiles) {
       mbar_expect_tx(bar, Cfg::METRIC_BYTES);
-      tma_load_1d(Gs, prm.metric + tile0 * (long long)Cfg::METRIC_DOUBLES, Cfg::METRIC_BYTES, bar, policy);
+      tma_load_1d(Gs, metric + tile0 * (long long)Cfg::METRIC_DOUBLES, Cfg::METRIC_BYTES, bar, policy);
     }
   }
   __syncthreads();
 
-  // software pipeline of the gather: indices two tiles ahead, values one tile ahead
-  int idx_cur[N], idx_nxt[N];
+  // software pipeline of the gather: cell descriptors two tiles ahead, values one tile ahead
+  int base_cur = (active && tile0 < n_tiles) ? __ldg(cell_base + tile0 * CPT + c) : kNoCell;
+  int base_nxt = (active && tile0 + tstride < n_tiles) ? __ldg(cell_base + (tile0 + tstride) * CPT + c) : kNoCell;
   double u_nxt[N];
-  {
-    const long long cell0 = tile0 * CPT + c, cell1 = (tile0 + tstride) * CPT + c;
-    const bool v0 = active && tile0 < prm.n_tiles && cell0 < prm.n_cells;
-    const bool v1 = active && (tile0 + tstride) < prm.n_tiles && cell1 < prm.n_cells;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      idx_cur[k] = v0 ? __ldg(prm.l2g + cell0 * N3 + (k * N + b) * N + a) : -1;
-      idx_nxt[k] = v1 ? __ldg(prm.l2g + cell1 * N3 + (k * N + b) * N + a) : -1;
-    }
-#pragma unroll
-    for (int k = 0; k < N; ++k) u_nxt[k] = idx_cur[k] >= 0 ? __ldg(prm.src + idx_cur[k]) : 0.0;
-  }
+  gather_column<N>(u_nxt, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
 
   uint32_t parity = 0;
-  for (long long tile = tile0; tile < prm.n_tiles; tile += tstride) {
+  for (long long tile = tile0; tile < n_tiles; tile += tstride) {
     double u[N];
-    int idx_n2[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) u[k] = u_nxt[k];
-    {
-      // issue next tile's gather and the index loads of the tile after it
-      const long long cell2 = (tile + 2 * tstride) * CPT + c;
-      const bool v2 = active && (tile + 2 * tstride) < prm.n_tiles && cell2 < prm.n_cells;
-#pragma unroll
-      for (int k = 0; k < N; ++k) u_nxt[k] = idx_nxt[k] >= 0 ? __ldg(prm.src + idx_nxt[k]) : 0.0;
-#pragma unroll
-      for (int k = 0; k < N; ++k) idx_n2[k] = v2 ? __ldg(prm.l2g + cell2 * N3 + (k * N + b) * N + a) : -1;
-    }
+    // issue next tile's gather and the descriptor load of the tile after it
+    gather_column<N>(u_nxt, src, l2g_irr, base_nxt, ab_off, ab_irr, sz);
+    const int base_n2 =
+        (active && tile + 2 * tstride < n_tiles) ? __ldg(cell_base + (tile + 2 * tstride) * CPT + c) : kNoCell;
 
     double t[N];   // z-direction data that stays in registers across the quadrature phase
     double mv[N];  // Helmholtz: values at the quadrature points (home column)
@@ -178,14 +278,8 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
       // (1) home (i=a, j=b): publish the column, z-derivative in registers
       if (active) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) s0[(k * N + b) * NP + a] = u[k];
-#pragma unroll
-        for (int k = 0; k < N; ++k) {
-          double s = 0.0;
-#pragma unroll
-          for (int m = 0; m < N; ++m) s += Dt[k * N + m] * u[m];
-          t[k] = s;
-        }
+        for (int k = 0; k < N; ++k) s0[hA + k * A2] = u[k];
+        contract_in_regs<N>(t, Dz, u);
         if constexpr (HELM) {
 #pragma unroll
           for (int k = 0; k < N; ++k) mv[k] = u[k];
@@ -196,95 +290,46 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
       if (active) {
         double v[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = s0[(b * N + a) * NP + i];
+        for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
+        contract_to_smem<N>(s1 + xA, 1, Dx, v);
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          double s = 0.0;
-#pragma unroll
-          for (int m = 0; m < N; ++m) s += Dt[i * N + m] * v[m];
-          s1[(b * N + a) * NP + i] = s;
-        }
-#pragma unroll
-        for (int j = 0; j < N; ++j) v[j] = s0[(b * N + j) * NP + a];
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-          double s = 0.0;
-#pragma unroll
-          for (int m = 0; m < N; ++m) s += Dt[j * N + m] * v[m];
-          s2[(b * N + j) * NP + a] = s;
-        }
+        for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
+        contract_to_smem<N>(s2 + yB, B1, Dy, v);
       }
       __syncthreads();
     } else {
       // ---------------- Gauss quadrature: interpolate to the q-points first
-      // (1) home (i=a, j=b): z-interpolation in registers
-      if (active) {
-#pragma unroll
-        for (int q = 0; q < N; ++q) {
-          double s = 0.0;
-#pragma unroll
-          for (int k = 0; k < N; ++k) s += Bm[q * N + k] * u[k];
-          s0[(q * N + b) * NP + a] = s;
-        }
-      }
+      // (1) home (i=a, j=b): z-interpolation
+      if (active) contract_to_smem<N>(s0 + hA, A2, Bz, u);
       __syncthreads();
       // (2) x-line (j=a, qz=b): x-interpolation in place
       if (active) {
         double v[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = s0[(b * N + a) * NP + i];
-#pragma unroll
-        for (int q = 0; q < N; ++q) {
-          double s = 0.0;
-#pragma unroll
-          for (int i = 0; i < N; ++i) s += Bm[q * N + i] * v[i];
-          s0[(b * N + a) * NP + q] = s;
-        }
+        for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
+        contract_to_smem<N>(s0 + xA, 1, Bx, v);
       }
       __syncthreads();
       // (3) y-line (qx=a, qz=b): y-interpolation (values at q-points), then d/dy
       if (active) {
         double v[N], w[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) v[j] = s0[(b * N + j) * NP + a];
+        for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
+        contract_in_regs<N>(w, By, v);
 #pragma unroll
-        for (int q = 0; q < N; ++q) {
-          double s = 0.0;
-#pragma unroll
-          for (int j = 0; j < N; ++j) s += Bm[q * N + j] * v[j];
-          w[q] = s;
-          s0[(b * N + q) * NP + a] = s;
-        }
-#pragma unroll
-        for (int q = 0; q < N; ++q) {
-          double s = 0.0;
-#pragma unroll
-          for (int rr = 0; rr < N; ++rr) s += Dt[q * N + rr] * w[rr];
-          s2[(b * N + q) * NP + a] = s;
-        }
+        for (int q = 0; q < N; ++q) s0[yA + q * A1] = w[q];
+        contract_to_smem<N>(s2 + yB, B1, Dy, w);
       }
       __syncthreads();
       // (4) x-line (qy=a, qz=b): d/dx ; home (qx=a, qy=b): d/dz in registers
       if (active) {
         double v[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = s0[(b * N + a) * NP + i];
+        for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
+        contract_to_smem<N>(s1 + xA, 1, Dx, v);
 #pragma unroll
-        for (int q = 0; q < N; ++q) {
-          double s = 0.0;
-#pragma unroll
-          for (int rr = 0; rr < N; ++rr) s += Dt[q * N + rr] * v[rr];
-          s1[(b * N + a) * NP + q] = s;
-        }
-#pragma unroll
-        for (int k = 0; k < N; ++k) v[k] = s0[(k * N + b) * NP + a];
-#pragma unroll
-        for (int q = 0; q < N; ++q) {
-          double s = 0.0;
-#pragma unroll
-          for (int rr = 0; rr < N; ++rr) s += Dt[q * N + rr] * v[rr];
-          t[q] = s;
-        }
+        for (int k = 0; k < N; ++k) v[k] = s0[hA + k * A2];
+        contract_in_regs<N>(t, Dz, v);
         if constexpr (HELM) {
 #pragma unroll
           for (int k = 0; k < N; ++k) mv[k] = v[k];
@@ -299,58 +344,51 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
     if (active) {
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        const int q = (k * N + b) * N + a, w = (k * N + b) * NP + a;
-        const double ur = s1[w], us = s2[w], ut = t[k];
+        const int q = (k * N + b) * N + a, wA = hA + k * A2, wB = hB + k * B2;
+        const double ur = s1[wA], us = s2[wB], ut = t[k];
         const double g0 = gm[q], g1 = gm[N3 + q], g2 = gm[2 * N3 + q];
         const double g3 = gm[3 * N3 + q], g4 = gm[4 * N3 + q], g5 = gm[5 * N3 + q];
-        s1[w] = ur * g0 + us * g3 + ut * g4;
-        s2[w] = ur * g3 + us * g1 + ut * g5;
+        s1[wA] = ur * g0 + us * g3 + ut * g4;
+        s2[wB] = ur * g3 + us * g1 + ut * g5;
         t[k] = ur * g4 + us * g5 + ut * g2;
         if constexpr (HELM) mv[k] *= gm[6 * N3 + q];
       }
     }
     __syncthreads();
     // the metric buffer is free: fetch the next tile's metric behind the remaining work
-    if (tid == 0 && tile + tstride < prm.n_tiles) {
+    if (tid == 0 && tile + tstride < n_tiles) {
       mbar_expect_tx(bar, Cfg::METRIC_BYTES);
-      tma_load_1d(Gs, prm.metric + (tile + tstride) * (long long)Cfg::METRIC_DOUBLES, Cfg::METRIC_BYTES, bar, policy);
+      tma_load_1d(Gs, metric + (tile + tstride) * (long long)Cfg::METRIC_DOUBLES, Cfg::METRIC_BYTES, bar, policy);
     }
 
-    double out[N];
+    int idx[N];
+    column_indices<N>(idx, l2g_irr, base_cur, ab_off, ab_irr, sz);
+    const bool col_interior = OVERWRITE && a > 0 && a < P && b > 0 && b < P;
+    const bool do_scatter = base_cur != kNoCell;
+
     if constexpr (QUAD == 1) {
       // (4) transposed derivative along x- and y-lines, in place
       if (active) {
         double v[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = s1[(b * N + a) * NP + i];
+        for (int i = 0; i < N; ++i) v[i] = s1[xA + i];
+        contract_to_smem<N>(s1 + xA, 1, DTx, v);
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          double s = 0.0;
-#pragma unroll
-          for (int m = 0; m < N; ++m) s += Dt[m * N + i] * v[m];
-          s1[(b * N + a) * NP + i] = s;
-        }
-#pragma unroll
-        for (int j = 0; j < N; ++j) v[j] = s2[(b * N + j) * NP + a];
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-          double s = 0.0;
-#pragma unroll
-          for (int m = 0; m < N; ++m) s += Dt[m * N + j] * v[m];
-          s2[(b * N + j) * NP + a] = s;
-        }
+        for (int j = 0; j < N; ++j) v[j] = s2[yB + j * B1];
+        contract_to_smem<N>(s2 + yB, B1, DTy, v);
       }
       __syncthreads();
-      // (5) home: z-transpose in registers, sum the three directions
-      if (active) {
+      // (5) home: z-transpose in registers, sum the three directions, scatter
+      if (do_scatter) {
+        double o[N];
+        contract_in_regs<N>(o, DTz, t);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-          const int w = (k * N + b) * NP + a;
-          double s = s1[w] + s2[w];
-#pragma unroll
-          for (int m = 0; m < N; ++m) s += Dt[m * N + k] * t[m];
+          double s = o[k] + s1[hA + k * A2] + s2[hB + k * B2];
           if constexpr (HELM) s += mv[k];
-          out[k] = s;
+          double *dp = dst + idx[k];
+          if (col_interior && k > 0 && k < P) *dp = s;     // multiplicity 1: plain store
+          else atomicAdd(dp, s);                           // skeleton: red.global.add.f64
         }
       }
     } else {
@@ -358,21 +396,15 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
       if (active) {
         double v[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = s1[(b * N + a) * NP + i];
+        for (int i = 0; i < N; ++i) v[i] = s1[xA + i];
+        contract_to_smem<N>(s1 + xA, 1, DTx, v);
+        if constexpr (HELM) {
+          double o[N];
+          contract_in_regs<N>(o, DTz, t);
 #pragma unroll
-        for (int rr = 0; rr < N; ++rr) {
-          double s = 0.0;
-#pragma unroll
-          for (int q = 0; q < N; ++q) s += Dt[q * N + rr] * v[q];
-          s1[(b * N + a) * NP + rr] = s;
-        }
-#pragma unroll
-        for (int rr = 0; rr < N; ++rr) {
-          double s = 0.0;
-#pragma unroll
-          for (int q = 0; q < N; ++q) s += Dt[q * N + rr] * t[q];
-          if constexpr (HELM) s += mv[rr];
-          s0[(rr * N + b) * NP + a] = s;
+          for (int k = 0; k < N; ++k) s0[hA + k * A2] = o[k] + mv[k];
+        } else {
+          contract_to_smem<N>(s0 + hA, A2, DTz, t);
         }
       }
       __syncthreads();
@@ -380,60 +412,37 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
       if (active) {
         double v[N], y[N];
 #pragma unroll
-        for (int q = 0; q < N; ++q) v[q] = s2[(b * N + q) * NP + a];
+        for (int q = 0; q < N; ++q) v[q] = s2[yB + q * B1];
+        contract_in_regs<N>(y, DTy, v);
 #pragma unroll
-        for (int rr = 0; rr < N; ++rr) {
-          double s = s1[(b * N + rr) * NP + a] + s0[(b * N + rr) * NP + a];
-#pragma unroll
-          for (int q = 0; q < N; ++q) s += Dt[q * N + rr] * v[q];
-          y[rr] = s;
-        }
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-          double s = 0.0;
-#pragma unroll
-          for (int q = 0; q < N; ++q) s += Bm[q * N + j] * y[q];
-          s0[(b * N + j) * NP + a] = s;
-        }
+        for (int q = 0; q < N; ++q) y[q] += s1[yA + q * A1] + s0[yA + q * A1];
+        contract_to_smem<N>(s0 + yA, A1, BTy, y);
       }
       __syncthreads();
       // (7) x-line (j=a, qz=b): B^T along x in place
       if (active) {
         double v[N];
 #pragma unroll
-        for (int q = 0; q < N; ++q) v[q] = s0[(b * N + a) * NP + q];
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          double s = 0.0;
-#pragma unroll
-          for (int q = 0; q < N; ++q) s += Bm[q * N + i] * v[q];
-          s0[(b * N + a) * NP + i] = s;
-        }
+        for (int q = 0; q < N; ++q) v[q] = s0[xA + q];
+        contract_to_smem<N>(s0 + xA, 1, BTx, v);
       }
       __syncthreads();
-      // (8) home (i=a, j=b): B^T along z in registers
-      if (active) {
-        double v[N];
+      // (8) home (i=a, j=b): B^T along z in registers, scatter
+      if (do_scatter) {
+        double v[N], o[N];
 #pragma unroll
-        for (int q = 0; q < N; ++q) v[q] = s0[(q * N + b) * NP + a];
+        for (int q = 0; q < N; ++q) v[q] = s0[hA + q * A2];
+        contract_in_regs<N>(o, BTz, v);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-          double s = 0.0;
-#pragma unroll
-          for (int q = 0; q < N; ++q) s += Bm[q * N + k] * v[q];
-          out[k] = s;
+          double *dp = dst + idx[k];
+          if (col_interior && k > 0 && k < P) *dp = o[k];
+          else atomicAdd(dp, o[k]);
         }
       }
     }
-
-    // distribute_local_to_global (bp5/fe_evaluation_gl.h:161-181): atomic add
-    if (active) {
-#pragma unroll
-      for (int k = 0; k < N; ++k)
-        if (idx_cur[k] >= 0) atomicAdd(prm.dst + idx_cur[k], out[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < N; ++k) { idx_cur[k] = idx_nxt[k]; idx_nxt[k] = idx_n2[k]; }
+    base_cur = base_nxt;
+    base_nxt = base_n2;
   }
 }
 

@@ -78,7 +78,10 @@ template <int MODE, bool DIAG>
 __global__ void __launch_bounds__(256) cg_update_kernel(const CgState *__restrict__ st, double *__restrict__ p,
                                                         double *__restrict__ r, double *__restrict__ v,
                                                         double *__restrict__ x, const double *__restrict__ diag,
-                                                        long long n) {
+                                                        const uint32_t *__restrict__ skel, long long n) {
+  // "v = 0" (solver.h:69,101,137).  (Restricting it to the skeleton bit mask `skel` was measured
+  // slower: scattered partial-sector writes, and L2 fills the sectors anyway.)
+  (void)skel;
   if (st->state != 0) return;
   const double alpha = st->alpha, beta = st->beta;
   double apa = 0.0, aob = 0.0;
@@ -287,9 +290,9 @@ static unsigned stream_grid(long long n, int sm_count) {
 
 template <int MODE>
 static void launch_update(bool has_diag, unsigned grid, cudaStream_t s, const CgState *st, double *p, double *r,
-                          double *v, double *x, const double *diag, long long n) {
-  if (has_diag) cg_update_kernel<MODE, true><<<grid, 256, 0, s>>>(st, p, r, v, x, diag, n);
-  else cg_update_kernel<MODE, false><<<grid, 256, 0, s>>>(st, p, r, v, x, diag, n);
+                          double *v, double *x, const double *diag, const uint32_t *skel, long long n) {
+  if (has_diag) cg_update_kernel<MODE, true><<<grid, 256, 0, s>>>(st, p, r, v, x, diag, skel, n);
+  else cg_update_kernel<MODE, false><<<grid, 256, 0, s>>>(st, p, r, v, x, diag, skel, n);
 }
 
 int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diagv, int variant, int control,
@@ -329,8 +332,8 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
   int x_zero = 0;
   if ((rc = vec_all_zero(ctx, x->d, n, &x_zero))) return rc;
   if (!x_zero) {
-    BP5_CUDA(cudaMemsetAsync(g, 0, sizeof(double) * n, s));
-    if ((rc = apply_cell_loop(op, g, x->d))) return rc;
+    if ((rc = apply_zero_skeleton(op, g))) return rc;
+    if ((rc = apply_cell_loop(op, g, x->d, true))) return rc;
     if ((rc = apply_copy_constrained(op, g, x->d))) return rc;
     if ((rc = vec_axpy(ctx, g, 1.0, -1.0, b->d, n, 0))) return rc;
   } else if ((rc = vec_axpy(ctx, g, 0.0, -1.0, b->d, n, 1)))
@@ -386,20 +389,21 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
       const int cur = it + 1;
       if (variant == BP5_CG_MERGED) {
         // 1) update region (solver.h:413-448), with the parity-correct x update
-        if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x->d, diag, n);
-        else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x->d, diag, n);
-        else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, n);
+        if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x->d, diag, op->skel_mask, n);
+        else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x->d, diag, op->skel_mask, n);
+        else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, op->skel_mask, n);
         ctx->launches++;
-        // 2) h = A d with do_zero_out = false (solver.h:475; h zeroed by the update kernel)
-        if ((rc = apply_cell_loop(op, h, d))) break;
+        // 2) h = A d with do_zero_out = false (solver.h:475; h's skeleton zeroed by the update kernel,
+        //    its cell-interior entries are overwritten by the cell kernel)
+        if ((rc = apply_cell_loop(op, h, d, true))) break;
         if ((rc = apply_copy_constrained(op, h, d))) break;
         // 3)+4) dots and scalars (solver.h:478-533)
         if (has_diag) cg_dots_kernel<true><<<kCgBlocks, kCgThreads, 0, s>>>(st, d, g, h, diag, n, partials, hist_dev);
         else cg_dots_kernel<false><<<kCgBlocks, kCgThreads, 0, s>>>(st, d, g, h, diag, n, partials, hist_dev);
         ctx->launches++;
       } else {
-        if (cudaMemsetAsync(h, 0, sizeof(double) * n, s) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
-        if ((rc = apply_cell_loop(op, h, d))) break;
+        if ((rc = apply_zero_skeleton(op, h))) break;
+        if ((rc = apply_cell_loop(op, h, d, true))) break;
         if ((rc = apply_copy_constrained(op, h, d))) break;
         std_dh_kernel<<<kCgBlocks, kCgThreads, 0, s>>>(st, d, h, n, partials);
         if (has_diag) {

@@ -108,8 +108,12 @@ struct bp5_operator_s {
   int64_t n_tiles = 0;
   int64_t tile_doubles = 0;     // metric doubles per tile (padded to a multiple of 2)
   // device data
-  int *l2g = nullptr;           // [n_tiles*cpt][n^3] local dof index, x fastest
-  double *metric = nullptr;     // Poisson: [cell][6][n^3]; Helmholtz: [cell][7][n^3] (6 + a*JxW)
+  int *cell_base = nullptr;     // [n_tiles*cpt] per-cell dof descriptor: >= 0 affine base (idx = base + i + j*od0 +
+                                // k*od0*od1), < 0: -(slot+1) into l2g_irr, INT_MIN: padding cell
+  int *l2g_irr = nullptr;       // [n_irregular][n^3] explicit local dof indices (cells touching lower ghost layers)
+  int64_t n_irregular = 0;
+  uint32_t *skel_mask = nullptr; // bit i set: owned dof i is shared by more than one cell (skeleton)
+  double *metric = nullptr;     // [tile][cpt][planes][n^3]; planes: 6 (Poisson) or 7 (Helmholtz: + a*JxW)
   int metric_planes = 6;
   int *constrained = nullptr;   // local owned indices of Dirichlet dofs
   int64_t n_constrained = 0;
@@ -137,7 +141,8 @@ int operator_export_coords(bp5_operator_t op, double *host_out);
 int operator_export_global_indices(bp5_operator_t op, int64_t *host_out);
 // apply.cu
 int apply_choose(bp5_operator_t op);                 // picks cells_per_tile + kernel name
-int apply_cell_loop(bp5_operator_t op, double *dst, const double *src);
+int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior);
+int apply_zero_skeleton(bp5_operator_t op, double *dst);
 int apply_copy_constrained(bp5_operator_t op, double *dst, const double *src);
 // vector.cu
 int vec_fill(bp5_context_t ctx, double *d, int64_t n, double v);

@@ -8,6 +8,7 @@
 // Everything is generated on the GPU from the analytic mesh description; no
 // O(n_dofs) host arrays are built except the Dirichlet index list.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <vector>
 
@@ -102,16 +103,37 @@ __device__ __forceinline__ double det3(const double J[3][3]) {
          J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
 }
 
-// One block per local cell.  Writes l2g[cell][n3] and metric[cell][planes][n3].
-__global__ void setup_cells_kernel(BlockGeom g, int *__restrict__ l2g, double *__restrict__ metric) {
+// bit i of mask: owned dof i lies on a cell face (shared by more than one cell,
+// or by a cell of a neighbouring block): the "skeleton".  One thread per word.
+__global__ void skeleton_mask_kernel(BlockGeom g, uint32_t *__restrict__ mask, long long n_words) {
+  const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  uint32_t bits = 0;
+  for (int bit = 0; bit < 32; ++bit) {
+    const long long idx = w * 32 + bit;
+    if (idx >= g.n_owned) break;
+    const int i = (int)(idx % g.od[0]) + g.hlo[0];
+    const int j = (int)((idx / g.od[0]) % g.od[1]) + g.hlo[1];
+    const int k = (int)(idx / ((long long)g.od[0] * g.od[1])) + g.hlo[2];
+    if (i % g.p == 0 || j % g.p == 0 || k % g.p == 0) bits |= 1u << bit;
+  }
+  mask[w] = bits;
+}
+
+// One block per local cell.  Writes metric[tile][cell in tile][planes][n3] and,
+// for irregular cells (cell_base < 0), the explicit index table l2g_irr[slot][n3].
+__global__ void setup_cells_kernel(BlockGeom g, const int *__restrict__ cell_base, int *__restrict__ l2g_irr,
+                                   double *__restrict__ metric) {
   extern __shared__ double sm[];
   const int n = g.n, n2 = n * n, n3 = n2 * n;
   const long long cell = blockIdx.x;
   const int lcx = cell % g.lc[0], lcy = (cell / g.lc[0]) % g.lc[1], lcz = cell / ((long long)g.lc[0] * g.lc[1]);
   const int t = threadIdx.x;
   const int i = t % n, j = (t / n) % n, k = t / n2;
-  if (t < n3)
-    l2g[cell * n3 + t] = (int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
+  const int base = cell_base[cell];
+  if (t < n3 && base < 0)
+    l2g_irr[(long long)(-(base + 1)) * n3 + t] =
+        (int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
   double J[3][3], xr[3];
   cell_jacobian(g, c_tab.B, c_tab.Dg, sm, g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz, J, xr);
   if (t >= n3) return;
@@ -220,15 +242,40 @@ int operator_setup_device(bp5_operator_t op) {
   const int n = op->n, n3 = n * n * n;
   const BlockGeom g = make_geom(op);
   const int64_t padded_cells = op->n_tiles * op->cells_per_tile;
-  BP5_CUDA(cudaMalloc(&op->l2g, sizeof(int) * padded_cells * n3));
-  BP5_CUDA(cudaMemsetAsync(op->l2g, 0, sizeof(int) * padded_cells * n3, ctx->stream));
+  // per-cell dof descriptors: affine base for regular cells, slot of an explicit
+  // table for cells that touch a lower ghost layer, INT_MIN for tile padding
+  std::vector<int> base((size_t)padded_cells, INT_MIN);
+  int64_t n_irr = 0;
+  {
+    const int p = op->p;
+    int64_t cell = 0;
+    for (int cz = 0; cz < op->lc[2]; ++cz)
+      for (int cy = 0; cy < op->lc[1]; ++cy)
+        for (int cx = 0; cx < op->lc[0]; ++cx, ++cell) {
+          const bool irregular = (cx == 0 && op->has_lo[0]) || (cy == 0 && op->has_lo[1]) || (cz == 0 && op->has_lo[2]);
+          if (irregular)
+            base[cell] = -(int)(n_irr++) - 1;
+          else
+            base[cell] = (int)((cx * p - op->has_lo[0]) +
+                               (int64_t)op->od[0] * ((cy * p - op->has_lo[1]) + (int64_t)op->od[1] * (cz * p - op->has_lo[2])));
+        }
+  }
+  op->n_irregular = n_irr;
+  BP5_CUDA(cudaMalloc(&op->cell_base, sizeof(int) * padded_cells));
+  BP5_CUDA(cudaMemcpyAsync(op->cell_base, base.data(), sizeof(int) * padded_cells, cudaMemcpyHostToDevice, ctx->stream));
+  BP5_CUDA(cudaMalloc(&op->l2g_irr, sizeof(int) * std::max<int64_t>(n_irr, 1) * n3));
   const size_t mbytes = sizeof(double) * op->n_tiles * op->tile_doubles;
   BP5_CUDA(cudaMalloc(&op->metric, mbytes));
   BP5_CUDA(cudaMemsetAsync(op->metric, 0, mbytes, ctx->stream));
   BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
   const int threads = ((n3 + 31) / 32) * 32;
   const size_t smem = sizeof(double) * 8 * n3;
-  setup_cells_kernel<<<(unsigned)op->n_cells, threads, smem, ctx->stream>>>(g, op->l2g, op->metric);
+  setup_cells_kernel<<<(unsigned)op->n_cells, threads, smem, ctx->stream>>>(g, op->cell_base, op->l2g_irr, op->metric);
+  BP5_CHECK_LAUNCH();
+  ctx->launches++;
+  const long long n_words = (op->n_owned + 31) / 32;
+  BP5_CUDA(cudaMalloc(&op->skel_mask, sizeof(uint32_t) * std::max<long long>(n_words, 1)));
+  skeleton_mask_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, ctx->stream>>>(g, op->skel_mask, n_words);
   BP5_CHECK_LAUNCH();
   ctx->launches++;
 
