@@ -1,0 +1,142 @@
+"""N>1 leg of bench.py: one rank per GPU (torchrun), weak scaling -- every GPU holds a
+cells^3 block of a P_x x P_y x P_z partition (1x1x1, 2x1x1, 2x2x1, 2x2x2), halo exchange over
+NCCL/NVLink inside every operator application and one allreduce of the 7 CG scalars per iteration."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def run(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import dealceed_b200 as dc
+    from dealceed_b200.distributed import DistributedPoisson
+    import bench as single
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    quad_ids = {"gll": dc.QUAD_GLL, "gauss": dc.QUAD_GAUSS}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    P = DistributedPoisson(args.degree, (args.cells,) * 3, quadrature=quad_ids[args.quadrature], device=local_rank)
+    op, ctx = P.op, P.ctx
+    b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+    op.assemble_rhs(b)
+    bnorm = P.l2_norm(b)
+    control = dc.IterationNumberControl(single.MAX_ITS, 1e-6 * bnorm)
+    op.do_zero_out = False
+
+    def solve():
+        x.set(0.0)
+        P.cg_solve(x, b, control)
+
+    for _ in range(args.warmup):
+        solve()
+    ctx.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count
+    op.profile(True)
+    sampler = single.ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(P.stream)
+    its_total = 0
+    for _ in range(args.steps):
+        solve()
+        its_total += control.last_step()
+    e1.record(P.stream)
+    e1.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    secs_local = e0.elapsed_time(e1) * 1e-3
+    t = torch.tensor([secs_local], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    k_launches, k_ms = op.profile_result()
+    op.profile(False)
+    launches = ctx.launch_count - launches0
+    xnorm = P.l2_norm(x)
+
+    # end to end: pinned host b -> device, solve, x -> pinned host, every step
+    n_loc = op.n_owned
+    bh = torch.empty(n_loc, dtype=torch.float64, pin_memory=True)
+    xh = torch.empty(n_loc, dtype=torch.float64, pin_memory=True)
+    bh.numpy()[:] = b.to_host()
+    bview, xview = P.view(b), P.view(x)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_its = 0
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        with torch.cuda.stream(P.stream):
+            bview[:n_loc].copy_(bh, non_blocking=True)
+            xh.zero_()
+            xview[:n_loc].copy_(xh, non_blocking=True)
+        P.cg_solve(x, b, control)
+        with torch.cuda.stream(P.stream):
+            xh.copy_(xview[:n_loc], non_blocking=True)
+        ctx.synchronize()
+        e2e_its += control.last_step()
+    dist.barrier()
+    e2e_local = time.perf_counter() - t0
+    t = torch.tensor([e2e_local], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_secs = float(t.item())
+
+    bytes_vmult, bytes_cg = op.algorithmic_bytes()
+    if rank == 0:
+        n_glob = P.n_global
+        k_s = k_ms * 1e-3 / max(1, k_launches)
+        ach = bytes_vmult / k_s / 1e9
+        grid = P.part.grid
+        out = {
+            "metric": single.METRIC, "value": n_glob * its_total / secs / 1e9, "unit": single.UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"BP5 Poisson, p={args.degree}, {args.cells}^3 cells per GPU, {grid[0]}x{grid[1]}x{grid[2]} blocks = "
+                            f"{n_glob} DoFs, {args.quadrature} quadrature, merged CG, IterationNumberControl({single.MAX_ITS}, 1e-6|b|), "
+                            f"{its_total / args.steps:.0f} iterations per step",
+                "quadrature": args.quadrature, "degree": args.degree, "cells_per_gpu": args.cells ** 3,
+                "dofs_global": n_glob, "dofs_per_gpu": n_glob / world,
+                "parallelism": f"domain decomposition {grid[0]}x{grid[1]}x{grid[2]}, NCCL halo (send/recv) + allreduce(7 doubles)/iteration",
+                "iterations_per_step": its_total / args.steps,
+                "l2": "no flush: vectors and metric are far larger than the 126 MB L2", "kernel": op.kernel_name,
+            },
+            "clocks": clocks,
+            "e2e": {"value": n_glob * e2e_its / e2e_secs / 1e9, "unit": single.UNIT,
+                    "h2d_bytes_per_step": 2 * n_loc * 8 * world, "d2h_bytes_per_step": n_loc * 8 * world,
+                    "api": "per rank: pinned host b, x0 -> device, DistributedPoisson.cg_solve, x -> host"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": op.kernel_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": bytes_vmult,
+                         "avg_launch_ms": k_s * 1e3, "launches_timed": k_launches, "note": "rank 0's cell kernel",
+                         "kernel_share_of_step": k_ms * 1e-3 / secs,
+                         "cg_frac_per_gpu": bytes_cg * its_total / secs / 1e9 / hbm_peak},
+            "check": {"x_l2": xnorm, "b_l2": bnorm, "last_residual": control.last_value()},
+        }
+        print(json.dumps(out))
+    # release every torch object that touched the library's stream before that stream goes away
+    ctx.synchronize()
+    del bview, xview, bh, xh, t
+    torch.cuda.synchronize()
+    b.close(); x.close()
+    P.close()
+    dist.destroy_process_group()
+    return 0

@@ -98,6 +98,18 @@ ABI = [
                                _dp, C.c_int]),
     ("bp5_cg_solve_host", C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.POINTER(C.c_int), _dp]),
+    ("bp5_operator_halo_info", C.c_int, [_vp] + [C.POINTER(C.c_int64)] * 4),
+    ("bp5_operator_halo_pack", C.c_int, [_vp, _vp, _vp]),
+    ("bp5_operator_halo_unpack_add", C.c_int, [_vp, _vp, _vp]),
+    ("bp5_cg_step_begin", C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int]),
+    ("bp5_cg_step_vectors", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    ("bp5_cg_step_update", C.c_int, [_vp, C.c_int]),
+    ("bp5_cg_step_apply_local", C.c_int, [_vp]),
+    ("bp5_cg_step_constrained", C.c_int, [_vp]),
+    ("bp5_cg_step_local_dots", C.c_int, [_vp, _vp]),
+    ("bp5_cg_step_scalars", C.c_int, [_vp, _vp]),
+    ("bp5_cg_step_poll", C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp]),
+    ("bp5_cg_step_finish", C.c_int, [_vp, _dp]),
 ]
 
 

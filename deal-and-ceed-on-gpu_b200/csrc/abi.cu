@@ -480,4 +480,109 @@ int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, i
   BP5_ABI_GUARD_END
 }
 
+
+// ------------------------------------------------- partitioned meshes: halo + stepwise CG
+int bp5_operator_halo_info(bp5_operator_t op, int64_t *send_count, int64_t *send_offset, int64_t *recv_count,
+                           int64_t *recv_offset) {
+  BP5_REQUIRE(op && send_count && send_offset && recv_count && recv_offset, "null argument");
+  return halo_info(op, send_count, send_offset, recv_count, recv_offset);
+}
+
+int bp5_operator_halo_pack(bp5_operator_t op, bp5_vector_t vec, double *sendbuf_dev) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && sendbuf_dev, "null argument");
+  int rc;
+  if ((rc = check_vec(op, vec))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return halo_pack(op, vec->d, sendbuf_dev);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_operator_halo_unpack_add(bp5_operator_t op, bp5_vector_t vec, const double *recvbuf_dev) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && recvbuf_dev, "null argument");
+  int rc;
+  if ((rc = check_vec(op, vec))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return halo_unpack_add(op, vec->d, recvbuf_dev);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_cg_step_begin(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,
+                      int max_its, double res0, int history_len) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op, "null operator");
+  int rc;
+  if ((rc = check_vec(op, x)) || (rc = check_vec(op, b))) return rc;
+  if (diag && (rc = check_vec(op, diag))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return cg_step_begin(op, x, b, diag, control, tol, max_its, res0, history_len);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_cg_step_vectors(bp5_operator_t op, bp5_vector_t *g, bp5_vector_t *d, bp5_vector_t *h) {
+  BP5_REQUIRE(op && op->g, "bp5_cg_step_begin has not been called");
+  if (g) *g = op->g;
+  if (d) *d = op->d;
+  if (h) *h = op->h;
+  return BP5_OK;
+}
+
+#define BP5_STEP_GUARD()                                                              \
+  BP5_REQUIRE(op && op->cg_scalars && op->cg_x, "bp5_cg_step_begin has not been called"); \
+  BP5_CUDA(cudaSetDevice(op->ctx->device))
+
+int bp5_cg_step_update(bp5_operator_t op, int iteration) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_STEP_GUARD();
+  BP5_REQUIRE(iteration >= 1, "iterations are 1-based");
+  return cg_step_update(op, iteration);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_cg_step_apply_local(bp5_operator_t op) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_STEP_GUARD();
+  // h (zeroed by the update step) = local cells' part of A d; the caller exchanges halos around this
+  return apply_cell_loop(op, op->h->d, op->d->d, true);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_cg_step_constrained(bp5_operator_t op) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_STEP_GUARD();
+  return apply_copy_constrained(op, op->h->d, op->d->d);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_cg_step_local_dots(bp5_operator_t op, double *sums7_dev) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_STEP_GUARD();
+  BP5_REQUIRE(sums7_dev, "null buffer");
+  return cg_step_local_dots(op, sums7_dev);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_cg_step_scalars(bp5_operator_t op, const double *sums7_dev) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_STEP_GUARD();
+  BP5_REQUIRE(sums7_dev, "null buffer");
+  return cg_step_scalars(op, sums7_dev);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_cg_step_poll(bp5_operator_t op, int *state, int *last_step, double *last_value) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_STEP_GUARD();
+  return cg_step_poll(op, state, last_step, last_value);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_cg_step_finish(bp5_operator_t op, double *history) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_STEP_GUARD();
+  return cg_step_finish(op, history);
+  BP5_ABI_GUARD_END
+}
+
 }  // extern "C"

@@ -102,12 +102,43 @@ __global__ void __launch_bounds__(256) cg_update_kernel(const CgState *__restric
   }
 }
 
-template <bool DIAG>
+// scalar recurrences of one iteration from the seven (globally summed) dot products
+// (solver.h:497-533); one thread
+__device__ __forceinline__ void cg_scalar_step(CgState *st, const double (&rr)[7], double *history) {
+  const int it = st->it + 1;
+  st->alpha_old = st->alpha;
+  st->beta_old = st->beta;
+  st->it = it;
+  if (rr[0] == 0.0) { st->state = 3; return; }                 // ExcDivideByZero, solver.h:501
+  const double alpha = rr[6] / rr[0];                         // solver.h:502
+  // solver.h:504-505; clamped at 0 (deviation): at exact convergence the three-term
+  // expression can round slightly negative and the unguarded sqrt would report NaN.
+  const double res = sqrt(fmax(0.0, rr[3] + 2 * alpha * rr[2] + alpha * alpha * rr[1]));
+  st->alpha = alpha;
+  st->res = res;
+  if (history && it < st->history_len) history[it] = res;
+  const int conv = control_check(st->control, it, st->max_its, res, st->tol);
+  if (conv != 0) { st->state = conv; return; }
+  st->beta = alpha * (rr[4] + alpha * rr[5]) / rr[6];         // solver.h:533
+}
+
+// partitioned meshes: the sums come back from an allreduce over the blocks
+__global__ void cg_scalars_kernel(CgState *st, const double *__restrict__ sums, double *history) {
+  if (st->state != 0 || threadIdx.x != 0 || blockIdx.x != 0) return;
+  double rr[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) rr[j] = sums[j];
+  cg_scalar_step(st, rr, history);
+}
+
+// FUSE: the last block also runs the scalar recurrences (single block of the mesh);
+// otherwise it writes the seven local sums to sums_out for the caller's allreduce.
+template <bool DIAG, bool FUSE>
 __global__ void __launch_bounds__(kCgThreads) cg_dots_kernel(CgState *st, const double *__restrict__ p,
                                                              const double *__restrict__ r,
                                                              const double *__restrict__ v,
                                                              const double *__restrict__ diag, long long n,
-                                                             double *partials, double *history) {
+                                                             double *partials, double *history, double *sums_out) {
   if (st->state != 0) return;
   __shared__ double sh[7 * 32];
   __shared__ bool is_last;
@@ -146,22 +177,11 @@ __global__ void __launch_bounds__(kCgThreads) cg_dots_kernel(CgState *st, const 
 #pragma unroll
     for (int j = 0; j < K; ++j) rr[j] = s[j];
     if (!DIAG) { rr[4] = rr[2]; rr[5] = rr[1]; rr[6] = rr[3]; }
-    const int it = st->it + 1;
-    st->alpha_old = st->alpha;
-    st->beta_old = st->beta;
     st->ticket = 0;
-    st->it = it;
-    if (rr[0] == 0.0) { st->state = 3; return; }                 // ExcDivideByZero, solver.h:501
-    const double alpha = rr[6] / rr[0];                         // solver.h:502
-    // solver.h:504-505; clamped at 0 (deviation): at exact convergence the three-term
-    // expression can round slightly negative and the unguarded sqrt would report NaN.
-    const double res = sqrt(fmax(0.0, rr[3] + 2 * alpha * rr[2] + alpha * alpha * rr[1]));
-    st->alpha = alpha;
-    st->res = res;
-    if (history && it < st->history_len) history[it] = res;
-    const int conv = control_check(st->control, it, st->max_its, res, st->tol);
-    if (conv != 0) { st->state = conv; return; }
-    st->beta = alpha * (rr[4] + alpha * rr[5]) / rr[6];         // solver.h:533
+    if (FUSE) cg_scalar_step(st, rr, history);
+    else
+#pragma unroll
+      for (int j = 0; j < 7; ++j) sums_out[j] = rr[j];
   }
 }
 
@@ -398,8 +418,10 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
         if ((rc = apply_cell_loop(op, h, d, true))) break;
         if ((rc = apply_copy_constrained(op, h, d))) break;
         // 3)+4) dots and scalars (solver.h:478-533)
-        if (has_diag) cg_dots_kernel<true><<<kCgBlocks, kCgThreads, 0, s>>>(st, d, g, h, diag, n, partials, hist_dev);
-        else cg_dots_kernel<false><<<kCgBlocks, kCgThreads, 0, s>>>(st, d, g, h, diag, n, partials, hist_dev);
+        if (has_diag)
+          cg_dots_kernel<true, true><<<kCgBlocks, kCgThreads, 0, s>>>(st, d, g, h, diag, n, partials, hist_dev, nullptr);
+        else
+          cg_dots_kernel<false, true><<<kCgBlocks, kCgThreads, 0, s>>>(st, d, g, h, diag, n, partials, hist_dev, nullptr);
         ctx->launches++;
       } else {
         if ((rc = apply_zero_skeleton(op, h))) break;
@@ -455,6 +477,121 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
     return BP5_ERR_NO_CONVERGENCE;
   }
   if (fin.state != 1) { set_error("CG ended in unexpected state %d", fin.state); return BP5_ERR_INVALID; }
+  return BP5_OK;
+}
+
+// ------------------------------------------------------------------------
+// Stepwise merged CG for partitioned meshes.  The host that owns the
+// communicator interleaves: update -> [halo: update_ghost_values(d)] -> cell loop
+// -> [halo: compress(add)(h)] -> Dirichlet copy -> local dots -> [allreduce of 7
+// doubles, solver.h:493] -> scalars.  Nothing here synchronises except poll().
+static int stepwise_buffers(bp5_operator_t op, int hist_len) {
+  bp5_context_t ctx = op->ctx;
+  int rc;
+  if (!op->g) {
+    if ((rc = bp5_vector_create(ctx, op->n_owned, op->n_ghost, &op->g))) return rc;
+    if ((rc = bp5_vector_create(ctx, op->n_owned, op->n_ghost, &op->d))) return rc;
+    if ((rc = bp5_vector_create(ctx, op->n_owned, op->n_ghost, &op->h))) return rc;
+  }
+  const size_t need = 256 + sizeof(double) * kCgBlocks * 7 + sizeof(double) * (hist_len > 0 ? hist_len : 1);
+  if (!op->cg_scalars || op->cg_scalars_bytes < need) {
+    if (op->cg_scalars) cudaFree(op->cg_scalars);
+    op->cg_scalars = nullptr;
+    BP5_CUDA(cudaMalloc(&op->cg_scalars, need));
+    op->cg_scalars_bytes = need;
+  }
+  return BP5_OK;
+}
+
+int cg_step_begin(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,
+                  int max_its, double res0, int history_len) {
+  int rc;
+  if ((rc = stepwise_buffers(op, history_len))) return rc;
+  op->cg_x = x; op->cg_diag = diag; op->cg_hist_len = history_len;
+  const long long n = op->n_owned;
+  // g = -b  (x == 0 on entry: g = A x - b, solver.h:375-381), ghosts zero
+  BP5_CUDA(cudaMemsetAsync(op->g->d, 0, sizeof(double) * (n + op->n_ghost), op->ctx->stream));
+  if ((rc = vec_axpy(op->ctx, op->g->d, 0.0, -1.0, b->d, n, 1))) return rc;
+  CgState init{};
+  init.tol = tol; init.res = res0; init.max_its = max_its; init.control = control; init.history_len = history_len;
+  BP5_CUDA(cudaMemcpyAsync(op->cg_scalars, &init, sizeof(CgState), cudaMemcpyHostToDevice, op->ctx->stream));
+  BP5_CUDA(cudaStreamSynchronize(op->ctx->stream));   // `init` lives on this stack frame
+  op->skip_flag = &reinterpret_cast<CgState *>(op->cg_scalars)->state;
+  return BP5_OK;
+}
+
+int cg_step_update(bp5_operator_t op, int cur) {
+  CgState *st = reinterpret_cast<CgState *>(op->cg_scalars);
+  const long long n = op->n_owned;
+  const unsigned grid = stream_grid(n, op->ctx->sm_count);
+  const double *diag = op->cg_diag ? op->cg_diag->d : nullptr;
+  const bool has_diag = diag != nullptr;
+  cudaStream_t s = op->ctx->stream;
+  double *g = op->g->d, *d = op->d->d, *h = op->h->d, *x = op->cg_x->d;
+  if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x, diag, op->skel_mask, n);
+  else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x, diag, op->skel_mask, n);
+  else launch_update<3>(has_diag, grid, s, st, d, g, h, x, diag, op->skel_mask, n);
+  BP5_CHECK_LAUNCH();
+  op->ctx->launches++;
+  // the ghost entries of h receive contributions for the neighbouring owners: start them at zero
+  if (op->n_ghost) BP5_CUDA(cudaMemsetAsync(h + n, 0, sizeof(double) * op->n_ghost, s));
+  return BP5_OK;
+}
+
+int cg_step_local_dots(bp5_operator_t op, double *sums_dev) {
+  CgState *st = reinterpret_cast<CgState *>(op->cg_scalars);
+  double *partials = reinterpret_cast<double *>(reinterpret_cast<char *>(op->cg_scalars) + 256);
+  const double *diag = op->cg_diag ? op->cg_diag->d : nullptr;
+  cudaStream_t s = op->ctx->stream;
+  const long long n = op->n_owned;
+  if (diag)
+    cg_dots_kernel<true, false><<<kCgBlocks, kCgThreads, 0, s>>>(st, op->d->d, op->g->d, op->h->d, diag, n, partials,
+                                                                 nullptr, sums_dev);
+  else
+    cg_dots_kernel<false, false><<<kCgBlocks, kCgThreads, 0, s>>>(st, op->d->d, op->g->d, op->h->d, diag, n, partials,
+                                                                  nullptr, sums_dev);
+  BP5_CHECK_LAUNCH();
+  op->ctx->launches++;
+  return BP5_OK;
+}
+
+int cg_step_scalars(bp5_operator_t op, const double *sums_dev) {
+  CgState *st = reinterpret_cast<CgState *>(op->cg_scalars);
+  double *hist = op->cg_hist_len > 0
+                     ? reinterpret_cast<double *>(reinterpret_cast<char *>(op->cg_scalars) + 256) + kCgBlocks * 7
+                     : nullptr;
+  cg_scalars_kernel<<<1, 32, 0, op->ctx->stream>>>(st, sums_dev, hist);
+  BP5_CHECK_LAUNCH();
+  op->ctx->launches++;
+  return BP5_OK;
+}
+
+int cg_step_poll(bp5_operator_t op, int *state, int *it, double *res) {
+  CgState fin{};
+  BP5_CUDA(cudaMemcpyAsync(&fin, op->cg_scalars, sizeof(CgState), cudaMemcpyDeviceToHost, op->ctx->stream));
+  BP5_CUDA(cudaStreamSynchronize(op->ctx->stream));
+  if (state) *state = fin.state;
+  if (it) *it = fin.it;
+  if (res) *res = fin.res;
+  return BP5_OK;
+}
+
+int cg_step_finish(bp5_operator_t op, double *history) {
+  CgState *st = reinterpret_cast<CgState *>(op->cg_scalars);
+  const long long n = op->n_owned;
+  const unsigned grid = stream_grid(n, op->ctx->sm_count);
+  const double *diag = op->cg_diag ? op->cg_diag->d : nullptr;
+  cudaStream_t s = op->ctx->stream;
+  if (diag) cg_finish_kernel<true><<<grid, 256, 0, s>>>(st, op->cg_x->d, op->d->d, op->g->d, diag, n);
+  else cg_finish_kernel<false><<<grid, 256, 0, s>>>(st, op->cg_x->d, op->d->d, op->g->d, diag, n);
+  BP5_CHECK_LAUNCH();
+  op->ctx->launches++;
+  op->skip_flag = nullptr;
+  if (history && op->cg_hist_len > 1) {
+    double *hist = reinterpret_cast<double *>(reinterpret_cast<char *>(op->cg_scalars) + 256) + kCgBlocks * 7;
+    BP5_CUDA(cudaMemcpyAsync(history + 1, hist + 1, sizeof(double) * (op->cg_hist_len - 1), cudaMemcpyDeviceToHost, s));
+  }
+  BP5_CUDA(cudaStreamSynchronize(s));
   return BP5_OK;
 }
 

@@ -124,6 +124,8 @@ struct bp5_operator_s {
   bp5_vector_t xh = nullptr, bh = nullptr;  // device staging of bp5_cg_solve_host
   double *cg_scalars = nullptr; // device
   size_t cg_scalars_bytes = 0;
+  bp5_vector_t cg_x = nullptr, cg_diag = nullptr;   // stepwise CG: caller's solution / diagonal
+  int cg_hist_len = 0;
   // live per-launch timing of the cell kernel (bench.py roofline): events around every launch
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;   // start/stop pairs
@@ -149,7 +151,18 @@ int vec_fill(bp5_context_t ctx, double *d, int64_t n, double v);
 int vec_axpy(bp5_context_t ctx, double *y, double s, double a, const double *x, int64_t n, int mode);
 int vec_dot(bp5_context_t ctx, const double *x, const double *y, int64_t n, double *out);
 int vec_all_zero(bp5_context_t ctx, const double *x, int64_t n, int *out);
+// halo.cu
+int halo_info(bp5_operator_t op, int64_t *send_count, int64_t *send_offset, int64_t *recv_count, int64_t *recv_offset);
+int halo_pack(bp5_operator_t op, const double *vec, double *sendbuf);
+int halo_unpack_add(bp5_operator_t op, double *vec, const double *recvbuf);
 // cg.cu
+int cg_step_begin(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,
+                  int max_its, double res0, int history_len);
+int cg_step_update(bp5_operator_t op, int iteration);
+int cg_step_local_dots(bp5_operator_t op, double *sums_dev);
+int cg_step_scalars(bp5_operator_t op, const double *sums_dev);
+int cg_step_poll(bp5_operator_t op, int *state, int *it, double *res);
+int cg_step_finish(bp5_operator_t op, double *history);
 int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int variant, int control,
              double tol, int max_its, int *last_step, double *last_value, double *history, int history_len);
 }  // namespace bp5

@@ -173,6 +173,48 @@ int bp5_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t
 int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, int64_t n, int variant,
                       int control, double tol, int max_its, int *last_step, double *last_value);
 
+/* ---- partitioned meshes: halo exchange and stepwise CG -------------------- */
+/* Message shapes of update_ghost_values / compress(add) [UPSTREAM, inside cell_loop,
+ * requested at bp5/step-64.cu:241].  Index m = 1..7 is a direction mask (bit d set: the
+ * partner differs in dimension d); arrays have 8 entries, entry 0 unused.
+ *   send_count/offset[m]: entries this block packs for its UPPER neighbour in direction m,
+ *                         and where they sit in the packed send buffer;
+ *   recv_count/offset[m]: ghost entries owned by the LOWER neighbour in direction m, and
+ *                         where that (contiguous) group starts in the vector's ghost region. */
+int bp5_operator_halo_info(bp5_operator_t op, int64_t *send_count, int64_t *send_offset, int64_t *recv_count,
+                           int64_t *recv_offset);
+/* update_ghost_values, sender side: sendbuf[offset[m] + t] = vec[owned dof t of group m].
+ * The receiver needs no unpack: group m lands at vec + n_owned + recv_offset[m]. */
+int bp5_operator_halo_pack(bp5_operator_t op, bp5_vector_t vec, double *sendbuf_dev);
+/* compress(add), owner side: vec[owned dof t of group m] += recvbuf[offset[m] + t]
+ * (the sender ships its ghost groups as they are, then calls bp5_vector_zero_out_ghosts). */
+int bp5_operator_halo_unpack_add(bp5_operator_t op, bp5_vector_t vec, const double *recvbuf_dev);
+
+/* SolverCGFullMerge::solve (bp5/solver.h:343-542) split at its communication points, for a
+ * host that owns the communicator: per iteration it >= 1
+ *   bp5_cg_step_update(op, it)          1) update region, solver.h:413-448
+ *   [update_ghost_values(d)]            d, h, g from bp5_cg_step_vectors
+ *   bp5_cg_step_apply_local(op)         2) h += local cells' part of A d, solver.h:475
+ *   [compress(add)(h)]
+ *   bp5_cg_step_constrained(op)            Dirichlet copy, bp5/step-64.cu:275
+ *   bp5_cg_step_local_dots(op, s)       3) seven local sums, solver.h:478-485, left on the device
+ *   [allreduce(s, 7 doubles, sum)]      4) MPI_Allreduce, solver.h:493
+ *   bp5_cg_step_scalars(op, s)             alpha, beta, residual, stopping test, solver.h:497-533
+ * Everything is enqueued on the context's stream; only bp5_cg_step_poll synchronises.  After the
+ * stopping test fires every step becomes a no-op, so the host may poll every few iterations.
+ * begin(): x must be zero (g = -b); res0 = global |b|_2 computed by the caller. */
+int bp5_cg_step_begin(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,
+                      int max_its, double res0, int history_len);
+int bp5_cg_step_vectors(bp5_operator_t op, bp5_vector_t *g, bp5_vector_t *d, bp5_vector_t *h);
+int bp5_cg_step_update(bp5_operator_t op, int iteration);
+int bp5_cg_step_apply_local(bp5_operator_t op);
+int bp5_cg_step_constrained(bp5_operator_t op);
+int bp5_cg_step_local_dots(bp5_operator_t op, double *sums7_dev);
+int bp5_cg_step_scalars(bp5_operator_t op, const double *sums7_dev);
+int bp5_cg_step_poll(bp5_operator_t op, int *state, int *last_step, double *last_value);
+/* owed x update (solver.h:509-526); history (optional, host) receives history[1..] */
+int bp5_cg_step_finish(bp5_operator_t op, double *history);
+
 #ifdef __cplusplus
 }
 #endif

@@ -419,6 +419,9 @@ void vmult(const Mesh &m, int kind, int semantics, bool zero_dst, const double *
     s = tmp.data();
   }
   apply_dispatch(m, kind, s, dst);
+  // semantics 2: the bare cell loop (MatrixFree::cell_loop without
+  // copy_constrained_values) -- used to emulate one block of a partition
+  if (semantics == 2) return;
 #pragma omp parallel for schedule(static)
   for (int gz = 0; gz < m.nd[2]; ++gz)
     for (int gy = 0; gy < m.nd[1]; ++gy)

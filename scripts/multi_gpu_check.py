@@ -1,0 +1,51 @@
+"""torchrun parity check of the partitioned path on N GPUs against the oracle (small mesh):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/multi_gpu_check.py
+Prints one OK/FAIL line per check on rank 0; exit code 1 on failure."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np, torch, torch.distributed as dist
+import dealceed_b200 as dc
+from dealceed_b200.distributed import DistributedPoisson
+import oracle as O
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local_rank = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(local_rank)
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+fails = 0
+for p, cpg, quad, deform in [(2, (3, 2, 2), dc.QUAD_GAUSS, 0), (4, (2, 2, 3), dc.QUAD_GLL, 1), (6, (2, 2, 2), dc.QUAD_GLL, 1), (5, (3, 3, 2), dc.QUAD_GAUSS, 0)]:
+    P = DistributedPoisson(p, cpg, quadrature=quad, deformation=deform, eps=0.1, device=local_rank)
+    cells = P.part.cells
+    m = O.OracleMesh(p, cells, quad=quad, deform=deform, eps=0.1)
+    gi = P.op.global_indices()
+    own = gi[: P.op.n_owned]
+    u = np.random.default_rng(5).standard_normal(m.n_dofs)
+    src, dst = P.op.initialize_dof_vector(), P.op.initialize_dof_vector()
+    full = np.zeros(P.op.n_owned + P.op.n_ghost); full[: P.op.n_owned] = u[own]
+    src.import_host(full)
+    P.vmult(dst, src)
+    ref = m.vmult(u)
+    err = np.linalg.norm(dst.to_host() - ref[own]) ** 2
+    tot = P.allreduce_scalar(err)
+    rel = np.sqrt(tot) / np.linalg.norm(ref)
+    # merged CG
+    b, x = P.op.initialize_dof_vector(), P.op.initialize_dof_vector()
+    P.op.assemble_rhs(b)
+    bo = m.rhs()
+    tol = 1e-8 * np.linalg.norm(bo)
+    ctl = dc.SolverControl(500, tol)
+    P.cg_solve(x, b, ctl, poll_every=3, history=True)
+    xo, its, res, hist, ok = m.cg(bo, variant=1, control=1, tol=tol, max_its=500)
+    xerr = np.sqrt(P.allreduce_scalar(np.linalg.norm(x.to_host() - xo[own]) ** 2)) / np.linalg.norm(xo)
+    good = rel <= 1e-12 and abs(ctl.last_step() - its) <= 1 and xerr <= 1e-7
+    fails += 0 if good else 1
+    if rank == 0:
+        print(f"{'OK  ' if good else 'FAIL'} world={world} grid={P.part.grid} p={p} cells={cells} quad={quad} deform={deform}: "
+              f"vmult rel err {rel:.2e}, CG its {ctl.last_step()} (oracle {its}), x rel err {xerr:.2e}", flush=True)
+    for v in (src, dst, b, x):
+        v.close()
+    P.close()
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(1 if fails else 0)
