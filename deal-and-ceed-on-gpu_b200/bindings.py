@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbp5b200.so")
+LIB_PATH = os.environ.get("BP5_LIB", os.path.join(_HERE, "libbp5b200.so"))   # BP5_LIB: tuning builds only
 
 QUAD_GAUSS, QUAD_GLL = 0, 1
 OP_POISSON, OP_HELMHOLTZ = 0, 1

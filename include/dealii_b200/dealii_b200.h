@@ -1,0 +1,364 @@
+// dealii_b200.h -- header-only C++ facade over the C ABI (include/bp5_b200.h).
+//
+// Re-creates, for the BP5 / step-64 hot path only, the deal.II-style host
+// interface the reference is written against, so that driver and solver code
+// shaped like bp5/step-64.cu and bp5/solver.h compiles against this library:
+//
+//   BP5::PoissonOperator<dim, fe_degree>            bp5/step-64.cu:198-276
+//   Step64::HelmholtzOperator<dim, fe_degree>       step-64/step-64.cu:232-322
+//   LinearAlgebra::distributed::Vector<double, MemorySpace::CUDA>   [UPSTREAM]
+//        (bp5/step-64.cu:321-323,349,363-367,417,432,445; solver.h:352-382,405,417,511)
+//   SolverControl / IterationNumberControl           bp5/step-64.cu:443-445,460
+//   SolverCG, SolverCGFullMerge                      bp5/step-64.cu:446-453; solver.h:15-31
+//   DiagonalMatrix                                   bp5/step-64.cu:428-432
+//   Triangulation / GridGenerator::subdivided_hyper_rectangle / DoFHandler / FE_Q /
+//   AffineConstraints: only as far as the drivers use them to DESCRIBE the
+//   structured mesh (bp5/step-64.cu:341-368,656-663); the mesh itself is
+//   generated on the GPU by the library.
+//
+// Errors: every C status code is turned back into the C++ exception the
+// reference throws (SolverControl::NoConvergence, ExcDivideByZero, ...).
+// One host thread per GPU, one stream per context (the reference uses the
+// default stream and one MPI rank per GPU, bp5/step-64.cu:704-707,720).
+#pragma once
+
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <iostream>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../bp5_b200.h"
+
+namespace dealii {
+
+namespace types { using global_dof_index = unsigned int; }
+namespace MemorySpace { struct Host {}; struct CUDA {}; }
+
+struct ExcMessage : std::runtime_error { using std::runtime_error::runtime_error; };
+struct ExcDivideByZero : std::runtime_error { ExcDivideByZero() : std::runtime_error("ExcDivideByZero") {} };
+
+// ------------------------------------------------------------------ SolverControl
+class SolverControl {
+ public:
+  enum State { iterate = 0, success, failure };
+  class NoConvergence : public std::runtime_error {
+   public:
+    NoConvergence(unsigned int step, double residual)
+        : std::runtime_error("Iterative method reported convergence failure in step " + std::to_string(step) +
+                             ". The residual in the last step was " + std::to_string(residual) + "."),
+          last_step(step), last_residual(residual) {}
+    const unsigned int last_step;
+    const double last_residual;
+  };
+  SolverControl(unsigned int n = 100, double tol = 1e-10) : maxsteps(n), tol(tol) {}
+  virtual ~SolverControl() = default;
+  unsigned int last_step() const { return lstep; }
+  double last_value() const { return lvalue; }
+  double tolerance() const { return tol; }
+  unsigned int max_steps() const { return maxsteps; }
+  virtual int abi_kind() const { return BP5_CONTROL_SOLVER; }          // failure at max_steps
+  void record(unsigned int step, double value) { lstep = step; lvalue = value; }
+
+ protected:
+  unsigned int maxsteps;
+  double tol;
+  unsigned int lstep = 0;
+  double lvalue = 0.0;
+};
+
+// success at the tolerance OR at max_steps (bp5/step-64.cu:443-445)
+class IterationNumberControl : public SolverControl {
+ public:
+  using SolverControl::SolverControl;
+  int abi_kind() const override { return BP5_CONTROL_ITERATION_NUMBER; }
+};
+
+// ------------------------------------------------------------------ context
+namespace b200 {
+inline void check(int rc) {
+  if (rc == BP5_OK) return;
+  const std::string msg = bp5_last_error();
+  if (rc == BP5_ERR_DIVIDE_BY_ZERO) throw ExcDivideByZero();
+  throw ExcMessage("bp5_b200 error " + std::to_string(rc) + ": " + msg);
+}
+// one context per process: device = rank % n_devices (bp5/step-64.cu:704-707)
+class Context {
+ public:
+  static bp5_context_t get(int device = -1) {
+    static Context c(device < 0 ? 0 : device);
+    return c.h;
+  }
+  static void synchronize() { check(bp5_context_synchronize(get())); }   // cudaDeviceSynchronize in the driver
+
+ private:
+  explicit Context(int device) { check(bp5_context_create(device, &h)); }
+  ~Context() { bp5_context_destroy(h); }
+  bp5_context_t h = nullptr;
+};
+}  // namespace b200
+
+// ------------------------------------------------------------------ mesh description
+template <int dim> struct Point {
+  std::array<double, dim> v{};
+  double &operator[](unsigned d) { return v[d]; }
+  double operator[](unsigned d) const { return v[d]; }
+};
+
+// what the drivers do to a parallel::distributed::Triangulation (bp5/step-64.cu:656-663)
+template <int dim> class Triangulation {
+ public:
+  void clear() { subdivisions.assign(dim, 1); refinements = 0; }
+  void refine_global(unsigned int n) { refinements += n; }
+  unsigned long long n_global_active_cells() const {
+    unsigned long long n = 1;
+    for (int d = 0; d < dim; ++d) n *= cells(d);
+    return n;
+  }
+  unsigned int cells(int d) const { return subdivisions[d] << refinements; }
+  std::vector<unsigned int> subdivisions = std::vector<unsigned int>(dim, 1);
+  Point<dim> p1, p2;
+  unsigned int refinements = 0;
+  // smooth deformation of the mesh (BASELINE config 5; not in the reference)
+  int deformation = 0;
+  double deformation_eps = 0.0;
+};
+namespace parallel { namespace distributed { template <int dim> using Triangulation = dealii::Triangulation<dim>; } }
+
+namespace GridGenerator {
+template <int dim>
+void subdivided_hyper_rectangle(Triangulation<dim> &tria, const std::vector<unsigned int> &subdivisions,
+                                const Point<dim> &p1, const Point<dim> &p2) {
+  tria.subdivisions = subdivisions; tria.p1 = p1; tria.p2 = p2; tria.refinements = 0;
+}
+template <int dim> void hyper_cube(Triangulation<dim> &tria, double a = 0., double b = 1.) {
+  Point<dim> p1, p2;
+  for (int d = 0; d < dim; ++d) { p1[d] = a; p2[d] = b; }
+  subdivided_hyper_rectangle(tria, std::vector<unsigned int>(dim, 1), p1, p2);
+}
+}  // namespace GridGenerator
+
+template <int dim> struct FE_Q {
+  explicit FE_Q(unsigned int degree) : degree(degree), dofs_per_cell(1) {
+    for (int d = 0; d < dim; ++d) dofs_per_cell *= degree + 1;
+  }
+  unsigned int degree, dofs_per_cell;
+};
+
+template <int dim> class DoFHandler {
+ public:
+  explicit DoFHandler(const Triangulation<dim> &tria) : tria(&tria) {}
+  void distribute_dofs(const FE_Q<dim> &fe) { degree = fe.degree; }
+  unsigned long long n_dofs() const {
+    unsigned long long n = 1;
+    for (int d = 0; d < dim; ++d) n *= (unsigned long long)tria->cells(d) * degree + 1;
+    return n;
+  }
+  const Triangulation<dim> &get_triangulation() const { return *tria; }
+  unsigned int degree = 1;
+
+ private:
+  const Triangulation<dim> *tria;
+};
+
+// zero Dirichlet values on the whole boundary (boundary id 0), bp5/step-64.cu:351-358
+template <typename Number = double> struct AffineConstraints {
+  void clear() {}
+  void close() {}
+};
+
+// ------------------------------------------------------------------ vector
+namespace LinearAlgebra { namespace distributed {
+template <typename Number, typename MemorySpaceType = MemorySpace::CUDA> class Vector;
+
+template <> class Vector<double, MemorySpace::CUDA> {
+ public:
+  using value_type = double;
+  using size_type = types::global_dof_index;
+  Vector() = default;
+  Vector(const Vector &) = delete;
+  Vector &operator=(const Vector &) = delete;
+  ~Vector() { bp5_vector_destroy(h); }
+
+  void reinit(long long n_owned, long long n_ghost = 0) {
+    bp5_vector_destroy(h); h = nullptr;
+    b200::check(bp5_vector_create(b200::Context::get(), n_owned, n_ghost, &h));
+    constant = 0.0; is_constant = true;
+  }
+  void reinit(const Vector &other, bool = false) {          // solver.h:369-371, bp5/step-64.cu:367,431
+    bp5_vector_destroy(h); h = nullptr;
+    b200::check(bp5_vector_create_like(other.h, &h));
+    constant = 0.0; is_constant = true;
+  }
+  void adopt(bp5_vector_t handle) { bp5_vector_destroy(h); h = handle; constant = 0.0; is_constant = true; }
+  Vector &operator=(double s) { b200::check(bp5_vector_set(h, s)); constant = s; is_constant = true; return *this; }
+  double l2_norm() const { double v; b200::check(bp5_vector_norm_sqr_local(h, &v)); return std::sqrt(v); }
+  double operator*(const Vector &o) const { double v; b200::check(bp5_vector_dot_local(h, o.h, &v)); return v; }
+  bool all_zero() const { int z; b200::check(bp5_vector_all_zero_local(h, &z)); return z != 0; }
+  void add(double a, const Vector &v) { b200::check(bp5_vector_add(h, a, v.h)); is_constant = false; }
+  void equ(double a, const Vector &v) { b200::check(bp5_vector_equ(h, a, v.h)); is_constant = false; }
+  void sadd(double s, double a, const Vector &v) { b200::check(bp5_vector_sadd(h, s, a, v.h)); is_constant = false; }
+  void zero_out_ghosts() { b200::check(bp5_vector_zero_out_ghosts(h)); }
+  double *get_values() { is_constant = false; return bp5_vector_get_values(h); }
+  const double *get_values() const { return bp5_vector_get_values(h); }
+  size_type local_size() const { int64_t a = 0, g = 0; bp5_vector_local_size(h, &a, &g); return (size_type)a; }
+  size_type size() const { return local_size(); }
+  // import(ReadWriteVector, insert) / the reverse, bp5/step-64.cu:415-417,553-555
+  void import_from_host(const std::vector<double> &v) {
+    b200::check(bp5_vector_import_host(h, v.data(), (int64_t)v.size())); is_constant = false;
+  }
+  void copy_to_host(std::vector<double> &v) const {
+    v.resize(local_size());
+    b200::check(bp5_vector_export_host(h, v.data(), (int64_t)v.size()));
+  }
+  bp5_vector_t handle() const { return h; }
+  void mark_modified() { is_constant = false; }
+  bool is_constant_value(double s) const { return is_constant && constant == s; }
+
+ private:
+  bp5_vector_t h = nullptr;
+  double constant = 0.0;     // set by operator=(double) until the next modification
+  bool is_constant = false;
+};
+} }  // namespace LinearAlgebra::distributed
+
+template <typename VectorType> class DiagonalMatrix {
+ public:
+  VectorType &get_vector() { return diagonal; }
+  const VectorType &get_vector() const { return diagonal; }
+
+ private:
+  VectorType diagonal;
+};
+
+// ------------------------------------------------------------------ operators
+namespace b200 {
+template <int dim, int fe_degree, int operator_kind> class MatrixFreeOperator {
+  static_assert(dim == 3, "the hot path is three-dimensional");
+ public:
+  using VectorType = LinearAlgebra::distributed::Vector<double, MemorySpace::CUDA>;
+  MatrixFreeOperator(const DoFHandler<dim> &dof_handler, const AffineConstraints<double> &, int quadrature)
+      : do_zero_out(true) {
+    const Triangulation<dim> &t = dof_handler.get_triangulation();
+    bp5_problem_t pr{};
+    pr.degree = fe_degree; pr.quadrature = quadrature; pr.operator_kind = operator_kind;
+    pr.geometry_mode = BP5_GEOM_STORED;
+    for (int d = 0; d < 3; ++d) {
+      pr.cells[d] = (int32_t)t.cells(d); pr.lower[d] = t.p1[d]; pr.upper[d] = t.p2[d];
+      pr.part_grid[d] = 1; pr.part_coord[d] = 0;
+    }
+    pr.deformation = t.deformation; pr.deformation_eps = t.deformation_eps;
+    check(bp5_operator_create(Context::get(), &pr, &h));
+  }
+  MatrixFreeOperator(const MatrixFreeOperator &) = delete;
+  ~MatrixFreeOperator() { bp5_operator_destroy(h); }
+
+  void vmult(VectorType &dst, const VectorType &src) const {       // bp5/step-64.cu:263-276
+    check(bp5_operator_set_zero_out(h, do_zero_out));
+    check(bp5_operator_vmult(h, dst.handle(), src.handle()));
+    dst.mark_modified();
+  }
+  void initialize_dof_vector(VectorType &vec) const {             // bp5/step-64.cu:210-215
+    bp5_vector_t v = nullptr;
+    check(bp5_operator_initialize_dof_vector(h, &v));
+    vec.adopt(v);
+  }
+  // assemble_rhs of the drivers (bp5/step-64.cu:372-418), done on the device
+  void assemble_rhs(VectorType &b) const { check(bp5_operator_assemble_rhs(h, b.handle())); b.mark_modified(); }
+  bp5_operator_t handle() const { return h; }
+
+ private:
+  bp5_operator_t h = nullptr;
+
+ public:
+  bool do_zero_out;                                               // bp5/step-64.cu:223
+};
+}  // namespace b200
+
+// ------------------------------------------------------------------ solvers
+namespace b200 {
+template <typename VectorType, int variant> class SolverCGBase {
+ public:
+  explicit SolverCGBase(SolverControl &cn) : control(cn) {}
+  virtual ~SolverCGBase() = default;
+  template <typename MatrixType, typename PreconditionerType>
+  void solve(const MatrixType &A, VectorType &x, const VectorType &b, const PreconditionerType &preconditioner) {
+    // the reference passes a DiagonalMatrix of ones (bp5/step-64.cu:428-432) and reads it in every
+    // pass; an all-ones diagonal is recognised and not read at all
+    const VectorType &diag = preconditioner.get_vector();
+    bp5_vector_t dh = diag.is_constant_value(1.0) ? nullptr : diag.handle();
+    check(bp5_operator_set_zero_out(A.handle(), A.do_zero_out));
+    int its = 0;
+    double val = 0.0;
+    const int rc = bp5_cg_solve(A.handle(), x.handle(), b.handle(), dh, variant, control.abi_kind(),
+                                control.tolerance(), (int)control.max_steps(), &its, &val, nullptr, 0);
+    control.record((unsigned)its, val);
+    x.mark_modified();
+    if (rc == BP5_ERR_NO_CONVERGENCE) throw SolverControl::NoConvergence((unsigned)its, val);   // solver.h:539-540
+    check(rc);
+  }
+
+ protected:
+  SolverControl &control;
+};
+}  // namespace b200
+
+// dealii::SolverCG as the drivers use it ("pcg-standard", bp5/step-64.cu:446-453)
+template <typename VectorType> class SolverCG : public b200::SolverCGBase<VectorType, BP5_CG_STANDARD> {
+ public:
+  using b200::SolverCGBase<VectorType, BP5_CG_STANDARD>::SolverCGBase;
+};
+// SolverCGFullMerge (bp5/solver.h:15-31), "pcg-merged"
+template <typename VectorType> class SolverCGFullMerge : public b200::SolverCGBase<VectorType, BP5_CG_MERGED> {
+ public:
+  using b200::SolverCGBase<VectorType, BP5_CG_MERGED>::SolverCGBase;
+};
+
+// ------------------------------------------------------------------ small utilities of the drivers
+class Timer {
+ public:
+  Timer() : t0(std::chrono::steady_clock::now()) {}
+  double wall_time() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+
+ private:
+  std::chrono::steady_clock::time_point t0;
+};
+
+class ConditionalOStream {
+ public:
+  ConditionalOStream(std::ostream &os, bool active) : os(os), active(active) {}
+  template <typename T> const ConditionalOStream &operator<<(const T &t) const { if (active) os << t; return *this; }
+  const ConditionalOStream &operator<<(std::ostream &(*f)(std::ostream &)) const { if (active) os << f; return *this; }
+
+ private:
+  std::ostream &os;
+  bool active;
+};
+
+}  // namespace dealii
+
+// ------------------------------------------------------------------ the two operators of the reference
+namespace BP5 {
+// quadrature: BP5_QUAD_GAUSS is the reference default, BP5_QUAD_GLL its COLLOCATION switch (bp5/step-64.cu:48,243-247)
+template <int dim, int fe_degree>
+class PoissonOperator : public dealii::b200::MatrixFreeOperator<dim, fe_degree, BP5_OP_POISSON> {
+ public:
+  PoissonOperator(const dealii::DoFHandler<dim> &dof_handler, const dealii::AffineConstraints<double> &constraints,
+                  int quadrature = BP5_QUAD_GAUSS)
+      : dealii::b200::MatrixFreeOperator<dim, fe_degree, BP5_OP_POISSON>(dof_handler, constraints, quadrature) {}
+};
+}  // namespace BP5
+
+namespace Step64 {
+template <int dim, int fe_degree>
+class HelmholtzOperator : public dealii::b200::MatrixFreeOperator<dim, fe_degree, BP5_OP_HELMHOLTZ> {
+ public:
+  HelmholtzOperator(const dealii::DoFHandler<dim> &dof_handler, const dealii::AffineConstraints<double> &constraints)
+      : dealii::b200::MatrixFreeOperator<dim, fe_degree, BP5_OP_HELMHOLTZ>(dof_handler, constraints, BP5_QUAD_GAUSS) {
+    this->do_zero_out = true;                                       // step-64/step-64.cu:316 (dst = 0.)
+  }
+};
+}  // namespace Step64

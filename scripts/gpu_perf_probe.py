@@ -19,7 +19,7 @@ for p in degrees:
         src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
         src.import_host(np.random.default_rng(0).standard_normal(n))
         bytes_v, bytes_cg = op.algorithmic_bytes()
-        for _ in range(3): op.vmult(dst, src)
+        for _ in range(3): op.vmult(dst, src); op.cell_loop(dst, src)
         ctx.synchronize()
         reps = 10
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -1,0 +1,50 @@
+"""-m gpu: the host-only C++ drivers written against the dealii_b200 facade (examples/), i.e. the
+reference's own experiment through the C ABI: BP5 ladder cycles 7-8 at degree 5 (bp5/step-64.cu:724-730)
+and the step-64 Helmholtz tutorial run."""
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")], stdout=subprocess.DEVNULL)
+
+
+def test_bp5_driver_reproduces_ladder_fixture():
+    _build()
+    gold = json.load(open(os.path.join(GOLD, "bp5_ladder_p5.json")))
+    for quad in ("gauss", "gll"):
+        out = subprocess.run([os.path.join(ROOT, "build", "examples", "bp5_step64"), "--degree", "5", "--cycle-min", "7",
+                              "--cycle-max", "8", "--repetitions", "2", "--quadrature", quad],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        text = out.stdout
+        for tag in ("pcg-standard", "pcg-merged", "vmult"):
+            assert len(re.findall(rf"^{tag} \d+ [0-9.e+]+$", text, flags=re.M)) == 2, text[-1500:]
+        blocks = text.split("Cycle ")[1:]
+        for blk, cyc in zip(blocks, (7, 8)):
+            g = gold[f"cycle{cyc}_{quad}"]
+            assert f"Number of degrees of freedom: {g['n_dofs']}" in blk
+            solved = re.findall(r"Solved in (\d+) iterations with time \S+ and DoFs/s \S+ norm (\S+)", blk)
+            assert len(solved) == 4            # 2 repetitions x (standard, merged)
+            for its, norm in solved:
+                assert abs(int(its) - g["its_merged"]) <= 1
+                assert float(norm) == pytest.approx(g["x_l2"], rel=1e-5)
+
+
+def test_step64_driver_reproduces_tutorial_iterations():
+    _build()
+    out = subprocess.run([os.path.join(ROOT, "build", "examples", "step64_helmholtz"), "2"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    its = [int(v) for v in re.findall(r"Solved in (\d+) iterations", out.stdout)]
+    assert len(its) == 4                        # (SolverCG, merged) x 2 cycles
+    for got, ref in zip(its, (27, 60, 27, 60)):  # deal.II step-64 tutorial: 343 DoFs -> 27, 2197 -> 60
+        assert abs(got - ref) <= 1
