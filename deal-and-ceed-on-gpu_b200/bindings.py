@@ -80,6 +80,7 @@ ABI = [
     ("bp5_context_launch_count", C.c_int64, [_vp]),
     ("bp5_vector_create", C.c_int, [_vp, C.c_int64, C.c_int64, C.POINTER(_vp)]),
     ("bp5_vector_create_like", C.c_int, [_vp, C.POINTER(_vp)]),
+    ("bp5_vector_owner", _vp, [_vp]),
     ("bp5_vector_destroy", C.c_int, [_vp]),
     ("bp5_vector_local_size", C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("bp5_vector_get_values", _vp, [_vp]),
@@ -90,6 +91,7 @@ ABI = [
     ("bp5_vector_add", C.c_int, [_vp, C.c_double, _vp]),
     ("bp5_vector_equ", C.c_int, [_vp, C.c_double, _vp]),
     ("bp5_vector_sadd", C.c_int, [_vp, C.c_double, C.c_double, _vp]),
+    ("bp5_vector_scale", C.c_int, [_vp, _vp]),
     ("bp5_vector_dot_local", C.c_int, [_vp, _vp, _dp]),
     ("bp5_vector_norm_sqr_local", C.c_int, [_vp, _dp]),
     ("bp5_vector_all_zero_local", C.c_int, [_vp, C.POINTER(C.c_int)]),
@@ -98,6 +100,7 @@ ABI = [
                                _dp, C.c_int]),
     ("bp5_cg_solve_host", C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.POINTER(C.c_int), _dp]),
+    ("bp5_operator_matrix_free_data", C.c_int, [_vp, _vp]),
     ("bp5_operator_halo_info", C.c_int, [_vp] + [C.POINTER(C.c_int64)] * 4),
     ("bp5_operator_halo_pack", C.c_int, [_vp, _vp, _vp]),
     ("bp5_operator_halo_unpack_add", C.c_int, [_vp, _vp, _vp]),

@@ -156,6 +156,8 @@ int bp5_operator_destroy(bp5_operator_t op) {
   cudaFree(op->cell_base);
   cudaFree(op->l2g_irr);
   cudaFree(op->skel_mask);
+  cudaFree(op->mf_l2g); cudaFree(op->mf_constraint_mask); cudaFree(op->mf_inv_jacobian);
+  cudaFree(op->mf_jxw); cudaFree(op->mf_q_points);
   cudaFree(op->metric);
   cudaFree(op->constrained);
   cudaFree(op->cg_scalars);
@@ -180,7 +182,9 @@ int bp5_operator_sizes(bp5_operator_t op, int64_t *n_owned, int64_t *n_ghost, in
 
 int bp5_operator_initialize_dof_vector(bp5_operator_t op, bp5_vector_t *vec) {
   BP5_REQUIRE(op && vec, "null argument");
-  return bp5_vector_create(op->ctx, op->n_owned, op->n_ghost, vec);
+  const int rc = bp5_vector_create(op->ctx, op->n_owned, op->n_ghost, vec);
+  if (rc == BP5_OK) (*vec)->owner = op;
+  return rc;
 }
 
 int bp5_operator_set_zero_out(bp5_operator_t op, int z) {
@@ -349,8 +353,12 @@ int bp5_vector_create(bp5_context_t ctx, int64_t n_owned, int64_t n_ghost, bp5_v
 
 int bp5_vector_create_like(bp5_vector_t other, bp5_vector_t *out) {
   BP5_REQUIRE(other, "null vector");
-  return bp5_vector_create(other->ctx, other->n_owned, other->n_ghost, out);
+  const int rc = bp5_vector_create(other->ctx, other->n_owned, other->n_ghost, out);
+  if (rc == BP5_OK) (*out)->owner = other->owner;
+  return rc;
 }
+
+bp5_operator_t bp5_vector_owner(bp5_vector_t v) { return v ? v->owner : nullptr; }
 
 int bp5_vector_destroy(bp5_vector_t v) {
   if (!v) return BP5_OK;
@@ -427,6 +435,12 @@ int bp5_vector_sadd(bp5_vector_t y, double s, double a, bp5_vector_t x) {
   BP5_CUDA(cudaSetDevice(y->ctx->device));
   return vec_axpy(y->ctx, y->d, s, a, x->d, y->n_owned, 2);
 }
+int bp5_vector_scale(bp5_vector_t y, bp5_vector_t x) {
+  int rc;
+  if ((rc = same_layout(y, x))) return rc;
+  BP5_CUDA(cudaSetDevice(y->ctx->device));
+  return vec_axpy(y->ctx, y->d, 1.0, 1.0, x->d, y->n_owned, 3);
+}
 int bp5_vector_dot_local(bp5_vector_t x, bp5_vector_t y, double *out) {
   int rc;
   if ((rc = same_layout(x, y))) return rc;
@@ -480,6 +494,34 @@ int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, i
   BP5_ABI_GUARD_END
 }
 
+
+// ------------------------------------------------- user-written cell functors
+int bp5_operator_matrix_free_data(bp5_operator_t op, bp5_matrix_free_data_t *out) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && out, "null argument");
+  BP5_REQUIRE(op->n_ghost == 0, "the generic functor path handles a single block");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  int rc;
+  if ((rc = operator_generic_data(op))) return rc;
+  std::memset(out, 0, sizeof(*out));
+  out->q_points = op->mf_q_points;
+  out->local_to_global = op->mf_l2g;
+  out->inv_jacobian = op->mf_inv_jacobian;
+  out->JxW = op->mf_jxw;
+  out->constraint_mask = op->mf_constraint_mask;
+  out->n_cells = (unsigned int)op->n_cells;
+  out->padding_length = (unsigned int)op->mf_padding;
+  out->n_q_points_1d = op->n;
+  out->collocation = op->prob.quadrature == BP5_QUAD_GLL;
+  for (int q = 0; q < op->n; ++q)
+    for (int i = 0; i < op->n; ++i) {
+      out->shape_values[q * op->n + i] = op->tab.B[q * op->n + i];
+      out->shape_gradients[q * op->n + i] = op->tab.Dg[q * op->n + i];
+      out->co_shape_gradients[q * op->n + i] = op->tab.Dt[q * op->n + i];
+    }
+  return BP5_OK;
+  BP5_ABI_GUARD_END
+}
 
 // ------------------------------------------------- partitioned meshes: halo + stepwise CG
 int bp5_operator_halo_info(bp5_operator_t op, int64_t *send_count, int64_t *send_offset, int64_t *recv_count,

@@ -87,6 +87,7 @@ struct bp5_vector_s {
   bp5_context_t ctx = nullptr;
   int64_t n_owned = 0, n_ghost = 0;
   double *d = nullptr;
+  bp5_operator_t owner = nullptr;   // operator whose initialize_dof_vector made it (its "partitioner"), or null
 };
 
 struct bp5_operator_s {
@@ -112,6 +113,10 @@ struct bp5_operator_s {
                                 // k*od0*od1), < 0: -(slot+1) into l2g_irr, INT_MIN: padding cell
   int *l2g_irr = nullptr;       // [n_irregular][n^3] explicit local dof indices (cells touching lower ghost layers)
   int64_t n_irregular = 0;
+  // deal.II-layout arrays for user-written cell functors (built on first request)
+  unsigned int *mf_l2g = nullptr, *mf_constraint_mask = nullptr;
+  double *mf_inv_jacobian = nullptr, *mf_jxw = nullptr, *mf_q_points = nullptr;
+  int mf_padding = 0;
   uint32_t *skel_mask = nullptr; // bit i set: owned dof i is shared by more than one cell (skeleton)
   double *metric = nullptr;     // [tile][cpt][planes][n^3]; planes: 6 (Poisson) or 7 (Helmholtz: + a*JxW)
   int metric_planes = 6;
@@ -138,6 +143,7 @@ namespace bp5 {
 int operator_setup_device(bp5_operator_t op);
 int operator_assemble_rhs(bp5_operator_t op, double *b_dev);
 int operator_l2_norm_sqr(bp5_operator_t op, const double *u_dev, double *out);
+int operator_generic_data(bp5_operator_t op);
 int operator_export_coefficients(bp5_operator_t op, double *host_out);
 int operator_export_coords(bp5_operator_t op, double *host_out);
 int operator_export_global_indices(bp5_operator_t op, int64_t *host_out);

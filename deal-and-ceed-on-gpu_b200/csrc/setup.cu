@@ -362,6 +362,74 @@ static int dof_info(bp5_operator_t op, double *xyz_host, int64_t *gidx_host) {
 int operator_export_coords(bp5_operator_t op, double *host_out) { return dof_info(op, host_out, nullptr); }
 int operator_export_global_indices(bp5_operator_t op, int64_t *host_out) { return dof_info(op, nullptr, host_out); }
 
+// ---------------------------------------------------------------------------
+// deal.II-layout geometry for user-written cell functors (CUDAWrappers::MatrixFree::Data as
+// the reference's functors index it):
+//   inv_jacobian[(d*3+e)*n_cells*pad + cell*pad + q]   bp5/step-64.cu:94-97, fe_evaluation_gl.h:340,365
+//   JxW[cell*pad + q]                                   bp5/step-64.cu:109, fe_evaluation_gl.h:299
+//   local_to_global[cell*pad + i]                       fe_evaluation_gl.h:118,144
+//   q_points[cell*pad + q] (3 doubles each)             step-64/step-64.cu:105-108
+// pad = next power of two >= n^3 (padding_length).
+__global__ void generic_data_kernel(BlockGeom g, int pad, unsigned int *__restrict__ l2g, double *__restrict__ inv_jac,
+                                    double *__restrict__ jxw, double *__restrict__ qpts) {
+  extern __shared__ double sm[];
+  const int n = g.n, n2 = n * n, n3 = n2 * n;
+  const long long cell = blockIdx.x;
+  const long long n_cells = gridDim.x;
+  const int lcx = cell % g.lc[0], lcy = (cell / g.lc[0]) % g.lc[1], lcz = cell / ((long long)g.lc[0] * g.lc[1]);
+  const int t = threadIdx.x;
+  const int i = t % n, j = (t / n) % n, k = t / n2;
+  if (t < n3) l2g[cell * pad + t] = (unsigned int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
+  double J[3][3], xr[3];
+  cell_jacobian(g, c_tab.B, c_tab.Dg, sm, g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz, J, xr);
+  if (t >= n3) return;
+  const double det = det3(J), id = 1.0 / det;
+  double I[3][3];
+  I[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * id;
+  I[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+  I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+  I[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * id;
+  I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+  I[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+  I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * id;
+  I[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+  I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+  const long long plane = n_cells * pad, at = cell * pad + t;
+  for (int d = 0; d < 3; ++d)
+    for (int e = 0; e < 3; ++e) inv_jac[(d * 3 + e) * plane + at] = I[d][e];
+  jxw[at] = det * c_tab.wq[i] * c_tab.wq[j] * c_tab.wq[k];
+  for (int d = 0; d < 3; ++d) qpts[3 * at + d] = xr[d];
+}
+
+int operator_generic_data(bp5_operator_t op) {
+  if (op->mf_l2g) return BP5_OK;
+  bp5_context_t ctx = op->ctx;
+  const int n = op->n, n3 = n * n * n;
+  int pad = 1;
+  while (pad < n3) pad <<= 1;
+  op->mf_padding = pad;
+  const size_t cells = (size_t)op->n_cells;
+  BP5_CUDA(cudaMalloc(&op->mf_l2g, sizeof(unsigned int) * cells * pad));
+  BP5_CUDA(cudaMalloc(&op->mf_inv_jacobian, sizeof(double) * 9 * cells * pad));
+  BP5_CUDA(cudaMalloc(&op->mf_jxw, sizeof(double) * cells * pad));
+  BP5_CUDA(cudaMalloc(&op->mf_q_points, sizeof(double) * 3 * cells * pad));
+  BP5_CUDA(cudaMalloc(&op->mf_constraint_mask, sizeof(unsigned int) * cells));
+  BP5_CUDA(cudaMemsetAsync(op->mf_l2g, 0, sizeof(unsigned int) * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->mf_inv_jacobian, 0, sizeof(double) * 9 * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->mf_jxw, 0, sizeof(double) * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->mf_q_points, 0, sizeof(double) * 3 * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->mf_constraint_mask, 0, sizeof(unsigned int) * cells, ctx->stream));   // conforming mesh
+  const BlockGeom g = make_geom(op);
+  BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = ((n3 + 31) / 32) * 32;
+  generic_data_kernel<<<(unsigned)op->n_cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
+      g, pad, op->mf_l2g, op->mf_inv_jacobian, op->mf_jxw, op->mf_q_points);
+  BP5_CHECK_LAUNCH();
+  ctx->launches++;
+  BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BP5_OK;
+}
+
 int operator_l2_norm_sqr(bp5_operator_t, const double *, double *) {
   set_error("l2 norm with QGauss(p+2) not implemented yet");
   return BP5_ERR_UNSUPPORTED;

@@ -16,13 +16,14 @@ __global__ void fill_kernel(double *__restrict__ d, long long n, double v) {
     d[i] = v;
 }
 
-// mode 0: y += a x ; 1: y = a x ; 2: y = s y + a x
+// mode 0: y += a x ; 1: y = a x ; 2: y = s y + a x ; 3: y = y .* x
 template <int MODE>
 __global__ void axpy_kernel(double *__restrict__ y, double s, double a, const double *__restrict__ x, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (MODE == 0) y[i] += a * x[i];
     else if (MODE == 1) y[i] = a * x[i];
-    else y[i] = s * y[i] + a * x[i];
+    else if (MODE == 2) y[i] = s * y[i] + a * x[i];
+    else y[i] *= x[i];
   }
 }
 
@@ -95,7 +96,8 @@ int vec_axpy(bp5_context_t ctx, double *y, double s, double a, const double *x, 
   const unsigned g = grid_for(n, 256, 148 * 16);
   if (mode == 0) axpy_kernel<0><<<g, 256, 0, ctx->stream>>>(y, s, a, x, n);
   else if (mode == 1) axpy_kernel<1><<<g, 256, 0, ctx->stream>>>(y, s, a, x, n);
-  else axpy_kernel<2><<<g, 256, 0, ctx->stream>>>(y, s, a, x, n);
+  else if (mode == 2) axpy_kernel<2><<<g, 256, 0, ctx->stream>>>(y, s, a, x, n);
+  else axpy_kernel<3><<<g, 256, 0, ctx->stream>>>(y, s, a, x, n);
   BP5_CHECK_LAUNCH();
   ctx->launches++;
   return BP5_OK;

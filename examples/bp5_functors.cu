@@ -1,0 +1,369 @@
+// The reference's operators, written the way the reference writes them -- as device functors on
+// CUDAWrappers::MatrixFree / FEEvaluationGL -- and compiled against this library's re-creation of
+// that interface (include/dealii_b200/cuda_matrix_free.cuh):
+//
+//   UserBP5::JacobianFunctor, LocalPoissonOperator, PoissonOperator   after bp5/step-64.cu:60-276
+//   UserStep64::VaryingCoefficientFunctor, HelmholtzOperatorQuad,
+//               LocalHelmholtzOperator, HelmholtzOperator             after step-64/step-64.cu:69-322
+//
+// The program applies each user-written operator and the library's tuned operator
+// (BP5::PoissonOperator / Step64::HelmholtzOperator, csrc/apply.cuh) to the same vectors, solves
+// with SolverCGFullMerge around both, and prints norms that tests/test_gpu_functor_api.py compares
+// with the CPU oracle.
+//
+//   bp5_functors <degree 2..6> <gauss|gll> <cells_x> <cells_y> <cells_z> <deformation eps> [cell edge = 1]
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+
+#include "dealii_b200/cuda_matrix_free.cuh"
+
+using namespace dealii;
+using VectorType = LinearAlgebra::distributed::Vector<double, MemorySpace::CUDA>;
+
+namespace UserBP5 {
+// merged coefficient G = JxW * J^-1 J^-T, upper triangle in planes xx,yy,zz,xy,xz,yz
+template <int dim, int fe_degree> class JacobianFunctor {
+ public:
+  JacobianFunctor(double *coefficient, const unsigned int n_cells) : coef(coefficient), n_cells(n_cells) {}
+  __device__ void operator()(const unsigned int cell, const typename CUDAWrappers::MatrixFree<dim, double>::Data *gpu_data);
+  static const unsigned int n_dofs_1d = fe_degree + 1;
+  static const unsigned int n_q_points = Utilities::pow(n_dofs_1d, dim);
+
+ private:
+  double *coef;
+  const unsigned int n_cells;
+};
+
+template <int dim, int fe_degree>
+__device__ void JacobianFunctor<dim, fe_degree>::operator()(
+    const unsigned int cell, const typename CUDAWrappers::MatrixFree<dim, double>::Data *gpu_data) {
+  const unsigned int q = CUDAWrappers::q_point_id_in_cell<dim>(fe_degree + 1);
+  const std::size_t plane = (std::size_t)gpu_data->n_cells * gpu_data->padding_length;
+  const std::size_t at = (std::size_t)cell * gpu_data->padding_length + q;
+  Tensor<2, dim> inv_jac;
+  for (unsigned int d = 0; d < dim; ++d)
+    for (unsigned int e = 0; e < dim; ++e) inv_jac[d][e] = gpu_data->inv_jacobian[at + plane * (d * dim + e)];
+  const double JxW = gpu_data->JxW[at];
+  const std::size_t stride = (std::size_t)n_cells * n_q_points, out = (std::size_t)cell * n_q_points + q;
+  unsigned int c = dim;
+  for (unsigned int d = 0; d < dim; ++d)
+    for (unsigned int e = d; e < dim; ++e) {
+      double sum = 0.;
+      for (unsigned int f = 0; f < dim; ++f) sum += inv_jac[d][f] * inv_jac[e][f];
+      coef[out + (d == e ? d : c++) * stride] = JxW * sum;
+    }
+}
+
+template <int dim, int fe_degree> class LocalPoissonOperator {
+ public:
+  LocalPoissonOperator(double *coefficient, const unsigned int n_cells) : n_cells(n_cells), coef(coefficient) {}
+  __device__ void operator()(const unsigned int cell, const typename CUDAWrappers::MatrixFree<dim, double>::Data *gpu_data,
+                             CUDAWrappers::SharedData<dim, double> *shared_data, const double *src, double *dst) const;
+  static const unsigned int n_dofs_1d = fe_degree + 1;
+  static const unsigned int n_local_dofs = Utilities::pow(fe_degree + 1, dim);
+  static const unsigned int n_q_points = Utilities::pow(fe_degree + 1, dim);
+
+ private:
+  const unsigned int n_cells;
+  double *coef;
+};
+
+template <int dim, int fe_degree>
+__device__ void LocalPoissonOperator<dim, fe_degree>::operator()(
+    const unsigned int cell, const typename CUDAWrappers::MatrixFree<dim, double>::Data *gpu_data,
+    CUDAWrappers::SharedData<dim, double> *shared_data, const double *src, double *dst) const {
+  CUDAWrappers::FEEvaluationGL<dim, fe_degree, fe_degree + 1, 1, double> fe_eval(cell, gpu_data, shared_data);
+  fe_eval.read_dof_values(src);
+  fe_eval.evaluate(false, true);
+  // g <- G g with THIS cell's metric (the shipped kernel reads cell 0's, bp5/step-64.cu:161-177)
+  const std::size_t offset = (std::size_t)n_q_points * n_cells;
+  const unsigned int q = CUDAWrappers::internal::compute_index<dim, fe_degree + 1>();
+  const double *G = coef + (std::size_t)cell * n_q_points + q;
+  const double g0 = shared_data->gradients[0][q], g1 = shared_data->gradients[1][q], g2 = shared_data->gradients[2][q];
+  shared_data->gradients[0][q] = g0 * G[0] + g1 * G[3 * offset] + g2 * G[4 * offset];
+  shared_data->gradients[1][q] = g0 * G[3 * offset] + g1 * G[1 * offset] + g2 * G[5 * offset];
+  shared_data->gradients[2][q] = g0 * G[4 * offset] + g1 * G[5 * offset] + g2 * G[2 * offset];
+  __syncthreads();
+  fe_eval.integrate(false, true);
+  fe_eval.distribute_local_to_global(dst);
+}
+
+// the non-merged branch of the reference (#else at bp5/step-64.cu:189-191): J^-1 and JxW at every point
+template <int dim, int fe_degree> class LocalPoissonOperatorPlain {
+ public:
+  __device__ void operator()(const unsigned int cell, const typename CUDAWrappers::MatrixFree<dim, double>::Data *gpu_data,
+                             CUDAWrappers::SharedData<dim, double> *shared_data, const double *src, double *dst) const {
+    CUDAWrappers::FEEvaluationGL<dim, fe_degree, fe_degree + 1, 1, double> fe_eval(cell, gpu_data, shared_data);
+    fe_eval.read_dof_values(src);
+    fe_eval.evaluate(false, true);
+    fe_eval.submit_gradient(fe_eval.get_gradient());
+    __syncthreads();
+    fe_eval.integrate(false, true);
+    fe_eval.distribute_local_to_global(dst);
+  }
+  static const unsigned int n_dofs_1d = fe_degree + 1;
+  static const unsigned int n_local_dofs = Utilities::pow(fe_degree + 1, dim);
+  static const unsigned int n_q_points = Utilities::pow(fe_degree + 1, dim);
+};
+
+template <int dim, int fe_degree> class PoissonOperator {
+ public:
+  PoissonOperator(const DoFHandler<dim> &dof_handler, const AffineConstraints<double> &constraints, bool collocation);
+  void vmult(VectorType &dst, const VectorType &src) const;
+  void vmult_plain(VectorType &dst, const VectorType &src) const;
+  void initialize_dof_vector(VectorType &vec) const { mf_data.initialize_dof_vector(vec); }
+  const double *coefficients() const { return coef.get_values(); }
+  std::size_t n_coefficients() const { return coef.size(); }
+
+ private:
+  CUDAWrappers::MatrixFree<dim, double> mf_data;
+  LinearAlgebra::CUDAWrappers::Vector<double> coef;
+  unsigned int n_owned_cells;
+
+ public:
+  bool do_zero_out;
+};
+
+template <int dim, int fe_degree>
+PoissonOperator<dim, fe_degree>::PoissonOperator(const DoFHandler<dim> &dof_handler,
+                                                 const AffineConstraints<double> &constraints, bool collocation)
+    : do_zero_out(true) {
+  MappingQGeneric<dim> mapping(fe_degree);
+  typename CUDAWrappers::MatrixFree<dim, double>::AdditionalData additional_data;
+  additional_data.mapping_update_flags = update_values | update_gradients | update_JxW_values | update_quadrature_points;
+  additional_data.overlap_communication_computation = true;
+  if (collocation) mf_data.reinit(mapping, dof_handler, constraints, QGaussLobatto<1>(fe_degree + 1), additional_data);
+  else mf_data.reinit(mapping, dof_handler, constraints, QGauss<1>(fe_degree + 1), additional_data);
+  n_owned_cells =
+      dynamic_cast<const parallel::Triangulation<dim> *>(&dof_handler.get_triangulation())->n_locally_owned_active_cells();
+  coef.reinit(Utilities::pow(fe_degree + 1, dim) * n_owned_cells * dim * (dim + 1) / 2);
+  const JacobianFunctor<dim, fe_degree> functor(coef.get_values(), n_owned_cells);
+  mf_data.evaluate_coefficients(functor);
+}
+
+template <int dim, int fe_degree> void PoissonOperator<dim, fe_degree>::vmult(VectorType &dst, const VectorType &src) const {
+  if (do_zero_out) dst = 0.;
+  LocalPoissonOperator<dim, fe_degree> local_poisson_operator(coef.get_values(), n_owned_cells);
+  mf_data.cell_loop(local_poisson_operator, src, dst);
+  mf_data.copy_constrained_values(src, dst);
+}
+template <int dim, int fe_degree>
+void PoissonOperator<dim, fe_degree>::vmult_plain(VectorType &dst, const VectorType &src) const {
+  if (do_zero_out) dst = 0.;
+  mf_data.cell_loop(LocalPoissonOperatorPlain<dim, fe_degree>(), src, dst);
+  mf_data.copy_constrained_values(src, dst);
+}
+}  // namespace UserBP5
+
+namespace UserStep64 {
+template <int dim, int fe_degree> class VaryingCoefficientFunctor {
+ public:
+  VaryingCoefficientFunctor(double *coefficient) : coef(coefficient) {}
+  __device__ void operator()(const unsigned int cell, const typename CUDAWrappers::MatrixFree<dim, double>::Data *gpu_data) {
+    const unsigned int pos = CUDAWrappers::local_q_point_id<dim, double>(cell, gpu_data, n_dofs_1d, n_q_points);
+    const Point<dim> q_point = CUDAWrappers::get_quadrature_point<dim, double>(cell, gpu_data, n_dofs_1d);
+    double p_square = 0.;
+    for (unsigned int i = 0; i < dim; ++i) p_square += q_point[i] * q_point[i];
+    coef[pos] = 10. / (0.05 + 2. * p_square);        // a(x), step-64/step-64.cu:100-118
+  }
+  static const unsigned int n_dofs_1d = fe_degree + 1;
+  static const unsigned int n_local_dofs = Utilities::pow(n_dofs_1d, dim);
+  static const unsigned int n_q_points = Utilities::pow(n_dofs_1d, dim);
+
+ private:
+  double *coef;
+};
+
+template <int dim, int fe_degree> class HelmholtzOperatorQuad {
+ public:
+  __device__ HelmholtzOperatorQuad(double coef) : coef(coef) {}
+  __device__ void operator()(CUDAWrappers::FEEvaluation<dim, fe_degree> *fe_eval, const unsigned int q) const {
+    fe_eval->submit_value(coef * fe_eval->get_value(q), q);
+    fe_eval->submit_gradient(fe_eval->get_gradient(q), q);
+  }
+
+ private:
+  double coef;
+};
+
+template <int dim, int fe_degree> class LocalHelmholtzOperator {
+ public:
+  LocalHelmholtzOperator(double *coefficient) : coef(coefficient) {}
+  __device__ void operator()(const unsigned int cell, const typename CUDAWrappers::MatrixFree<dim, double>::Data *gpu_data,
+                             CUDAWrappers::SharedData<dim, double> *shared_data, const double *src, double *dst) const {
+    const unsigned int pos = CUDAWrappers::local_q_point_id<dim, double>(cell, gpu_data, n_dofs_1d, n_q_points);
+    CUDAWrappers::FEEvaluation<dim, fe_degree, fe_degree + 1, 1, double> fe_eval(cell, gpu_data, shared_data);
+    fe_eval.read_dof_values(src);
+    fe_eval.evaluate(true, true);
+    fe_eval.apply_quad_point_operations(HelmholtzOperatorQuad<dim, fe_degree>(coef[pos]));
+    fe_eval.integrate(true, true);
+    fe_eval.distribute_local_to_global(dst);
+  }
+  static const unsigned int n_dofs_1d = fe_degree + 1;
+  static const unsigned int n_local_dofs = Utilities::pow(fe_degree + 1, dim);
+  static const unsigned int n_q_points = Utilities::pow(fe_degree + 1, dim);
+
+ private:
+  double *coef;
+};
+
+template <int dim, int fe_degree> class HelmholtzOperator {
+ public:
+  HelmholtzOperator(const DoFHandler<dim> &dof_handler, const AffineConstraints<double> &constraints) {
+    MappingQGeneric<dim> mapping(fe_degree);
+    typename CUDAWrappers::MatrixFree<dim, double>::AdditionalData additional_data;
+    additional_data.mapping_update_flags = update_values | update_gradients | update_JxW_values | update_quadrature_points;
+    const QGauss<1> quad(fe_degree + 1);
+    mf_data.reinit(mapping, dof_handler, constraints, quad, additional_data);
+    const unsigned int n_owned_cells =
+        dynamic_cast<const parallel::Triangulation<dim> *>(&dof_handler.get_triangulation())->n_locally_owned_active_cells();
+    coef.reinit(Utilities::pow(fe_degree + 1, dim) * n_owned_cells);
+    const VaryingCoefficientFunctor<dim, fe_degree> functor(coef.get_values());
+    mf_data.evaluate_coefficients(functor);
+  }
+  void vmult(VectorType &dst, const VectorType &src) const {
+    dst = 0.;
+    LocalHelmholtzOperator<dim, fe_degree> helmholtz_operator(coef.get_values());
+    mf_data.cell_loop(helmholtz_operator, src, dst);
+    mf_data.copy_constrained_values(src, dst);
+  }
+  void initialize_dof_vector(VectorType &vec) const { mf_data.initialize_dof_vector(vec); }
+
+ private:
+  CUDAWrappers::MatrixFree<dim, double> mf_data;
+  LinearAlgebra::CUDAWrappers::Vector<double> coef;
+};
+}  // namespace UserStep64
+
+// ------------------------------------------------------------------------------------------------
+static double rel_diff(const std::vector<double> &a, const std::vector<double> &b) {
+  double num = 0., den = 0.;
+  for (std::size_t i = 0; i < a.size(); ++i) { num += (a[i] - b[i]) * (a[i] - b[i]); den += b[i] * b[i]; }
+  return std::sqrt(num / (den > 0. ? den : 1.));
+}
+
+template <int dim, int fe_degree>
+int run(bool collocation, const std::vector<unsigned int> &cells, double eps, double cell_edge) {
+  parallel::distributed::Triangulation<dim> triangulation;
+  Point<dim> p2;
+  for (int d = 0; d < dim; ++d) p2[d] = cells[d] * cell_edge;
+  GridGenerator::subdivided_hyper_rectangle(triangulation, cells, Point<dim>(), p2);
+  if (eps != 0.) { triangulation.deformation = 1; triangulation.deformation_eps = eps; }
+  FE_Q<dim> fe(fe_degree);
+  DoFHandler<dim> dof_handler(triangulation);
+  dof_handler.distribute_dofs(fe);
+  AffineConstraints<double> constraints;
+  std::cout << std::setprecision(15);
+  std::cout << "n_dofs " << dof_handler.n_dofs() << std::endl;
+  int failures = 0;
+  auto report = [&](const char *what, double err, double tol) {
+    std::cout << what << " " << err << (err <= tol ? "" : "   <-- FAIL") << std::endl;
+    if (!(err <= tol)) ++failures;
+  };
+
+  {  // ---- BP5
+    UserBP5::PoissonOperator<dim, fe_degree> user_op(dof_handler, constraints, collocation);
+    BP5::PoissonOperator<dim, fe_degree> lib_op(dof_handler, constraints, collocation ? BP5_QUAD_GLL : BP5_QUAD_GAUSS);
+    // the coefficient the user functor computed from inv_jacobian / JxW vs the library's stored metric
+    std::vector<double> cu(user_op.n_coefficients()), cl(user_op.n_coefficients());
+    cudaMemcpy(cu.data(), user_op.coefficients(), sizeof(double) * cu.size(), cudaMemcpyDeviceToHost);
+    b200::check(bp5_operator_export_coefficients(lib_op.handle(), cl.data()));
+    report("bp5_coefficient_rel_diff", rel_diff(cu, cl), 1e-13);
+
+    VectorType b, y_user, y_lib, y_plain, z_user, x_user, x_lib;
+    lib_op.initialize_dof_vector(b);
+    lib_op.assemble_rhs(b);
+    VectorType bu;                       // same values in a vector that belongs to the user operator
+    user_op.initialize_dof_vector(bu);
+    bu.equ(1., b);
+    y_user.reinit(bu); y_plain.reinit(bu); z_user.reinit(bu); x_user.reinit(bu);
+    y_lib.reinit(b); x_lib.reinit(b);
+    user_op.vmult(y_user, bu);
+    user_op.vmult_plain(y_plain, bu);
+    lib_op.vmult(y_lib, b);
+    user_op.vmult(z_user, y_user);
+    std::vector<double> a, c;
+    y_user.copy_to_host(a); y_lib.copy_to_host(c);
+    report("bp5_vmult_user_vs_library", rel_diff(a, c), 1e-12);
+    y_plain.copy_to_host(a);
+    report("bp5_vmult_plain_vs_library", rel_diff(a, c), 1e-12);
+    std::cout << "bp5_norm_b " << b.l2_norm() << std::endl;
+    std::cout << "bp5_norm_Ab " << y_user.l2_norm() << std::endl;
+    std::cout << "bp5_norm_AAb " << z_user.l2_norm() << std::endl;
+
+    DiagonalMatrix<VectorType> preconditioner;
+    preconditioner.get_vector().reinit(b);
+    preconditioner.get_vector() = 1.;
+    const double tol = 1e-6 * b.l2_norm();
+    IterationNumberControl c_user(200, tol), c_lib(200, tol), c_std(200, tol);
+    user_op.do_zero_out = false;         // bp5/step-64.cu:483
+    SolverCGFullMerge<VectorType>(c_user).solve(user_op, x_user, bu, preconditioner);
+    lib_op.do_zero_out = false;
+    SolverCGFullMerge<VectorType>(c_lib).solve(lib_op, x_lib, b, preconditioner);
+    std::cout << "bp5_merged_its_user " << c_user.last_step() << std::endl;
+    std::cout << "bp5_merged_its_library " << c_lib.last_step() << std::endl;
+    std::cout << "bp5_norm_x " << x_user.l2_norm() << std::endl;
+    x_user.copy_to_host(a); x_lib.copy_to_host(c);
+    report("bp5_x_user_vs_library", rel_diff(a, c), 1e-8);
+    if (std::abs((int)c_user.last_step() - (int)c_lib.last_step()) > 1) { ++failures; std::cout << "iteration counts differ <-- FAIL\n"; }
+    user_op.do_zero_out = true;
+    x_user = 0.;
+    SolverCG<VectorType>(c_std).solve(user_op, x_user, bu, preconditioner);
+    std::cout << "bp5_standard_its_user " << c_std.last_step() << std::endl;
+    x_user.copy_to_host(a);
+    report("bp5_x_standard_vs_library", rel_diff(a, c), 1e-8);
+  }
+  if (!collocation) {  // ---- step-64 Helmholtz (QGauss only in the reference)
+    UserStep64::HelmholtzOperator<dim, fe_degree> user_op(dof_handler, constraints);
+    Step64::HelmholtzOperator<dim, fe_degree> lib_op(dof_handler, constraints);
+    VectorType b, bu, y_user, y_lib, x_user, x_lib;
+    lib_op.initialize_dof_vector(b);
+    lib_op.assemble_rhs(b);
+    user_op.initialize_dof_vector(bu);
+    bu.equ(1., b);
+    y_user.reinit(bu); x_user.reinit(bu); y_lib.reinit(b); x_lib.reinit(b);
+    user_op.vmult(y_user, bu);
+    lib_op.vmult(y_lib, b);
+    std::vector<double> a, c;
+    y_user.copy_to_host(a); y_lib.copy_to_host(c);
+    report("helmholtz_vmult_user_vs_library", rel_diff(a, c), 1e-12);
+    std::cout << "helmholtz_norm_Ab " << y_user.l2_norm() << std::endl;
+    DiagonalMatrix<VectorType> preconditioner;
+    preconditioner.get_vector().reinit(b);
+    preconditioner.get_vector() = 1.;
+    SolverControl c_user(b.size(), 1e-12 * b.l2_norm()), c_lib(b.size(), 1e-12 * b.l2_norm());   // step-64/step-64.cu:513
+    SolverCGFullMerge<VectorType>(c_user).solve(user_op, x_user, bu, preconditioner);
+    SolverCG<VectorType>(c_lib).solve(lib_op, x_lib, b, preconditioner);
+    std::cout << "helmholtz_merged_its_user " << c_user.last_step() << std::endl;
+    std::cout << "helmholtz_standard_its_library " << c_lib.last_step() << std::endl;
+    std::cout << "helmholtz_norm_x " << x_user.l2_norm() << std::endl;
+    x_user.copy_to_host(a); x_lib.copy_to_host(c);
+    report("helmholtz_x_user_vs_library", rel_diff(a, c), 1e-8);
+  }
+  std::cout << (failures ? "FAILED" : "OK") << std::endl;
+  return failures;
+}
+
+int main(int argc, char *argv[]) {
+  try {
+    const int degree = argc > 1 ? std::atoi(argv[1]) : 4;
+    const bool collocation = argc > 2 && std::strcmp(argv[2], "gll") == 0;
+    std::vector<unsigned int> cells(3, 3);
+    for (int d = 0; d < 3; ++d)
+      if (argc > 3 + d) cells[d] = std::atoi(argv[3 + d]);
+    const double eps = argc > 6 ? std::atof(argv[6]) : 0.1;
+    const double cell_edge = argc > 7 ? std::atof(argv[7]) : 1.0;
+    switch (degree) {
+      case 2: return run<3, 2>(collocation, cells, eps, cell_edge);
+      case 3: return run<3, 3>(collocation, cells, eps, cell_edge);
+      case 4: return run<3, 4>(collocation, cells, eps, cell_edge);
+      case 5: return run<3, 5>(collocation, cells, eps, cell_edge);
+      case 6: return run<3, 6>(collocation, cells, eps, cell_edge);
+      default: throw ExcMessage("degree must be 2..6");
+    }
+  } catch (std::exception &exc) {
+    std::cerr << "Exception on processing: " << std::endl << exc.what() << std::endl << "Aborting!" << std::endl;
+    return 1;
+  }
+}

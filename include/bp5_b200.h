@@ -136,6 +136,10 @@ int64_t bp5_context_launch_count(bp5_context_t ctx);
 /* [UPSTREAM] used at bp5/step-64.cu:321-323,349,363-367 ; solver.h:369-382 */
 int bp5_vector_create(bp5_context_t ctx, int64_t n_owned, int64_t n_ghost, bp5_vector_t *vec);
 int bp5_vector_create_like(bp5_vector_t other, bp5_vector_t *vec); /* reinit(other) */
+/* the operator whose initialize_dof_vector() produced this vector (directly or through
+ * reinit(other)) -- the role the Partitioner plays in deal.II [UPSTREAM]; NULL for
+ * vectors made by bp5_vector_create.  It must outlive the solves that use the vector. */
+bp5_operator_t bp5_vector_owner(bp5_vector_t vec);
 int bp5_vector_destroy(bp5_vector_t vec);
 int bp5_vector_local_size(bp5_vector_t vec, int64_t *n_owned, int64_t *n_ghost);
 double *bp5_vector_get_values(bp5_vector_t vec);                   /* get_values(): device pointer */
@@ -146,6 +150,7 @@ int bp5_vector_copy(bp5_vector_t dst, bp5_vector_t src);
 int bp5_vector_add(bp5_vector_t y, double a, bp5_vector_t x);      /* y.add(a, x) */
 int bp5_vector_equ(bp5_vector_t y, double a, bp5_vector_t x);      /* y.equ(a, x) */
 int bp5_vector_sadd(bp5_vector_t y, double s, double a, bp5_vector_t x); /* y = s*y + a*x */
+int bp5_vector_scale(bp5_vector_t y, bp5_vector_t x);              /* y.scale(x): y[i] *= x[i] */
 /* local (this block's owned range) parts of the reductions; the caller sums
  * over blocks (MPI_Allreduce in the reference, bp5/solver.h:493) */
 int bp5_vector_dot_local(bp5_vector_t x, bp5_vector_t y, double *out);
@@ -172,6 +177,32 @@ int bp5_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t
  * back -- the end-to-end entry point a host-side caller uses. */
 int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, int64_t n, int variant,
                       int control, double tol, int max_its, int *last_step, double *last_value);
+
+/* ---- user-written cell functors (generic MatrixFree path) ------------------- */
+/* What CUDAWrappers::MatrixFree<dim,double>::Data hands to a device functor
+ * (bp5/step-64.cu:69-75,128-138; bp5/fe_evaluation_gl.h:107-124), in deal.II's layout:
+ *   inv_jacobian[(d*3+e)*n_cells*padding_length + cell*padding_length + q] = d xi_d / d x_e
+ *   JxW[cell*padding_length + q],  local_to_global[cell*padding_length + i],
+ *   q_points[(cell*padding_length + q)*3 + c],  constraint_mask[cell] == 0 (conforming mesh),
+ * plus the 1D shape tables [q*n + i] that MatrixFree::reinit puts into constant memory
+ * [UPSTREAM]: values, gradients, and gradients of the basis through the quadrature points.
+ * Device arrays stay owned by the operator.  Single block (no ghosts).
+ * include/dealii_b200/cuda_matrix_free.cuh builds MatrixFree / FEEvaluationGL on this. */
+typedef struct bp5_matrix_free_data {
+  double *q_points;
+  unsigned int *local_to_global;
+  double *inv_jacobian;
+  double *JxW;
+  unsigned int *constraint_mask;
+  unsigned int n_cells;
+  unsigned int padding_length;
+  int n_q_points_1d;
+  int collocation;                 /* 1: Gauss-Lobatto quadrature on the nodes, shape_values == identity */
+  double shape_values[81];
+  double shape_gradients[81];
+  double co_shape_gradients[81];
+} bp5_matrix_free_data_t;
+int bp5_operator_matrix_free_data(bp5_operator_t op, bp5_matrix_free_data_t *out);
 
 /* ---- partitioned meshes: halo exchange and stepwise CG -------------------- */
 /* Message shapes of update_ghost_values / compress(add) [UPSTREAM, inside cell_loop,

@@ -29,6 +29,8 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../bp5_b200.h"
@@ -102,16 +104,24 @@ class Context {
 }  // namespace b200
 
 // ------------------------------------------------------------------ mesh description
-template <int dim> struct Point {
-  std::array<double, dim> v{};
-  double &operator[](unsigned d) { return v[d]; }
-  double operator[](unsigned d) const { return v[d]; }
+#ifdef __CUDACC__
+#define DEAL_II_B200_HOST_DEVICE __host__ __device__
+#else
+#define DEAL_II_B200_HOST_DEVICE
+#endif
+template <int dim, typename Number = double> struct Point {
+  Number v[dim] = {};
+  DEAL_II_B200_HOST_DEVICE Number &operator[](unsigned d) { return v[d]; }
+  DEAL_II_B200_HOST_DEVICE Number operator[](unsigned d) const { return v[d]; }
 };
 
 // what the drivers do to a parallel::distributed::Triangulation (bp5/step-64.cu:656-663)
 template <int dim> class Triangulation {
  public:
+  virtual ~Triangulation() = default;     // the operators dynamic_cast it (bp5/step-64.cu:250)
   void clear() { subdivisions.assign(dim, 1); refinements = 0; }
+  // one block per GPU; this facade drives one block
+  unsigned int n_locally_owned_active_cells() const { return (unsigned int)n_global_active_cells(); }
   void refine_global(unsigned int n) { refinements += n; }
   unsigned long long n_global_active_cells() const {
     unsigned long long n = 1;
@@ -126,7 +136,10 @@ template <int dim> class Triangulation {
   int deformation = 0;
   double deformation_eps = 0.0;
 };
-namespace parallel { namespace distributed { template <int dim> using Triangulation = dealii::Triangulation<dim>; } }
+namespace parallel {
+template <int dim> using Triangulation = dealii::Triangulation<dim>;
+namespace distributed { template <int dim> using Triangulation = dealii::Triangulation<dim>; }
+}  // namespace parallel
 
 namespace GridGenerator {
 template <int dim>
@@ -164,6 +177,25 @@ template <int dim> class DoFHandler {
   const Triangulation<dim> *tria;
 };
 
+// quadrature / mapping descriptions as the operator constructors name them (bp5/step-64.cu:234-247)
+template <int dim> struct Quadrature {
+  Quadrature(unsigned int n, int kind) : n_points_1d(n), abi_kind(kind) {}
+  unsigned int n_points_1d;
+  int abi_kind;
+};
+template <int dim> struct QGauss : Quadrature<dim> {
+  explicit QGauss(unsigned int n) : Quadrature<dim>(n, BP5_QUAD_GAUSS) {}
+};
+template <int dim> struct QGaussLobatto : Quadrature<dim> {
+  explicit QGaussLobatto(unsigned int n) : Quadrature<dim>(n, BP5_QUAD_GLL) {}
+};
+template <int dim> struct MappingQGeneric {
+  explicit MappingQGeneric(unsigned int degree) : degree(degree) {}
+  unsigned int degree;
+};
+enum UpdateFlags { update_default = 0, update_values = 1, update_gradients = 2, update_JxW_values = 4, update_quadrature_points = 8 };
+inline UpdateFlags operator|(UpdateFlags a, UpdateFlags b) { return static_cast<UpdateFlags>(int(a) | int(b)); }
+
 // zero Dirichlet values on the whole boundary (boundary id 0), bp5/step-64.cu:351-358
 template <typename Number = double> struct AffineConstraints {
   void clear() {}
@@ -181,19 +213,21 @@ template <> class Vector<double, MemorySpace::CUDA> {
   Vector() = default;
   Vector(const Vector &) = delete;
   Vector &operator=(const Vector &) = delete;
-  ~Vector() { bp5_vector_destroy(h); }
+  ~Vector() { release(); }
 
   void reinit(long long n_owned, long long n_ghost = 0) {
-    bp5_vector_destroy(h); h = nullptr;
+    release();
     b200::check(bp5_vector_create(b200::Context::get(), n_owned, n_ghost, &h));
     constant = 0.0; is_constant = true;
   }
   void reinit(const Vector &other, bool = false) {          // solver.h:369-371, bp5/step-64.cu:367,431
-    bp5_vector_destroy(h); h = nullptr;
+    release();
     b200::check(bp5_vector_create_like(other.h, &h));
     constant = 0.0; is_constant = true;
   }
-  void adopt(bp5_vector_t handle) { bp5_vector_destroy(h); h = handle; constant = 0.0; is_constant = true; }
+  void adopt(bp5_vector_t handle) { release(); h = handle; constant = 0.0; is_constant = true; }
+  // non-owning alias of a vector that lives in the library (the solver's temporaries)
+  void view(bp5_vector_t handle) { release(); h = handle; owning = false; is_constant = false; }
   Vector &operator=(double s) { b200::check(bp5_vector_set(h, s)); constant = s; is_constant = true; return *this; }
   double l2_norm() const { double v; b200::check(bp5_vector_norm_sqr_local(h, &v)); return std::sqrt(v); }
   double operator*(const Vector &o) const { double v; b200::check(bp5_vector_dot_local(h, o.h, &v)); return v; }
@@ -201,6 +235,7 @@ template <> class Vector<double, MemorySpace::CUDA> {
   void add(double a, const Vector &v) { b200::check(bp5_vector_add(h, a, v.h)); is_constant = false; }
   void equ(double a, const Vector &v) { b200::check(bp5_vector_equ(h, a, v.h)); is_constant = false; }
   void sadd(double s, double a, const Vector &v) { b200::check(bp5_vector_sadd(h, s, a, v.h)); is_constant = false; }
+  void scale(const Vector &v) { b200::check(bp5_vector_scale(h, v.h)); is_constant = false; }
   void zero_out_ghosts() { b200::check(bp5_vector_zero_out_ghosts(h)); }
   double *get_values() { is_constant = false; return bp5_vector_get_values(h); }
   const double *get_values() const { return bp5_vector_get_values(h); }
@@ -219,7 +254,9 @@ template <> class Vector<double, MemorySpace::CUDA> {
   bool is_constant_value(double s) const { return is_constant && constant == s; }
 
  private:
+  void release() { if (owning) bp5_vector_destroy(h); h = nullptr; owning = true; }
   bp5_vector_t h = nullptr;
+  bool owning = true;
   double constant = 0.0;     // set by operator=(double) until the next modification
   bool is_constant = false;
 };
@@ -280,28 +317,127 @@ template <int dim, int fe_degree, int operator_kind> class MatrixFreeOperator {
 
 // ------------------------------------------------------------------ solvers
 namespace b200 {
+// does MatrixType expose the library operator (BP5::PoissonOperator, Step64::HelmholtzOperator)?
+template <typename M, typename = void> struct has_native_handle : std::false_type {};
+template <typename M>
+struct has_native_handle<M, std::void_t<decltype(std::declval<const M &>().handle()), decltype(std::declval<const M &>().do_zero_out)>>
+    : std::is_same<decltype(std::declval<const M &>().handle()), bp5_operator_t> {};
+
 template <typename VectorType, int variant> class SolverCGBase {
  public:
   explicit SolverCGBase(SolverControl &cn) : control(cn) {}
   virtual ~SolverCGBase() = default;
+
   template <typename MatrixType, typename PreconditionerType>
   void solve(const MatrixType &A, VectorType &x, const VectorType &b, const PreconditionerType &preconditioner) {
     // the reference passes a DiagonalMatrix of ones (bp5/step-64.cu:428-432) and reads it in every
     // pass; an all-ones diagonal is recognised and not read at all
     const VectorType &diag = preconditioner.get_vector();
     bp5_vector_t dh = diag.is_constant_value(1.0) ? nullptr : diag.handle();
-    check(bp5_operator_set_zero_out(A.handle(), A.do_zero_out));
-    int its = 0;
-    double val = 0.0;
-    const int rc = bp5_cg_solve(A.handle(), x.handle(), b.handle(), dh, variant, control.abi_kind(),
-                                control.tolerance(), (int)control.max_steps(), &its, &val, nullptr, 0);
+    if constexpr (has_native_handle<MatrixType>::value) {
+      // library operator: the whole loop runs behind one ABI call with the tuned cell kernel
+      check(bp5_operator_set_zero_out(A.handle(), A.do_zero_out));
+      int its = 0;
+      double val = 0.0;
+      const int rc = bp5_cg_solve(A.handle(), x.handle(), b.handle(), dh, variant, control.abi_kind(),
+                                  control.tolerance(), (int)control.max_steps(), &its, &val, nullptr, 0);
+      finish(rc, its, val, x);
+    } else if constexpr (variant == BP5_CG_MERGED) {
+      solve_merged_generic(A, x, b, dh);
+    } else {
+      solve_standard_generic(A, x, b, diag, dh != nullptr);
+    }
+  }
+
+ protected:
+  void finish(int rc, int its, double val, VectorType &x) {
     control.record((unsigned)its, val);
     x.mark_modified();
     if (rc == BP5_ERR_NO_CONVERGENCE) throw SolverControl::NoConvergence((unsigned)its, val);   // solver.h:539-540
     check(rc);
   }
+  int host_check(unsigned step, double value) const {     // SolverControl::check [UPSTREAM]
+    if (control.abi_kind() == BP5_CONTROL_ITERATION_NUMBER && step >= control.max_steps()) return 1;
+    if (value <= control.tolerance()) return 1;
+    if (step >= control.max_steps() || std::isnan(value)) return 2;
+    return 0;
+  }
 
- protected:
+  // SolverCGFullMerge::solve (bp5/solver.h:343-542) around ANY operator with vmult(dst, src) -- e.g. one
+  // built from user-written device functors on CUDAWrappers::MatrixFree.  The update / dot-product kernels
+  // and the scalar recurrences are the library's (stepwise ABI); A.vmult runs between them on the same
+  // stream, so nothing but an "are we done" poll every few iterations reaches the host.
+  template <typename MatrixType>
+  void solve_merged_generic(const MatrixType &A, VectorType &x, const VectorType &b, bp5_vector_t dh) {
+    bp5_operator_t op = bp5_vector_owner(x.handle());
+    if (!op) throw ExcMessage("SolverCGFullMerge: x must come from initialize_dof_vector() or reinit(other)");
+    VectorType g0;
+    double res0;
+    const bool x_zero = x.all_zero();                     // solver.h:375-381
+    if (x_zero) res0 = b.l2_norm();
+    else { g0.reinit(x); A.vmult(g0, x); g0.add(-1., b); res0 = g0.l2_norm(); }
+    const int conv0 = host_check(0, res0);                // iteration_status(0, ...), solver.h:384
+    if (conv0 != 0) { finish(conv0 == 2 ? BP5_ERR_NO_CONVERGENCE : BP5_OK, 0, res0, x); return; }
+    check(bp5_cg_step_begin(op, x.handle(), b.handle(), dh, control.abi_kind(), control.tolerance(),
+                            (int)control.max_steps(), res0, 0));
+    bp5_vector_t gh, dd, hh;
+    check(bp5_cg_step_vectors(op, &gh, &dd, &hh));
+    if (!x_zero) check(bp5_vector_copy(gh, g0.handle()));
+    VectorType d, h, sums;
+    d.view(dd); h.view(hh);
+    sums.reinit(8);
+    int state = 0, its = 0;
+    double val = res0;
+    for (unsigned it = 1; it <= control.max_steps() && state == 0; ++it) {
+      check(bp5_cg_step_update(op, (int)it));             // 1) solver.h:413-448 (also zeroes h)
+      A.vmult(h, d);                                      // 2) solver.h:475
+      check(bp5_cg_step_local_dots(op, sums.get_values()));   // 3) solver.h:478-485
+      check(bp5_cg_step_scalars(op, sums.get_values()));      // 4) solver.h:497-533, on the device
+      if (it % 8 == 0 || it == control.max_steps()) check(bp5_cg_step_poll(op, &state, &its, &val));
+    }
+    check(bp5_cg_step_finish(op, nullptr));               // owed x update, solver.h:509-526
+    check(bp5_cg_step_poll(op, &state, &its, &val));
+    if (state == 3) { control.record((unsigned)its, val); throw ExcDivideByZero(); }   // solver.h:501
+    finish(state == 1 ? BP5_OK : BP5_ERR_NO_CONVERGENCE, its, val, x);
+  }
+
+  // dealii::SolverCG [UPSTREAM] with vector operations only ("pcg-standard", bp5/step-64.cu:446-453)
+  template <typename MatrixType>
+  void solve_standard_generic(const MatrixType &A, VectorType &x, const VectorType &b, const VectorType &diag,
+                              bool has_diag) {
+    VectorType g, d, h;
+    g.reinit(x); d.reinit(x); h.reinit(x);
+    if (!x.all_zero()) { A.vmult(g, x); g.add(-1., b); } else g.equ(-1., b);
+    double res = g.l2_norm();
+    unsigned it = 0;
+    int conv = host_check(0, res);
+    double gh = 0.;
+    if (conv == 0) {
+      if (has_diag) { h.equ(1., g); h.scale(diag); } else h.equ(1., g);
+      d.equ(-1., h);
+      gh = g * h;
+    }
+    while (conv == 0) {
+      ++it;
+      h = 0.;
+      A.vmult(h, d);
+      const double dAd = d * h;
+      if (dAd == 0.) { control.record(it, res); throw ExcDivideByZero(); }
+      const double alpha = gh / dAd;
+      x.add(alpha, d);
+      g.add(alpha, h);
+      res = g.l2_norm();
+      conv = host_check(it, res);
+      if (conv != 0) break;
+      if (has_diag) { h.equ(1., g); h.scale(diag); } else h.equ(1., g);
+      const double gh_new = g * h;
+      const double beta = gh_new / gh;
+      gh = gh_new;
+      d.sadd(beta, -1., h);
+    }
+    finish(conv == 2 ? BP5_ERR_NO_CONVERGENCE : BP5_OK, (int)it, res, x);
+  }
+
   SolverControl &control;
 };
 }  // namespace b200
