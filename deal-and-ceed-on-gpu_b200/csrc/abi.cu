@@ -586,14 +586,14 @@ int bp5_cg_step_apply_local(bp5_operator_t op) {
   BP5_ABI_GUARD_BEGIN
   BP5_STEP_GUARD();
   // h (zeroed by the update step) = local cells' part of A d; the caller exchanges halos around this
-  return apply_cell_loop(op, op->h->d, op->d->d, true);
+  return cg_step_apply_local(op);
   BP5_ABI_GUARD_END
 }
 
 int bp5_cg_step_constrained(bp5_operator_t op) {
   BP5_ABI_GUARD_BEGIN
   BP5_STEP_GUARD();
-  return apply_copy_constrained(op, op->h->d, op->d->d);
+  return cg_step_constrained(op);
   BP5_ABI_GUARD_END
 }
 

@@ -61,20 +61,27 @@ int apply_choose(bp5_operator_t op) {
   op->cells_per_tile = cpt;
   op->n_tiles = (op->n_cells + cpt - 1) / cpt;
   op->tile_doubles = ((int64_t)cpt * op->metric_planes * n3 + 1) & ~(int64_t)1;
+  // how the metric reaches the quadrature phase (ApplyCfg::MLOAD); BP5_MLOAD overrides for tuning runs
+  op->metric_path = 0;
+#ifdef BP5_ENABLE_MLOAD
+  if (const char *mv = getenv("BP5_MLOAD")) op->metric_path = atoi(mv);
+#endif
+  BP5_REQUIRE(op->metric_path >= 0 && op->metric_path <= 2, "BP5_MLOAD must be 0, 1 or 2");
+  static const char *const kPath[3] = {"metric=tma-smem", "metric=ldg-regs", "metric=ldg-regs-ahead"};
   char name[160];
-  snprintf(name, sizeof(name), "bp5_apply_kernel<p=%d,%s,%s,cells_per_tile=%d>", op->p,
+  snprintf(name, sizeof(name), "bp5_apply_kernel<p=%d,%s,%s,cells_per_tile=%d,%s>", op->p,
            op->prob.quadrature == BP5_QUAD_GLL ? "gll-collocation" : "gauss",
-           op->prob.operator_kind == BP5_OP_HELMHOLTZ ? "helmholtz" : "poisson", cpt);
+           op->prob.operator_kind == BP5_OP_HELMHOLTZ ? "helmholtz" : "poisson", cpt, kPath[op->metric_path]);
   op->kernel_name = name;
   return BP5_OK;
 }
 
-template <int P, int QUAD, int HELM, int OVERWRITE>
-static int launch(bp5_operator_t op, double *dst, const double *src) {
+template <int P, int QUAD, int HELM, int OVERWRITE, int MLOAD>
+static int launch(bp5_operator_t op, double *dst, const double *src, double *dot_partials) {
   constexpr int CPT = TileCells<P>::value;
-  using Cfg = ApplyCfg<P, CPT, 6 + HELM>;
+  using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = P + 1;
-  auto kernel = bp5_apply_kernel<P, QUAD, HELM, CPT, OVERWRITE>;
+  auto kernel = bp5_apply_kernel<P, QUAD, HELM, CPT, OVERWRITE, MLOAD>;
   static int blocks_per_sm = 0;   // per instantiation
   if (blocks_per_sm == 0) {
     BP5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -90,6 +97,7 @@ static int launch(bp5_operator_t op, double *dst, const double *src) {
   prm.src = src; prm.dst = dst;
   prm.n_tiles = op->n_tiles; prm.sy = op->od[0]; prm.sz = op->od[0] * op->od[1];
   prm.skip = op->skip_flag;
+  prm.dot_partials = dot_partials;
   for (int q = 0; q < N; ++q)
     for (int i = 0; i < N; ++i) {
       for (int d = 0; d < 3; ++d) {
@@ -100,6 +108,8 @@ static int launch(bp5_operator_t op, double *dst, const double *src) {
   long long grid = (long long)blocks_per_sm * op->ctx->sm_count;
   if (grid > op->n_tiles) grid = op->n_tiles;
   if (grid < 1) grid = 1;
+  BP5_REQUIRE(grid <= kApplyPartialCap, "apply grid exceeds the partial-sum buffer");
+  op->apply_grid = (int)grid;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (op->profile) {
     if (op->prof_used + 2 > op->prof_events.size()) {
@@ -115,30 +125,45 @@ static int launch(bp5_operator_t op, double *dst, const double *src) {
   return BP5_OK;
 }
 
-template <int P>
-static int launch_p(bp5_operator_t op, double *dst, const double *src, bool overwrite) {
+// mode: 0 dst += A src ; 1 overwrite cell-interior DoFs ; 2 = 1 + per-CTA partial sums of src . (A src)
+template <int P, int MLOAD>
+static int launch_pm(bp5_operator_t op, double *dst, const double *src, int mode, double *dp) {
   const bool gll = op->prob.quadrature == BP5_QUAD_GLL;
   const bool helm = op->prob.operator_kind == BP5_OP_HELMHOLTZ;
-  if (overwrite) {
-    if (gll) return helm ? launch<P, 1, 1, 1>(op, dst, src) : launch<P, 1, 0, 1>(op, dst, src);
-    return helm ? launch<P, 0, 1, 1>(op, dst, src) : launch<P, 0, 0, 1>(op, dst, src);
-  }
-  if (gll) return helm ? launch<P, 1, 1, 0>(op, dst, src) : launch<P, 1, 0, 0>(op, dst, src);
-  return helm ? launch<P, 0, 1, 0>(op, dst, src) : launch<P, 0, 0, 0>(op, dst, src);
+#define BP5_LAUNCH_MODE(M)                                                                                       \
+  (gll ? (helm ? launch<P, 1, 1, M, MLOAD>(op, dst, src, dp) : launch<P, 1, 0, M, MLOAD>(op, dst, src, dp))      \
+       : (helm ? launch<P, 0, 1, M, MLOAD>(op, dst, src, dp) : launch<P, 0, 0, M, MLOAD>(op, dst, src, dp)))
+  if (mode == 2) return BP5_LAUNCH_MODE(2);
+  if (mode == 1) return BP5_LAUNCH_MODE(1);
+  return BP5_LAUNCH_MODE(0);
+#undef BP5_LAUNCH_MODE
+}
+
+template <int P>
+static int launch_p(bp5_operator_t op, double *dst, const double *src, int mode, double *dp) {
+#ifdef BP5_ENABLE_MLOAD   // tuning builds: metric straight to registers (measured slower, profiles/r1_v3_notes.md)
+  if (op->metric_path == 1) return launch_pm<P, 1>(op, dst, src, mode, dp);
+  if (op->metric_path == 2) return launch_pm<P, 2>(op, dst, src, mode, dp);
+#endif
+  return launch_pm<P, 0>(op, dst, src, mode, dp);
 }
 
 // overwrite_interior: dst's skeleton (shared DoFs, see zero_skeleton) must be
 // zero on entry, cell-interior DoFs are overwritten; otherwise dst += A src.
-int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior) {
+// dot_partials != nullptr (needs overwrite_interior): the kernel also leaves op->apply_grid per-CTA parts of
+// src . (A src) there (see bp5_apply_kernel, OVERWRITE == 2).
+int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior, double *dot_partials) {
+  BP5_REQUIRE(dot_partials == nullptr || overwrite_interior, "the fused dot product needs the overwrite kernel");
+  const int mode = dot_partials ? 2 : (overwrite_interior ? 1 : 0);
   switch (op->p) {
-    case 1: return launch_p<1>(op, dst, src, overwrite_interior);
-    case 2: return launch_p<2>(op, dst, src, overwrite_interior);
-    case 3: return launch_p<3>(op, dst, src, overwrite_interior);
-    case 4: return launch_p<4>(op, dst, src, overwrite_interior);
-    case 5: return launch_p<5>(op, dst, src, overwrite_interior);
-    case 6: return launch_p<6>(op, dst, src, overwrite_interior);
-    case 7: return launch_p<7>(op, dst, src, overwrite_interior);
-    case 8: return launch_p<8>(op, dst, src, overwrite_interior);
+    case 1: return launch_p<1>(op, dst, src, mode, dot_partials);
+    case 2: return launch_p<2>(op, dst, src, mode, dot_partials);
+    case 3: return launch_p<3>(op, dst, src, mode, dot_partials);
+    case 4: return launch_p<4>(op, dst, src, mode, dot_partials);
+    case 5: return launch_p<5>(op, dst, src, mode, dot_partials);
+    case 6: return launch_p<6>(op, dst, src, mode, dot_partials);
+    case 7: return launch_p<7>(op, dst, src, mode, dot_partials);
+    case 8: return launch_p<8>(op, dst, src, mode, dot_partials);
   }
   set_error("unsupported degree %d", op->p);
   return BP5_ERR_UNSUPPORTED;
@@ -169,6 +194,42 @@ __global__ void copy_constrained_kernel(const int *__restrict__ list, long long 
                                         double *__restrict__ dst) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t < n) { const int i = list[t]; dst[i] = src[i]; }
+}
+
+// The same copy, and the correction the fused dot product needs: the cell kernel summed src_c * (A src)_c
+// for the Dirichlet rows too, but dst_c becomes src_c, so add sum_c src_c * (src_c - (A src)_c).  Exactly
+// zero whenever src vanishes on the Dirichlet set (always, inside the reference's CG).  Fixed grid,
+// per-block partials: deterministic.
+__global__ void __launch_bounds__(256) copy_constrained_dot_kernel(const int *__restrict__ list, long long n,
+                                                                   const double *__restrict__ src,
+                                                                   double *__restrict__ dst,
+                                                                   double *__restrict__ partials) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int i = list[t];
+    const double s = src[i];
+    acc += s * (s - dst[i]);
+    dst[i] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < 8 ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+  }
+}
+
+int apply_copy_constrained_dot(bp5_operator_t op, double *dst, const double *src, double *partials) {
+  copy_constrained_dot_kernel<<<kConstrainedPartials, 256, 0, op->ctx->stream>>>(op->constrained, op->n_constrained, src,
+                                                                                dst, partials);
+  BP5_CHECK_LAUNCH();
+  op->ctx->launches++;
+  return BP5_OK;
 }
 
 int apply_copy_constrained(bp5_operator_t op, double *dst, const double *src) {

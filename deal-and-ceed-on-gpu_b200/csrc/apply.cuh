@@ -67,6 +67,7 @@ struct ApplyParams {
   long long n_tiles;
   int sy, sz;             // affine strides of the owned box
   const int *skip;        // optional device flag: non-zero => nothing to do (CG already converged)
+  double *dot_partials;   // OVERWRITE == 2: [gridDim.x] per-CTA parts of src . (A src), summed by the CG dots kernel
   KernelTables<N> tab;
 };
 
@@ -109,6 +110,14 @@ __device__ __forceinline__ uint64_t make_evict_first_policy() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
+}
+
+// streaming 8-byte load for the metric when it goes straight to registers: read-only path,
+// no L1 allocation, L2 evict-first (every byte is used exactly once per operator application)
+__device__ __forceinline__ double ld_stream(const double *p, uint64_t policy) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+  return v;
 }
 
 // Local dof indices of the N points of one thread's z-column in a cell with
@@ -181,7 +190,18 @@ __device__ __forceinline__ void contract_in_regs(double (&w)[N], const double *_
   }
 }
 
-template <int P, int CPT, int PLANES>
+// MLOAD: how the metric reaches the quadrature phase.
+//   0: one TMA bulk copy per tile into shared memory (mbarrier), read back with LDS;
+//   1: plain streaming loads into registers, issued at the start of the tile;
+//   2: the same, issued one tile ahead (right after the previous quadrature phase).
+// tuning builds may force a minimum number of resident CTAs per SM (-D'BP5_MIN_BLOCKS(P)=...');
+// by default ptxas's own heuristic is kept: an explicit minimum of 1 makes it spend ~50 more registers
+#ifdef BP5_MIN_BLOCKS
+#define BP5_LAUNCH_BOUNDS(NT, P) __launch_bounds__(NT, BP5_MIN_BLOCKS(P))
+#else
+#define BP5_LAUNCH_BOUNDS(NT, P) __launch_bounds__(NT)
+#endif
+template <int P, int CPT, int PLANES, int MLOAD = 0>
 struct ApplyCfg {
   static constexpr int N = P + 1, N2 = N * N, N3 = N2 * N;
   using L = SmemLayout<N, CPT>;                            // per-array bank-conflict-minimising strides
@@ -190,25 +210,29 @@ struct ApplyCfg {
   static constexpr int METRIC_DOUBLES = (CPT * PLANES * N3 + 1) & ~1;  // per tile, padded to 16 bytes
   static constexpr uint32_t METRIC_BYTES = METRIC_DOUBLES * 8;
   static constexpr int WORK_DOUBLES = CPT * (2 * L::A_CS + L::B_CS);   // S0, S1 (layout A) and S2 (layout B)
-  static constexpr size_t SMEM_BYTES = (size_t)METRIC_BYTES + (size_t)WORK_DOUBLES * 8 + 16;
+  static constexpr int STAGE_DOUBLES = MLOAD == 0 ? METRIC_DOUBLES : 0;   // shared-memory staging of the metric
+  static constexpr size_t SMEM_BYTES = (size_t)STAGE_DOUBLES * 8 + (size_t)WORK_DOUBLES * 8 + 16;
   static_assert(METRIC_BYTES % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
 };
 
 // QUAD: 0 = Gauss (basis nodes != quadrature points: interpolate, then
 // collocation derivative), 1 = Gauss-Lobatto collocation (B = identity).
 // HELM: 0 = Poisson (6 planes), 1 = Helmholtz (7th plane a(x) JxW on the values).
-// OVERWRITE: 1 = cell-interior DoFs are stored, not added (dst's skeleton must be
+// OVERWRITE: 2 = like 1, and the CTA also reduces src . (A src) over its cells, evaluated at the
+// quadrature points as sum_q g_q^T G_q g_q (+ mass term) -- the "p.v" dot product of the merged CG
+// (bp5/solver.h:231,303) without reading either vector again;
+// 1 = cell-interior DoFs are stored, not added (dst's skeleton must be
 // zero on entry, its interior may hold anything); 0 = dst += A src everywhere.
-template <int P, int QUAD, int HELM, int CPT, int OVERWRITE>
-__global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
+template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0>
+__global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
     bp5_apply_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
-  using Cfg = ApplyCfg<P, CPT, 6 + HELM>;
+  using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = Cfg::N, N2 = Cfg::N2, N3 = Cfg::N3, PLANES = 6 + HELM;
   using L = typename Cfg::L;
   constexpr int A1 = L::A_S1, A2 = L::A_S2, B1 = L::B_S1, B2 = L::B_S2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *Gs = reinterpret_cast<double *>(smem_raw);                 // [CPT][PLANES][N3]
-  double *S0 = Gs + Cfg::METRIC_DOUBLES;                             // layout A (home + x-line + y-line readers)
+  double *S0 = Gs + Cfg::STAGE_DOUBLES;                              // layout A (home + x-line + y-line readers)
   double *S1 = S0 + CPT * L::A_CS;                                   // layout A (home + x-line)
   double *S2 = S1 + CPT * L::A_CS;                                   // layout B (home + y-line)
   uint64_t *bar = reinterpret_cast<uint64_t *>(S2 + CPT * L::B_CS);
@@ -243,16 +267,33 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
   double *__restrict__ dst = prm.dst;
   const double *__restrict__ metric = prm.metric;
   uint64_t policy = 0;
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_barrier_init();
-    policy = make_evict_first_policy();
-    if (tile0 < n_tiles) {
-      mbar_expect_tx(bar, Cfg::METRIC_BYTES);
-      tma_load_1d(Gs, metric + tile0 * (long long)Cfg::METRIC_DOUBLES, Cfg::METRIC_BYTES, bar, policy);
+  if constexpr (MLOAD == 0) {
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+      policy = make_evict_first_policy();
+      if (tile0 < n_tiles) {
+        mbar_expect_tx(bar, Cfg::METRIC_BYTES);
+        tma_load_1d(Gs, metric + tile0 * (long long)Cfg::METRIC_DOUBLES, Cfg::METRIC_BYTES, bar, policy);
+      }
     }
+    __syncthreads();
+  } else {
+    policy = make_evict_first_policy();
   }
-  __syncthreads();
+  // this thread's column of the metric within a tile: [c][plane][k][b][a]
+  const int gcol = c * PLANES * N3 + b * N + a;
+  [[maybe_unused]] double greg[N][PLANES];
+  auto load_metric = [&](long long tile) {
+    const double *gp = metric + tile * (long long)Cfg::METRIC_DOUBLES + gcol;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+      for (int pl = 0; pl < PLANES; ++pl) greg[k][pl] = ld_stream(gp + pl * N3 + k * N2, policy);
+  };
+  if constexpr (MLOAD == 2) {
+    if (active && tile0 < n_tiles) load_metric(tile0);
+  }
 
   // software pipeline of the gather: cell descriptors two tiles ahead, values one tile ahead
   int base_cur = (active && tile0 < n_tiles) ? __ldg(cell_base + tile0 * CPT + c) : kNoCell;
@@ -261,6 +302,7 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
   gather_column<N>(u_nxt, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
 
   uint32_t parity = 0;
+  [[maybe_unused]] double dot_acc = 0.0;
   for (long long tile = tile0; tile < n_tiles; tile += tstride) {
     double u[N];
 #pragma unroll
@@ -270,6 +312,9 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
     const int base_n2 =
         (active && tile + 2 * tstride < n_tiles) ? __ldg(cell_base + (tile + 2 * tstride) * CPT + c) : kNoCell;
 
+    if constexpr (MLOAD == 1) {
+      if (active) load_metric(tile);
+    }
     double t[N];   // z-direction data that stays in registers across the quadrature phase
     double mv[N];  // Helmholtz: values at the quadrature points (home column)
 
@@ -339,31 +384,49 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
     }
 
     // ---------------- quadrature-point phase (home): g <- G g  (bp5/step-64.cu:160-188)
-    mbar_wait(bar, parity);
-    parity ^= 1;
+    if constexpr (MLOAD == 0) {
+      mbar_wait(bar, parity);
+      parity ^= 1;
+    }
     if (active) {
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const int q = (k * N + b) * N + a, wA = hA + k * A2, wB = hB + k * B2;
         const double ur = s1[wA], us = s2[wB], ut = t[k];
-        const double g0 = gm[q], g1 = gm[N3 + q], g2 = gm[2 * N3 + q];
-        const double g3 = gm[3 * N3 + q], g4 = gm[4 * N3 + q], g5 = gm[5 * N3 + q];
-        s1[wA] = ur * g0 + us * g3 + ut * g4;
-        s2[wB] = ur * g3 + us * g1 + ut * g5;
-        t[k] = ur * g4 + us * g5 + ut * g2;
-        if constexpr (HELM) mv[k] *= gm[6 * N3 + q];
+        double g0, g1, g2, g3, g4, g5;
+        if constexpr (MLOAD == 0) {
+          g0 = gm[q]; g1 = gm[N3 + q]; g2 = gm[2 * N3 + q]; g3 = gm[3 * N3 + q]; g4 = gm[4 * N3 + q]; g5 = gm[5 * N3 + q];
+        } else {
+          g0 = greg[k][0]; g1 = greg[k][1]; g2 = greg[k][2]; g3 = greg[k][3]; g4 = greg[k][4]; g5 = greg[k][5];
+        }
+        const double vr = ur * g0 + us * g3 + ut * g4;
+        const double vs = ur * g3 + us * g1 + ut * g5;
+        const double vt = ur * g4 + us * g5 + ut * g2;
+        s1[wA] = vr;
+        s2[wB] = vs;
+        t[k] = vt;
+        if constexpr (OVERWRITE == 2) dot_acc += ur * vr + us * vs + ut * vt;
+        if constexpr (HELM) {
+          const double m_old = mv[k];
+          mv[k] = m_old * (MLOAD == 0 ? gm[6 * N3 + q] : greg[k][PLANES - 1]);
+          if constexpr (OVERWRITE == 2) dot_acc += m_old * mv[k];
+        }
       }
     }
     __syncthreads();
-    // the metric buffer is free: fetch the next tile's metric behind the remaining work
-    if (tid == 0 && tile + tstride < n_tiles) {
-      mbar_expect_tx(bar, Cfg::METRIC_BYTES);
-      tma_load_1d(Gs, metric + (tile + tstride) * (long long)Cfg::METRIC_DOUBLES, Cfg::METRIC_BYTES, bar, policy);
+    if constexpr (MLOAD == 0) {
+      // the metric buffer is free: fetch the next tile's metric behind the remaining work
+      if (tid == 0 && tile + tstride < n_tiles) {
+        mbar_expect_tx(bar, Cfg::METRIC_BYTES);
+        tma_load_1d(Gs, metric + (tile + tstride) * (long long)Cfg::METRIC_DOUBLES, Cfg::METRIC_BYTES, bar, policy);
+      }
+    } else if constexpr (MLOAD == 2) {
+      if (active && tile + tstride < n_tiles) load_metric(tile + tstride);
     }
 
     int idx[N];
     column_indices<N>(idx, l2g_irr, base_cur, ab_off, ab_irr, sz);
-    const bool col_interior = OVERWRITE && a > 0 && a < P && b > 0 && b < P;
+    const bool col_interior = OVERWRITE != 0 && a > 0 && a < P && b > 0 && b < P;
     const bool do_scatter = base_cur != kNoCell;
 
     if constexpr (QUAD == 1) {
@@ -443,6 +506,21 @@ __global__ void __launch_bounds__(ApplyCfg<P, CPT, 6 + HELM>::NT)
     }
     base_cur = base_nxt;
     base_nxt = base_n2;
+  }
+  if constexpr (OVERWRITE == 2) {
+    // CTA-wide sum in a fixed order (warp shuffles, then warp 0 over the per-warp sums)
+    __syncthreads();
+    double v = active ? dot_acc : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) S0[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+      v = tid < Cfg::NT / 32 ? S0[tid] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (tid == 0) prm.dot_partials[blockIdx.x] = v;
+    }
   }
 }
 

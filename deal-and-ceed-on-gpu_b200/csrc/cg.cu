@@ -28,6 +28,8 @@ namespace bp5 {
 constexpr int kCgBlocks = 592;
 constexpr int kCgThreads = 256;
 
+constexpr int kUpdatePartialCap = 4096;     // >= grid of the update kernel (sm_count * 16)
+
 struct CgState {
   double alpha, beta, alpha_old, beta_old;
   double res, tol, gh;
@@ -37,6 +39,31 @@ struct CgState {
   unsigned ticket;
   int history_len;
 };
+
+// device scratch of one solve: [CgState | dots partials | cell-kernel p.v partials | Dirichlet correction
+// partials | update-kernel r.r partials | residual history]
+struct CgBuffers {
+  CgState *st;
+  double *partials;    // [kCgBlocks][7]
+  double *ph;          // [kApplyPartialCap + kConstrainedPartials]
+  double *rr;          // [kUpdatePartialCap][2]
+  double *hist;        // [hist_len] or nullptr
+};
+static size_t cg_layout(void *base, int hist_len, CgBuffers *b) {
+  const size_t o_partials = 256;
+  const size_t o_ph = o_partials + sizeof(double) * kCgBlocks * 7;
+  const size_t o_rr = o_ph + sizeof(double) * (kApplyPartialCap + kConstrainedPartials);
+  const size_t o_hist = o_rr + sizeof(double) * kUpdatePartialCap * 2;
+  if (b) {
+    char *c = reinterpret_cast<char *>(base);
+    b->st = reinterpret_cast<CgState *>(c);
+    b->partials = reinterpret_cast<double *>(c + o_partials);
+    b->ph = reinterpret_cast<double *>(c + o_ph);
+    b->rr = reinterpret_cast<double *>(c + o_rr);
+    b->hist = hist_len > 0 ? reinterpret_cast<double *>(c + o_hist) : nullptr;
+  }
+  return o_hist + sizeof(double) * (hist_len > 0 ? hist_len : 1);
+}
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -74,32 +101,41 @@ __device__ __forceinline__ int control_check(int control, int step, int max_its,
 
 // ---------------------------------------------------------------- merged CG
 // MODE 0: update_a0 (solver.h:48-72)  1: update_a<false> (:74-104)  3: update_a1 (:106-140)
+// Fused here: r.r (and r.Dr) of the residual this kernel WRITES -- two of the seven sums of update_b
+// (solver.h:142-311) -- as per-block partials rr[block][2], so the dots pass does not have to form them.
 template <int MODE, bool DIAG>
 __global__ void __launch_bounds__(256) cg_update_kernel(const CgState *__restrict__ st, double *__restrict__ p,
                                                         double *__restrict__ r, double *__restrict__ v,
                                                         double *__restrict__ x, const double *__restrict__ diag,
-                                                        const uint32_t *__restrict__ skel, long long n) {
-  // "v = 0" (solver.h:69,101,137).  (Restricting it to the skeleton bit mask `skel` was measured
-  // slower: scattered partial-sector writes, and L2 fills the sectors anyway.)
-  (void)skel;
+                                                        double *__restrict__ rr, long long n) {
+  // "v = 0" (solver.h:69,101,137).  (Restricting it to the skeleton was measured slower: scattered
+  // partial-sector writes, and L2 fills the sectors anyway.)
   if (st->state != 0) return;
+  __shared__ double sh[2 * 32];
   const double alpha = st->alpha, beta = st->beta;
   double apa = 0.0, aob = 0.0;
   if (MODE == 3) { aob = st->alpha_old / st->beta_old; apa = alpha + aob; }
+  double s[2] = {0.0, 0.0};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double dg = DIAG ? diag[i] : 1.0;
+    double r_new;
     if (MODE == 0) {
-      p[i] = -dg * r[i];
+      r_new = r[i];
+      p[i] = -dg * r_new;
     } else {
       const double r_old = r[i];
-      const double r_new = r_old + alpha * v[i];
+      r_new = r_old + alpha * v[i];
       const double p_old = p[i];
       if (MODE == 3) x[i] += apa * p_old + aob * dg * r_old;
       r[i] = r_new;
       p[i] = beta * p_old - dg * r_new;
     }
     v[i] = 0.0;
+    s[0] += r_new * r_new;
+    if (DIAG) s[1] += r_new * dg * r_new;
   }
+  block_sum_k<2>(s, sh);
+  if (threadIdx.x == 0) { rr[2 * blockIdx.x] = s[0]; rr[2 * blockIdx.x + 1] = s[1]; }
 }
 
 // scalar recurrences of one iteration from the seven (globally summed) dot products
@@ -133,12 +169,15 @@ __global__ void cg_scalars_kernel(CgState *st, const double *__restrict__ sums, 
 
 // FUSE: the last block also runs the scalar recurrences (single block of the mesh);
 // otherwise it writes the seven local sums to sums_out for the caller's allreduce.
-template <bool DIAG, bool FUSE>
+// LEAN: p.v comes from the cell kernel (n_ph per-CTA partials in ph: cells + Dirichlet correction) and
+// r.r / r.Dr from the update kernel (n_rr per-block partials in rr): only r and v are read here.
+template <bool DIAG, bool FUSE, bool LEAN>
 __global__ void __launch_bounds__(kCgThreads) cg_dots_kernel(CgState *st, const double *__restrict__ p,
                                                              const double *__restrict__ r,
                                                              const double *__restrict__ v,
                                                              const double *__restrict__ diag, long long n,
-                                                             double *partials, double *history, double *sums_out) {
+                                                             double *partials, double *history, double *sums_out,
+                                                             const double *ph, int n_ph, const double *rr, int n_rr) {
   if (st->state != 0) return;
   __shared__ double sh[7 * 32];
   __shared__ bool is_last;
@@ -147,11 +186,13 @@ __global__ void __launch_bounds__(kCgThreads) cg_dots_kernel(CgState *st, const 
 #pragma unroll
   for (int j = 0; j < K; ++j) s[j] = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double ps = p[i], rs = r[i], vs = v[i];
-    s[0] += ps * vs; s[1] += vs * vs; s[2] += rs * vs; s[3] += rs * rs;
+    const double rs = r[i], vs = v[i];
+    s[1] += vs * vs; s[2] += rs * vs;
+    if (!LEAN) { s[0] += p[i] * vs; s[3] += rs * rs; }
     if (DIAG) {
       const double ds = diag[i], dv = ds * vs;
-      s[4] += rs * dv; s[5] += vs * dv; s[6] += rs * ds * rs;
+      s[4] += rs * dv; s[5] += vs * dv;
+      if (!LEAN) s[6] += rs * ds * rs;
     }
   }
   block_sum_k<K>(s, sh);
@@ -171,17 +212,26 @@ __global__ void __launch_bounds__(kCgThreads) cg_dots_kernel(CgState *st, const 
   for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
 #pragma unroll
     for (int j = 0; j < K; ++j) s[j] += __ldcg(&partials[b * 7 + j]);
+  if (LEAN) {
+    s[0] = 0.0; s[3] = 0.0;
+    if (DIAG) s[6] = 0.0;
+    for (int b = threadIdx.x; b < n_ph; b += blockDim.x) s[0] += __ldcg(&ph[b]);
+    for (int b = threadIdx.x; b < n_rr; b += blockDim.x) {
+      s[3] += __ldcg(&rr[2 * b]);
+      if (DIAG) s[6] += __ldcg(&rr[2 * b + 1]);
+    }
+  }
   block_sum_k<K>(s, sh);
   if (threadIdx.x == 0) {
-    double rr[7];
+    double q[7];
 #pragma unroll
-    for (int j = 0; j < K; ++j) rr[j] = s[j];
-    if (!DIAG) { rr[4] = rr[2]; rr[5] = rr[1]; rr[6] = rr[3]; }
+    for (int j = 0; j < K; ++j) q[j] = s[j];
+    if (!DIAG) { q[4] = q[2]; q[5] = q[1]; q[6] = q[3]; }
     st->ticket = 0;
-    if (FUSE) cg_scalar_step(st, rr, history);
+    if (FUSE) cg_scalar_step(st, q, history);
     else
 #pragma unroll
-      for (int j = 0; j < 7; ++j) sums_out[j] = rr[j];
+      for (int j = 0; j < 7; ++j) sums_out[j] = q[j];
   }
 }
 
@@ -212,30 +262,15 @@ __global__ void std_init_kernel(double *__restrict__ d, double *__restrict__ h, 
   }
 }
 
-// alpha = gh / (d.h)
-__global__ void __launch_bounds__(kCgThreads) std_dh_kernel(CgState *st, const double *__restrict__ d,
-                                                            const double *__restrict__ h, long long n,
-                                                            double *partials) {
+// alpha = gh / (d.h), d.h summed from the cell kernel's per-CTA partials of d.(A d) (+ Dirichlet correction):
+// one block, fixed order
+__global__ void __launch_bounds__(kCgThreads) std_alpha_kernel(CgState *st, const double *__restrict__ ph, int n_ph) {
   if (st->state != 0) return;
   __shared__ double sh[32];
-  __shared__ bool is_last;
   double s[1] = {0.0};
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    s[0] += d[i] * h[i];
+  for (int b = threadIdx.x; b < n_ph; b += blockDim.x) s[0] += ph[b];
   block_sum_k<1>(s, sh);
   if (threadIdx.x == 0) {
-    partials[blockIdx.x * 7] = s[0];
-    __threadfence();
-    is_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  s[0] = 0.0;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s[0] += __ldcg(&partials[b * 7]);
-  block_sum_k<1>(s, sh);
-  if (threadIdx.x == 0) {
-    st->ticket = 0;
     if (s[0] == 0.0) { st->state = 3; return; }
     st->alpha = st->gh / s[0];
   }
@@ -310,9 +345,21 @@ static unsigned stream_grid(long long n, int sm_count) {
 
 template <int MODE>
 static void launch_update(bool has_diag, unsigned grid, cudaStream_t s, const CgState *st, double *p, double *r,
-                          double *v, double *x, const double *diag, const uint32_t *skel, long long n) {
-  if (has_diag) cg_update_kernel<MODE, true><<<grid, 256, 0, s>>>(st, p, r, v, x, diag, skel, n);
-  else cg_update_kernel<MODE, false><<<grid, 256, 0, s>>>(st, p, r, v, x, diag, skel, n);
+                          double *v, double *x, const double *diag, double *rr, long long n) {
+  if (has_diag) cg_update_kernel<MODE, true><<<grid, 256, 0, s>>>(st, p, r, v, x, diag, rr, n);
+  else cg_update_kernel<MODE, false><<<grid, 256, 0, s>>>(st, p, r, v, x, diag, rr, n);
+}
+
+template <bool FUSE>
+static void launch_dots(bool has_diag, bool lean, cudaStream_t s, CgState *st, const double *p, const double *r,
+                        const double *v, const double *diag, long long n, const CgBuffers &cb, double *sums_out,
+                        int n_ph, int n_rr) {
+#define BP5_DOTS(D, L)                                                                                          \
+  cg_dots_kernel<D, FUSE, L><<<kCgBlocks, kCgThreads, 0, s>>>(st, p, r, v, diag, n, cb.partials, cb.hist, sums_out, \
+                                                            cb.ph, n_ph, cb.rr, n_rr)
+  if (has_diag) { if (lean) BP5_DOTS(true, true); else BP5_DOTS(true, false); }
+  else { if (lean) BP5_DOTS(false, true); else BP5_DOTS(false, false); }
+#undef BP5_DOTS
 }
 
 int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diagv, int variant, int control,
@@ -335,18 +382,18 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
   }
   double *g = op->g->d, *d = op->d->d, *h = op->h->d;
   const int hist_len = history ? history_len : 0;
-  const size_t state_bytes = 256;
-  const size_t partial_bytes = sizeof(double) * kCgBlocks * 7;
-  const size_t need = state_bytes + partial_bytes + sizeof(double) * (hist_len > 0 ? hist_len : 1);
+  const size_t need = cg_layout(nullptr, hist_len, nullptr);
   if (!op->cg_scalars || op->cg_scalars_bytes < need) {
     if (op->cg_scalars) cudaFree(op->cg_scalars);
     op->cg_scalars = nullptr;
     BP5_CUDA(cudaMalloc(&op->cg_scalars, need));
     op->cg_scalars_bytes = need;
   }
-  CgState *st = reinterpret_cast<CgState *>(op->cg_scalars);
-  double *partials = reinterpret_cast<double *>(reinterpret_cast<char *>(op->cg_scalars) + state_bytes);
-  double *hist_dev = hist_len > 0 ? partials + kCgBlocks * 7 : nullptr;
+  CgBuffers cb;
+  cg_layout(op->cg_scalars, hist_len, &cb);
+  CgState *st = cb.st;
+  double *partials = cb.partials;
+  double *hist_dev = cb.hist;
 
   // g = A x - b, or -b if x == 0 (solver.h:375-381)
   int x_zero = 0;
@@ -380,6 +427,8 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
   CgState init{};
   init.tol = tol; init.res = res; init.max_its = max_its; init.control = control; init.history_len = hist_len;
   const unsigned grid = stream_grid(n, ctx->sm_count);
+  BP5_REQUIRE(grid <= (unsigned)kUpdatePartialCap, "update grid exceeds the partial-sum buffer");
+  const int n_corr = op->n_constrained > 0 ? kConstrainedPartials : 0;
   if (variant == BP5_CG_STANDARD) {
     if (has_diag) std_init_kernel<true><<<grid, 256, 0, s>>>(d, h, g, diag, n);
     else std_init_kernel<false><<<grid, 256, 0, s>>>(d, h, g, diag, n);
@@ -409,25 +458,24 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
       const int cur = it + 1;
       if (variant == BP5_CG_MERGED) {
         // 1) update region (solver.h:413-448), with the parity-correct x update
-        if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x->d, diag, op->skel_mask, n);
-        else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x->d, diag, op->skel_mask, n);
-        else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, op->skel_mask, n);
+        //    (+ r.r, r.Dr of the new residual as per-block partials)
+        if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+        else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+        else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
         ctx->launches++;
         // 2) h = A d with do_zero_out = false (solver.h:475; h's skeleton zeroed by the update kernel,
-        //    its cell-interior entries are overwritten by the cell kernel)
-        if ((rc = apply_cell_loop(op, h, d, true))) break;
-        if ((rc = apply_copy_constrained(op, h, d))) break;
-        // 3)+4) dots and scalars (solver.h:478-533)
-        if (has_diag)
-          cg_dots_kernel<true, true><<<kCgBlocks, kCgThreads, 0, s>>>(st, d, g, h, diag, n, partials, hist_dev, nullptr);
-        else
-          cg_dots_kernel<false, true><<<kCgBlocks, kCgThreads, 0, s>>>(st, d, g, h, diag, n, partials, hist_dev, nullptr);
+        //    its cell-interior entries are overwritten by the cell kernel) + d.h as per-CTA partials
+        if ((rc = apply_cell_loop(op, h, d, true, cb.ph))) break;
+        if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + op->apply_grid))) break;
+        // 3)+4) the remaining dots (h.h, r.h, r.Dh, h.Dh) and the scalars (solver.h:478-533)
+        launch_dots<true>(has_diag, /*lean=*/true, s, st, d, g, h, diag, n, cb, nullptr, op->apply_grid + n_corr,
+                          (int)grid);
         ctx->launches++;
       } else {
         if ((rc = apply_zero_skeleton(op, h))) break;
-        if ((rc = apply_cell_loop(op, h, d, true))) break;
-        if ((rc = apply_copy_constrained(op, h, d))) break;
-        std_dh_kernel<<<kCgBlocks, kCgThreads, 0, s>>>(st, d, h, n, partials);
+        if ((rc = apply_cell_loop(op, h, d, true, cb.ph))) break;
+        if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + op->apply_grid))) break;
+        std_alpha_kernel<<<1, kCgThreads, 0, s>>>(st, cb.ph, op->apply_grid + n_corr);   // alpha = gh / (d.h)
         if (has_diag) {
           std_xg_kernel<true><<<kCgBlocks, kCgThreads, 0, s>>>(st, x->d, g, d, h, diag, n, partials, hist_dev);
           std_d_kernel<true><<<grid, 256, 0, s>>>(st, d, g, diag, n);
@@ -493,7 +541,7 @@ static int stepwise_buffers(bp5_operator_t op, int hist_len) {
     if ((rc = bp5_vector_create(ctx, op->n_owned, op->n_ghost, &op->d))) return rc;
     if ((rc = bp5_vector_create(ctx, op->n_owned, op->n_ghost, &op->h))) return rc;
   }
-  const size_t need = 256 + sizeof(double) * kCgBlocks * 7 + sizeof(double) * (hist_len > 0 ? hist_len : 1);
+  const size_t need = cg_layout(nullptr, hist_len, nullptr);
   if (!op->cg_scalars || op->cg_scalars_bytes < need) {
     if (op->cg_scalars) cudaFree(op->cg_scalars);
     op->cg_scalars = nullptr;
@@ -521,16 +569,21 @@ int cg_step_begin(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_
 }
 
 int cg_step_update(bp5_operator_t op, int cur) {
-  CgState *st = reinterpret_cast<CgState *>(op->cg_scalars);
+  CgBuffers cb;
+  cg_layout(op->cg_scalars, op->cg_hist_len, &cb);
+  CgState *st = cb.st;
   const long long n = op->n_owned;
   const unsigned grid = stream_grid(n, op->ctx->sm_count);
+  BP5_REQUIRE(grid <= (unsigned)kUpdatePartialCap, "update grid exceeds the partial-sum buffer");
+  op->cg_ph_valid = false;       // set again by cg_step_apply_local; a foreign vmult leaves it false
+  op->cg_update_grid = (int)grid;
   const double *diag = op->cg_diag ? op->cg_diag->d : nullptr;
   const bool has_diag = diag != nullptr;
   cudaStream_t s = op->ctx->stream;
   double *g = op->g->d, *d = op->d->d, *h = op->h->d, *x = op->cg_x->d;
-  if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x, diag, op->skel_mask, n);
-  else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x, diag, op->skel_mask, n);
-  else launch_update<3>(has_diag, grid, s, st, d, g, h, x, diag, op->skel_mask, n);
+  if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x, diag, cb.rr, n);
+  else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x, diag, cb.rr, n);
+  else launch_update<3>(has_diag, grid, s, st, d, g, h, x, diag, cb.rr, n);
   BP5_CHECK_LAUNCH();
   op->ctx->launches++;
   // the ghost entries of h receive contributions for the neighbouring owners: start them at zero
@@ -538,29 +591,42 @@ int cg_step_update(bp5_operator_t op, int cur) {
   return BP5_OK;
 }
 
+// 2) local cells' part of h = A d, with the fused d.h partials
+int cg_step_apply_local(bp5_operator_t op) {
+  CgBuffers cb;
+  cg_layout(op->cg_scalars, op->cg_hist_len, &cb);
+  const int rc = apply_cell_loop(op, op->h->d, op->d->d, true, cb.ph);
+  if (rc == BP5_OK) op->cg_ph_valid = true;
+  return rc;
+}
+
+// Dirichlet copy after the halo sum; keeps the fused d.h consistent with h_c = d_c
+int cg_step_constrained(bp5_operator_t op) {
+  if (op->n_constrained == 0) return BP5_OK;
+  if (!op->cg_ph_valid) return apply_copy_constrained(op, op->h->d, op->d->d);
+  CgBuffers cb;
+  cg_layout(op->cg_scalars, op->cg_hist_len, &cb);
+  return apply_copy_constrained_dot(op, op->h->d, op->d->d, cb.ph + op->apply_grid);
+}
+
 int cg_step_local_dots(bp5_operator_t op, double *sums_dev) {
-  CgState *st = reinterpret_cast<CgState *>(op->cg_scalars);
-  double *partials = reinterpret_cast<double *>(reinterpret_cast<char *>(op->cg_scalars) + 256);
+  CgBuffers cb;
+  cg_layout(op->cg_scalars, op->cg_hist_len, &cb);
   const double *diag = op->cg_diag ? op->cg_diag->d : nullptr;
-  cudaStream_t s = op->ctx->stream;
-  const long long n = op->n_owned;
-  if (diag)
-    cg_dots_kernel<true, false><<<kCgBlocks, kCgThreads, 0, s>>>(st, op->d->d, op->g->d, op->h->d, diag, n, partials,
-                                                                 nullptr, sums_dev);
-  else
-    cg_dots_kernel<false, false><<<kCgBlocks, kCgThreads, 0, s>>>(st, op->d->d, op->g->d, op->h->d, diag, n, partials,
-                                                                  nullptr, sums_dev);
+  // after a foreign vmult (user-written operator) there are no cell-kernel partials: read d as well
+  const bool lean = op->cg_ph_valid;
+  const int n_ph = lean ? op->apply_grid + (op->n_constrained > 0 ? kConstrainedPartials : 0) : 0;
+  launch_dots<false>(diag != nullptr, lean, op->ctx->stream, cb.st, op->d->d, op->g->d, op->h->d, diag, op->n_owned, cb,
+                     sums_dev, n_ph, op->cg_update_grid);
   BP5_CHECK_LAUNCH();
   op->ctx->launches++;
   return BP5_OK;
 }
 
 int cg_step_scalars(bp5_operator_t op, const double *sums_dev) {
-  CgState *st = reinterpret_cast<CgState *>(op->cg_scalars);
-  double *hist = op->cg_hist_len > 0
-                     ? reinterpret_cast<double *>(reinterpret_cast<char *>(op->cg_scalars) + 256) + kCgBlocks * 7
-                     : nullptr;
-  cg_scalars_kernel<<<1, 32, 0, op->ctx->stream>>>(st, sums_dev, hist);
+  CgBuffers cb;
+  cg_layout(op->cg_scalars, op->cg_hist_len, &cb);
+  cg_scalars_kernel<<<1, 32, 0, op->ctx->stream>>>(cb.st, sums_dev, cb.hist);
   BP5_CHECK_LAUNCH();
   op->ctx->launches++;
   return BP5_OK;
@@ -588,7 +654,9 @@ int cg_step_finish(bp5_operator_t op, double *history) {
   op->ctx->launches++;
   op->skip_flag = nullptr;
   if (history && op->cg_hist_len > 1) {
-    double *hist = reinterpret_cast<double *>(reinterpret_cast<char *>(op->cg_scalars) + 256) + kCgBlocks * 7;
+    CgBuffers cb;
+    cg_layout(op->cg_scalars, op->cg_hist_len, &cb);
+    double *hist = cb.hist;
     BP5_CUDA(cudaMemcpyAsync(history + 1, hist + 1, sizeof(double) * (op->cg_hist_len - 1), cudaMemcpyDeviceToHost, s));
   }
   BP5_CUDA(cudaStreamSynchronize(s));

@@ -14,6 +14,8 @@
 namespace bp5 {
 
 constexpr int kMaxDegree = 8;
+constexpr int kApplyPartialCap = 4096;      // per-CTA partial sums of the cell kernel's fused dot product
+constexpr int kConstrainedPartials = 148;   // blocks (= partial sums) of the Dirichlet-copy correction
 constexpr int kMaxN = kMaxDegree + 1;
 
 // ---- error plumbing --------------------------------------------------------
@@ -106,6 +108,8 @@ struct bp5_operator_s {
   int64_t ghost_offset[8] = {0}; // start of ghost group m (1..7) relative to n_owned
   int64_t ghost_size[8] = {0};
   int cells_per_tile = 1;
+  int apply_grid = 0;           // CTAs of the last cell-kernel launch (= number of fused-dot partial sums)
+  int metric_path = 0;          // ApplyCfg::MLOAD: 0 TMA -> shared memory, 1/2 streaming loads -> registers
   int64_t n_tiles = 0;
   int64_t tile_doubles = 0;     // metric doubles per tile (padded to a multiple of 2)
   // device data
@@ -131,6 +135,8 @@ struct bp5_operator_s {
   size_t cg_scalars_bytes = 0;
   bp5_vector_t cg_x = nullptr, cg_diag = nullptr;   // stepwise CG: caller's solution / diagonal
   int cg_hist_len = 0;
+  bool cg_ph_valid = false;     // stepwise CG: the cell kernel left d.h partials for the next dots step
+  int cg_update_grid = 0;       // stepwise CG: blocks (= r.r partials) of the last update step
   // live per-launch timing of the cell kernel (bench.py roofline): events around every launch
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;   // start/stop pairs
@@ -149,7 +155,9 @@ int operator_export_coords(bp5_operator_t op, double *host_out);
 int operator_export_global_indices(bp5_operator_t op, int64_t *host_out);
 // apply.cu
 int apply_choose(bp5_operator_t op);                 // picks cells_per_tile + kernel name
-int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior);
+int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior,
+                    double *dot_partials = nullptr);
+int apply_copy_constrained_dot(bp5_operator_t op, double *dst, const double *src, double *partials);
 int apply_zero_skeleton(bp5_operator_t op, double *dst);
 int apply_copy_constrained(bp5_operator_t op, double *dst, const double *src);
 // vector.cu
@@ -165,6 +173,8 @@ int halo_unpack_add(bp5_operator_t op, double *vec, const double *recvbuf);
 int cg_step_begin(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,
                   int max_its, double res0, int history_len);
 int cg_step_update(bp5_operator_t op, int iteration);
+int cg_step_apply_local(bp5_operator_t op);
+int cg_step_constrained(bp5_operator_t op);
 int cg_step_local_dots(bp5_operator_t op, double *sums_dev);
 int cg_step_scalars(bp5_operator_t op, const double *sums_dev);
 int cg_step_poll(bp5_operator_t op, int *state, int *it, double *res);

@@ -21,7 +21,7 @@ for p in degrees:
         bytes_v, bytes_cg = op.algorithmic_bytes()
         for _ in range(3): op.vmult(dst, src); op.cell_loop(dst, src)
         ctx.synchronize()
-        reps = 10
+        reps = int(os.environ.get('PROBE_REPS', '10'))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(reps): op.vmult(dst, src)
