@@ -37,6 +37,14 @@ class Problem(C.Structure):
     ]
 
 
+class PeerInfo(C.Structure):
+    """bp5_peer_info_t: what a rank publishes for the peer-memory transport."""
+    _fields_ = [("buf_handle", C.c_ubyte * 64), ("dvec_handle", C.c_ubyte * 64),
+                ("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("n_send", C.c_int64),
+                ("ghost_offset", C.c_int64 * 8), ("send_offset", C.c_int64 * 8),
+                ("rank", C.c_int32), ("device", C.c_int32)]
+
+
 class Bp5Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"bp5 error {code}: {msg}")
@@ -113,6 +121,12 @@ ABI = [
     ("bp5_cg_step_scalars", C.c_int, [_vp, _vp]),
     ("bp5_cg_step_poll", C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp]),
     ("bp5_cg_step_finish", C.c_int, [_vp, _dp]),
+    ("bp5_peer_export", C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(PeerInfo)]),
+    ("bp5_peer_connect", C.c_int, [_vp, C.POINTER(PeerInfo), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("bp5_peer_vmult", C.c_int, [_vp, _vp, _vp]),
+    ("bp5_peer_cg_solve", C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _dp, _dp,
+                                    C.c_int]),
+    ("bp5_peer_allreduce", C.c_int, [_vp, _dp, C.c_int]),
 ]
 
 

@@ -153,6 +153,7 @@ int bp5_operator_destroy(bp5_operator_t op) {
   if (!op) return BP5_OK;
   cudaSetDevice(op->ctx->device);
   cudaStreamSynchronize(op->ctx->stream);
+  peer_destroy(op);
   cudaFree(op->cell_base);
   cudaFree(op->l2g_irr);
   cudaFree(op->skel_mask);
@@ -624,6 +625,54 @@ int bp5_cg_step_finish(bp5_operator_t op, double *history) {
   BP5_ABI_GUARD_BEGIN
   BP5_STEP_GUARD();
   return cg_step_finish(op, history);
+  BP5_ABI_GUARD_END
+}
+
+// ------------------------------------------------- peer-memory transport
+int bp5_peer_export(bp5_operator_t op, int rank, int world, bp5_peer_info_t *info) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && info, "null argument");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return peer_export(op, rank, world, info);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_peer_connect(bp5_operator_t op, const bp5_peer_info_t *all_infos, const int32_t *upper_rank,
+                     const int32_t *lower_rank) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && all_infos && upper_rank && lower_rank, "null argument");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return peer_connect(op, all_infos, upper_rank, lower_rank);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_peer_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op, "null operator");
+  int rc;
+  if ((rc = check_vec(op, dst)) || (rc = check_vec(op, src))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return peer_vmult(op, dst, src);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_peer_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,
+                      int max_its, int *last_step, double *last_value, double *history, int history_len) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op, "null operator");
+  int rc;
+  if ((rc = check_vec(op, x)) || (rc = check_vec(op, b))) return rc;
+  if (diag && (rc = check_vec(op, diag))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return cg_solve_peer(op, x, b, diag, control, tol, max_its, last_step, last_value, history, history_len);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_peer_allreduce(bp5_operator_t op, double *values, int n) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && values && n >= 1 && n <= 8, "bad argument");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return peer_allreduce_host(op, values, n);
   BP5_ABI_GUARD_END
 }
 

@@ -59,7 +59,7 @@ int apply_choose(bp5_operator_t op) {
   BP5_REQUIRE(cpt > 0, "degree must be 1..8");
   const int n3 = op->n * op->n * op->n;
   op->cells_per_tile = cpt;
-  op->n_tiles = (op->n_cells + cpt - 1) / cpt;
+  operator_plan_tiles(op);
   op->tile_doubles = ((int64_t)cpt * op->metric_planes * n3 + 1) & ~(int64_t)1;
   // how the metric reaches the quadrature phase (ApplyCfg::MLOAD); BP5_MLOAD overrides for tuning runs
   op->metric_path = 0;
@@ -77,7 +77,7 @@ int apply_choose(bp5_operator_t op) {
 }
 
 template <int P, int QUAD, int HELM, int OVERWRITE, int MLOAD>
-static int launch(bp5_operator_t op, double *dst, const double *src, double *dot_partials) {
+static int launch(bp5_operator_t op, double *dst, const double *src, double *dot_partials, int which) {
   constexpr int CPT = TileCells<P>::value;
   using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = P + 1;
@@ -95,7 +95,10 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
   ApplyParams<N> prm;
   prm.metric = op->metric; prm.cell_base = op->cell_base; prm.l2g_irr = op->l2g_irr;
   prm.src = src; prm.dst = dst;
-  prm.n_tiles = op->n_tiles; prm.sy = op->od[0]; prm.sz = op->od[0] * op->od[1];
+  prm.tile_begin = which == 2 ? op->n_boundary_tiles : 0;
+  prm.n_tiles = which == 1 ? op->n_boundary_tiles : op->n_tiles;      // end of the range
+  prm.sy = op->od[0]; prm.sz = op->od[0] * op->od[1];
+  if (prm.n_tiles <= prm.tile_begin) { op->apply_grid = 0; return BP5_OK; }
   prm.skip = op->skip_flag;
   prm.dot_partials = dot_partials;
   for (int q = 0; q < N; ++q)
@@ -106,7 +109,7 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
       }
     }
   long long grid = (long long)blocks_per_sm * op->ctx->sm_count;
-  if (grid > op->n_tiles) grid = op->n_tiles;
+  if (grid > prm.n_tiles - prm.tile_begin) grid = prm.n_tiles - prm.tile_begin;
   if (grid < 1) grid = 1;
   BP5_REQUIRE(grid <= kApplyPartialCap, "apply grid exceeds the partial-sum buffer");
   op->apply_grid = (int)grid;
@@ -127,12 +130,12 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
 
 // mode: 0 dst += A src ; 1 overwrite cell-interior DoFs ; 2 = 1 + per-CTA partial sums of src . (A src)
 template <int P, int MLOAD>
-static int launch_pm(bp5_operator_t op, double *dst, const double *src, int mode, double *dp) {
+static int launch_pm(bp5_operator_t op, double *dst, const double *src, int mode, double *dp, int which) {
   const bool gll = op->prob.quadrature == BP5_QUAD_GLL;
   const bool helm = op->prob.operator_kind == BP5_OP_HELMHOLTZ;
 #define BP5_LAUNCH_MODE(M)                                                                                       \
-  (gll ? (helm ? launch<P, 1, 1, M, MLOAD>(op, dst, src, dp) : launch<P, 1, 0, M, MLOAD>(op, dst, src, dp))      \
-       : (helm ? launch<P, 0, 1, M, MLOAD>(op, dst, src, dp) : launch<P, 0, 0, M, MLOAD>(op, dst, src, dp)))
+  (gll ? (helm ? launch<P, 1, 1, M, MLOAD>(op, dst, src, dp, which) : launch<P, 1, 0, M, MLOAD>(op, dst, src, dp, which))      \
+       : (helm ? launch<P, 0, 1, M, MLOAD>(op, dst, src, dp, which) : launch<P, 0, 0, M, MLOAD>(op, dst, src, dp, which)))
   if (mode == 2) return BP5_LAUNCH_MODE(2);
   if (mode == 1) return BP5_LAUNCH_MODE(1);
   return BP5_LAUNCH_MODE(0);
@@ -140,30 +143,31 @@ static int launch_pm(bp5_operator_t op, double *dst, const double *src, int mode
 }
 
 template <int P>
-static int launch_p(bp5_operator_t op, double *dst, const double *src, int mode, double *dp) {
+static int launch_p(bp5_operator_t op, double *dst, const double *src, int mode, double *dp, int which) {
 #ifdef BP5_ENABLE_MLOAD   // tuning builds: metric straight to registers (measured slower, profiles/r1_v3_notes.md)
-  if (op->metric_path == 1) return launch_pm<P, 1>(op, dst, src, mode, dp);
-  if (op->metric_path == 2) return launch_pm<P, 2>(op, dst, src, mode, dp);
+  if (op->metric_path == 1) return launch_pm<P, 1>(op, dst, src, mode, dp, which);
+  if (op->metric_path == 2) return launch_pm<P, 2>(op, dst, src, mode, dp, which);
 #endif
-  return launch_pm<P, 0>(op, dst, src, mode, dp);
+  return launch_pm<P, 0>(op, dst, src, mode, dp, which);
 }
 
 // overwrite_interior: dst's skeleton (shared DoFs, see zero_skeleton) must be
 // zero on entry, cell-interior DoFs are overwritten; otherwise dst += A src.
 // dot_partials != nullptr (needs overwrite_interior): the kernel also leaves op->apply_grid per-CTA parts of
 // src . (A src) there (see bp5_apply_kernel, OVERWRITE == 2).
-int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior, double *dot_partials) {
+int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior, double *dot_partials,
+                    int which) {
   BP5_REQUIRE(dot_partials == nullptr || overwrite_interior, "the fused dot product needs the overwrite kernel");
   const int mode = dot_partials ? 2 : (overwrite_interior ? 1 : 0);
   switch (op->p) {
-    case 1: return launch_p<1>(op, dst, src, mode, dot_partials);
-    case 2: return launch_p<2>(op, dst, src, mode, dot_partials);
-    case 3: return launch_p<3>(op, dst, src, mode, dot_partials);
-    case 4: return launch_p<4>(op, dst, src, mode, dot_partials);
-    case 5: return launch_p<5>(op, dst, src, mode, dot_partials);
-    case 6: return launch_p<6>(op, dst, src, mode, dot_partials);
-    case 7: return launch_p<7>(op, dst, src, mode, dot_partials);
-    case 8: return launch_p<8>(op, dst, src, mode, dot_partials);
+    case 1: return launch_p<1>(op, dst, src, mode, dot_partials, which);
+    case 2: return launch_p<2>(op, dst, src, mode, dot_partials, which);
+    case 3: return launch_p<3>(op, dst, src, mode, dot_partials, which);
+    case 4: return launch_p<4>(op, dst, src, mode, dot_partials, which);
+    case 5: return launch_p<5>(op, dst, src, mode, dot_partials, which);
+    case 6: return launch_p<6>(op, dst, src, mode, dot_partials, which);
+    case 7: return launch_p<7>(op, dst, src, mode, dot_partials, which);
+    case 8: return launch_p<8>(op, dst, src, mode, dot_partials, which);
   }
   set_error("unsupported degree %d", op->p);
   return BP5_ERR_UNSUPPORTED;

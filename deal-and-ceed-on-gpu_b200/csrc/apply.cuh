@@ -64,7 +64,7 @@ struct ApplyParams {
   const int *l2g_irr;     // [n_irregular][N^3] explicit local dof indices, x fastest
   const double *src;
   double *dst;
-  long long n_tiles;
+  long long tile_begin, n_tiles;   // tiles [tile_begin, n_tiles) of the processing order
   int sy, sz;             // affine strides of the owned box
   const int *skip;        // optional device flag: non-zero => nothing to do (CG already converged)
   double *dot_partials;   // OVERWRITE == 2: [gridDim.x] per-CTA parts of src . (A src), summed by the CG dots kernel
@@ -257,7 +257,7 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
   const int xA = b * A2 + a * A1;                 // + i           : x-line (i, j=a, k=b)
   const int yA = b * A2 + a, yB = b * B2 + a;     // + j * {A1,B1} : y-line (i=a, j, k=b)
 
-  const long long tile0 = blockIdx.x;
+  const long long tile0 = prm.tile_begin + blockIdx.x;
   const long long tstride = gridDim.x;
   const long long n_tiles = prm.n_tiles;
   const int sz = prm.sz;

@@ -663,4 +663,143 @@ int cg_step_finish(bp5_operator_t op, double *history) {
   return BP5_OK;
 }
 
+// ------------------------------------------------------------------------
+// Merged CG over a partitioned mesh with the peer-memory transport (peer.cu): the whole loop is
+// enqueued from here, one rank per GPU, every rank the same sequence.  Per iteration:
+//   update (r, p, x; h = 0; r.r partials) -> forward halo of d -> boundary cells -> reverse halo of h
+//   -> interior cells (overlapping the reverse halo) -> add contributions -> Dirichlet copy
+//   -> local dots -> all-rank sum through the mailboxes -> scalar recurrences.
+// No NCCL / MPI call and no host synchronisation inside the loop; the host polls the state word of the
+// batch before last like cg_solve().  The sums are added in rank order on every rank, so alpha, beta and
+// the stopping decision are bitwise identical everywhere and all ranks stop in the same iteration.
+int cg_solve_peer(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diagv, int control, double tol,
+                  int max_its, int *last_step, double *last_value, double *history, int history_len) {
+  BP5_REQUIRE(op->peer && op->peer_connected, "peer transport not connected (bp5_peer_export / bp5_peer_connect)");
+  BP5_REQUIRE(max_its >= 0, "max_its must be >= 0");
+  bp5_context_t ctx = op->ctx;
+  cudaStream_t s = ctx->stream;
+  const long long n = op->n_owned;
+  const double *diag = diagv ? diagv->d : nullptr;
+  const bool has_diag = diag != nullptr;
+  int rc;
+  double *g = op->g->d, *d = op->d->d, *h = op->h->d;
+  const int hist_len = history ? history_len : 0;
+  const size_t need = cg_layout(nullptr, hist_len, nullptr);
+  if (!op->cg_scalars || op->cg_scalars_bytes < need) {
+    if (op->cg_scalars) cudaFree(op->cg_scalars);
+    op->cg_scalars = nullptr;
+    BP5_CUDA(cudaMalloc(&op->cg_scalars, need));
+    op->cg_scalars_bytes = need;
+  }
+  CgBuffers cb;
+  cg_layout(op->cg_scalars, hist_len, &cb);
+  CgState *st = cb.st;
+  double *sums = peer_scratch(op);            // [0,8) local, [8,16) global
+
+  // g = -b (x == 0 on entry), ghosts zero; res0 = global |g|
+  int x_zero = 0;
+  if ((rc = vec_all_zero(ctx, x->d, n, &x_zero))) return rc;
+  double flag[1] = {x_zero ? 0.0 : 1.0};
+  if ((rc = peer_allreduce_host(op, flag, 1))) return rc;
+  BP5_REQUIRE(flag[0] == 0.0, "bp5_peer_cg_solve needs x == 0 on entry");
+  BP5_CUDA(cudaMemsetAsync(g, 0, sizeof(double) * (n + op->n_ghost), s));
+  if ((rc = vec_axpy(ctx, g, 0.0, -1.0, b->d, n, 1))) return rc;
+  double gg[1] = {0.0};
+  if ((rc = vec_dot(ctx, g, g, n, &gg[0]))) return rc;
+  if ((rc = peer_allreduce_host(op, gg, 1))) return rc;
+  const double res0 = std::sqrt(gg[0]);
+  if (history && history_len > 0) history[0] = res0;
+  int conv = 0;
+  if (control == BP5_CONTROL_ITERATION_NUMBER && 0 >= max_its) conv = 1;
+  else if (res0 <= tol) conv = 1;
+  else if (0 >= max_its || std::isnan(res0)) conv = 2;
+  if (conv != 0) {
+    if (last_step) *last_step = 0;
+    if (last_value) *last_value = res0;
+    if (conv == 2) { set_error("NoConvergence: step 0, residual %.17g", res0); return BP5_ERR_NO_CONVERGENCE; }
+    return BP5_OK;
+  }
+  CgState init{};
+  init.tol = tol; init.res = res0; init.max_its = max_its; init.control = control; init.history_len = hist_len;
+  BP5_CUDA(cudaMemcpyAsync(st, &init, sizeof(CgState), cudaMemcpyHostToDevice, s));
+  BP5_CUDA(cudaStreamSynchronize(s));
+  const unsigned grid = stream_grid(n, ctx->sm_count);
+  BP5_REQUIRE(grid <= (unsigned)kUpdatePartialCap, "update grid exceeds the partial-sum buffer");
+  const int n_corr = op->n_constrained > 0 ? kConstrainedPartials : 0;
+
+  constexpr int kBatch = 8;
+  volatile int *poll_host = reinterpret_cast<volatile int *>(ctx->scratch_host + 8);
+  cudaEvent_t ev[2];
+  BP5_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  BP5_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  poll_host[0] = poll_host[1] = 0;
+  op->skip_flag = &st->state;
+  int it = 0, nbatch = 0;
+  bool done = false;
+  rc = BP5_OK;
+  while (!done && it < max_its && rc == BP5_OK) {
+    const int upto = std::min(max_its, it + kBatch);
+    for (; it < upto && rc == BP5_OK; ++it) {
+      const int cur = it + 1;
+      if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+      else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+      else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+      ctx->launches++;
+      if (op->n_ghost && cudaMemsetAsync(h + n, 0, sizeof(double) * op->n_ghost, s) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
+      if ((rc = peer_forward(op, d))) break;
+      if ((rc = apply_cell_loop(op, h, d, true, cb.ph, 1))) break;
+      const int grid_b = op->apply_grid;
+      if ((rc = peer_reverse(op, h))) break;
+      if ((rc = apply_cell_loop(op, h, d, true, cb.ph + grid_b, 2))) break;
+      const int n_ph = grid_b + op->apply_grid;
+      if ((rc = peer_wait_add(op, h))) break;
+      if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + n_ph))) break;
+      launch_dots<false>(has_diag, /*lean=*/true, s, st, d, g, h, diag, n, cb, sums, n_ph + n_corr, (int)grid);
+      ctx->launches++;
+      if ((rc = peer_allreduce(op, sums, sums + 8, 7, true))) break;
+      cg_scalars_kernel<<<1, 32, 0, s>>>(st, sums + 8, cb.hist);
+      ctx->launches++;
+    }
+    if (rc != BP5_OK) break;
+    const int slot = nbatch & 1;
+    if (cudaMemcpyAsync((void *)&poll_host[slot], &st->state, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaEventRecord(ev[slot], s) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
+    if (nbatch >= 1) {
+      if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
+      if (poll_host[slot ^ 1] != 0) done = true;
+    }
+    ++nbatch;
+  }
+  op->skip_flag = nullptr;
+  if (rc == BP5_OK) {
+    if (has_diag) cg_finish_kernel<true><<<grid, 256, 0, s>>>(st, x->d, d, g, diag, n);
+    else cg_finish_kernel<false><<<grid, 256, 0, s>>>(st, x->d, d, g, diag, n);
+    ctx->launches++;
+  }
+  CgState fin{};
+  cudaError_t e1 = cudaMemcpyAsync(&fin, st, sizeof(CgState), cudaMemcpyDeviceToHost, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  if (rc != BP5_OK) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("CG loop failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return BP5_ERR_CUDA;
+  }
+  BP5_CHECK_LAUNCH();
+  if (history && hist_len > 1) {
+    const int cnt = std::min(hist_len, fin.it + 1) - 1;
+    if (cnt > 0) BP5_CUDA(cudaMemcpy(history + 1, cb.hist + 1, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+  }
+  if (last_step) *last_step = fin.it;
+  if (last_value) *last_value = fin.res;
+  if (fin.state == 3) { set_error("ExcDivideByZero: d.Ad == 0 at iteration %d", fin.it); return BP5_ERR_DIVIDE_BY_ZERO; }
+  if (fin.state == 2) {
+    set_error("NoConvergence: step %d, residual %.17g", fin.it, fin.res);
+    return BP5_ERR_NO_CONVERGENCE;
+  }
+  if (fin.state != 1) { set_error("CG ended in unexpected state %d", fin.state); return BP5_ERR_INVALID; }
+  return BP5_OK;
+}
+
 }  // namespace bp5

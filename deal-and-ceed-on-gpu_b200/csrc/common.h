@@ -111,6 +111,8 @@ struct bp5_operator_s {
   int apply_grid = 0;           // CTAs of the last cell-kernel launch (= number of fused-dot partial sums)
   int metric_path = 0;          // ApplyCfg::MLOAD: 0 TMA -> shared memory, 1/2 streaming loads -> registers
   int64_t n_tiles = 0;
+  int64_t n_boundary_cells = 0;  // cells touching a lower ghost layer; they occupy tiles [0, n_boundary_tiles)
+  int64_t n_boundary_tiles = 0;
   int64_t tile_doubles = 0;     // metric doubles per tile (padded to a multiple of 2)
   // device data
   int *cell_base = nullptr;     // [n_tiles*cpt] per-cell dof descriptor: >= 0 affine base (idx = base + i + j*od0 +
@@ -141,11 +143,14 @@ struct bp5_operator_s {
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;   // start/stop pairs
   size_t prof_used = 0;
+  void *peer = nullptr;          // peer-memory transport state (peer.cu), or null
+  bool peer_connected = false;
   const int *skip_flag = nullptr; // device word: when non-zero the cell loop is a no-op (CG converged)
 };
 
 namespace bp5 {
 // setup.cu
+void operator_plan_tiles(bp5_operator_t op);       // fills n_boundary_cells, n_boundary_tiles, n_tiles
 int operator_setup_device(bp5_operator_t op);
 int operator_assemble_rhs(bp5_operator_t op, double *b_dev);
 int operator_l2_norm_sqr(bp5_operator_t op, const double *u_dev, double *out);
@@ -155,8 +160,9 @@ int operator_export_coords(bp5_operator_t op, double *host_out);
 int operator_export_global_indices(bp5_operator_t op, int64_t *host_out);
 // apply.cu
 int apply_choose(bp5_operator_t op);                 // picks cells_per_tile + kernel name
+// which: 0 all tiles, 1 boundary tiles only, 2 the others
 int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior,
-                    double *dot_partials = nullptr);
+                    double *dot_partials = nullptr, int which = 0);
 int apply_copy_constrained_dot(bp5_operator_t op, double *dst, const double *src, double *partials);
 int apply_zero_skeleton(bp5_operator_t op, double *dst);
 int apply_copy_constrained(bp5_operator_t op, double *dst, const double *src);
@@ -169,6 +175,19 @@ int vec_all_zero(bp5_context_t ctx, const double *x, int64_t n, int *out);
 int halo_info(bp5_operator_t op, int64_t *send_count, int64_t *send_offset, int64_t *recv_count, int64_t *recv_offset);
 int halo_pack(bp5_operator_t op, const double *vec, double *sendbuf);
 int halo_unpack_add(bp5_operator_t op, double *vec, const double *recvbuf);
+// peer.cu
+int peer_export(bp5_operator_t op, int rank, int world, bp5_peer_info_t *out);
+int peer_connect(bp5_operator_t op, const bp5_peer_info_t *all, const int *upper_rank, const int *lower_rank);
+void peer_destroy(bp5_operator_t op);
+int peer_forward(bp5_operator_t op, const double *vec);
+int peer_reverse(bp5_operator_t op, const double *vec);
+int peer_wait_add(bp5_operator_t op, double *vec);
+int peer_allreduce(bp5_operator_t op, const double *local_dev, double *out_dev, int n_vals, bool honour_skip);
+int peer_allreduce_host(bp5_operator_t op, double *vals, int n);
+int peer_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src);
+double *peer_scratch(bp5_operator_t op);
+int cg_solve_peer(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,
+                  int max_its, int *last_step, double *last_value, double *history, int history_len);
 // cg.cu
 int cg_step_begin(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,
                   int max_its, double res0, int history_len);

@@ -120,17 +120,19 @@ __global__ void skeleton_mask_kernel(BlockGeom g, uint32_t *__restrict__ mask, l
   mask[w] = bits;
 }
 
-// One block per local cell.  Writes metric[tile][cell in tile][planes][n3] and,
-// for irregular cells (cell_base < 0), the explicit index table l2g_irr[slot][n3].
-__global__ void setup_cells_kernel(BlockGeom g, const int *__restrict__ cell_base, int *__restrict__ l2g_irr,
-                                   double *__restrict__ metric) {
+// One block per local cell (lexicographic); `slot` is the cell's position in the processing order
+// (cell_slot()).  Writes metric[tile][cell in tile][planes][n3] at that position and, for
+// irregular cells (cell_base < 0), the explicit index table l2g_irr[table][n3].
+__global__ void setup_cells_kernel(BlockGeom g, const int *__restrict__ cell_base, const long long *__restrict__ slot_of,
+                                   int *__restrict__ l2g_irr, double *__restrict__ metric) {
   extern __shared__ double sm[];
   const int n = g.n, n2 = n * n, n3 = n2 * n;
   const long long cell = blockIdx.x;
   const int lcx = cell % g.lc[0], lcy = (cell / g.lc[0]) % g.lc[1], lcz = cell / ((long long)g.lc[0] * g.lc[1]);
   const int t = threadIdx.x;
   const int i = t % n, j = (t / n) % n, k = t / n2;
-  const int base = cell_base[cell];
+  const long long slot = slot_of[cell];
+  const int base = cell_base[slot];
   if (t < n3 && base < 0)
     l2g_irr[(long long)(-(base + 1)) * n3 + t] =
         (int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
@@ -157,7 +159,7 @@ __global__ void setup_cells_kernel(BlockGeom g, const int *__restrict__ cell_bas
     G[d] = jxw * (I[d][0] * I[d][0] + I[d][1] * I[d][1] + I[d][2] * I[d][2]);
     for (int e = d + 1; e < 3; ++e, ++pl) G[pl] = jxw * (I[d][0] * I[e][0] + I[d][1] * I[e][1] + I[d][2] * I[e][2]);
   }
-  double *out = metric + (cell / g.cpt) * g.tile_doubles + (cell % g.cpt) * (long long)g.planes * n3 + t;
+  double *out = metric + (slot / g.cpt) * g.tile_doubles + (slot % g.cpt) * (long long)g.planes * n3 + t;
   for (int c = 0; c < 6; ++c) out[(long long)c * n3] = G[c];
   if (g.planes == 7) {
     // VaryingCoefficientFunctor (step-64/step-64.cu:100-118) times JxW (submit_value,
@@ -237,6 +239,27 @@ static BlockGeom make_geom(bp5_operator_t op) {
   return g;
 }
 
+// Processing order of the cells (= order of cell_base and of the metric tiles): the cells that touch a
+// lower ghost layer ("boundary" cells: the only ones that read ghost values of src and write ghost
+// entries of dst) come first, padded to whole tiles, then all others in lexicographic order.  The cell
+// loop can then run [0, n_boundary_tiles) between the two halves of the halo exchange and
+// [n_boundary_tiles, n_tiles) concurrently with it (MatrixFree's overlap_communication_computation,
+// bp5/step-64.cu:241).  On a single block there are no boundary cells and the order is lexicographic.
+static bool cell_is_boundary(const bp5_operator_t op, int cx, int cy, int cz) {
+  return (cx == 0 && op->has_lo[0]) || (cy == 0 && op->has_lo[1]) || (cz == 0 && op->has_lo[2]);
+}
+
+void operator_plan_tiles(bp5_operator_t op) {
+  // boundary cells: all cells minus those whose three indices are >= has_lo
+  int64_t inner = 1;
+  for (int d = 0; d < 3; ++d) inner *= op->lc[d] - op->has_lo[d];
+  const int64_t n_b = op->n_cells - inner;
+  const int cpt = op->cells_per_tile;
+  op->n_boundary_cells = n_b;
+  op->n_boundary_tiles = (n_b + cpt - 1) / cpt;
+  op->n_tiles = op->n_boundary_tiles + (inner + cpt - 1) / cpt;
+}
+
 int operator_setup_device(bp5_operator_t op) {
   bp5_context_t ctx = op->ctx;
   const int n = op->n, n3 = n * n * n;
@@ -245,24 +268,30 @@ int operator_setup_device(bp5_operator_t op) {
   // per-cell dof descriptors: affine base for regular cells, slot of an explicit
   // table for cells that touch a lower ghost layer, INT_MIN for tile padding
   std::vector<int> base((size_t)padded_cells, INT_MIN);
+  std::vector<long long> slot_of((size_t)op->n_cells);
   int64_t n_irr = 0;
   {
     const int p = op->p;
-    int64_t cell = 0;
+    int64_t cell = 0, next_b = 0, next_i = op->n_boundary_tiles * op->cells_per_tile;
     for (int cz = 0; cz < op->lc[2]; ++cz)
       for (int cy = 0; cy < op->lc[1]; ++cy)
         for (int cx = 0; cx < op->lc[0]; ++cx, ++cell) {
-          const bool irregular = (cx == 0 && op->has_lo[0]) || (cy == 0 && op->has_lo[1]) || (cz == 0 && op->has_lo[2]);
+          const bool irregular = cell_is_boundary(op, cx, cy, cz);
+          const int64_t slot = irregular ? next_b++ : next_i++;
+          slot_of[cell] = slot;
           if (irregular)
-            base[cell] = -(int)(n_irr++) - 1;
+            base[slot] = -(int)(n_irr++) - 1;
           else
-            base[cell] = (int)((cx * p - op->has_lo[0]) +
+            base[slot] = (int)((cx * p - op->has_lo[0]) +
                                (int64_t)op->od[0] * ((cy * p - op->has_lo[1]) + (int64_t)op->od[1] * (cz * p - op->has_lo[2])));
         }
   }
   op->n_irregular = n_irr;
   BP5_CUDA(cudaMalloc(&op->cell_base, sizeof(int) * padded_cells));
   BP5_CUDA(cudaMemcpyAsync(op->cell_base, base.data(), sizeof(int) * padded_cells, cudaMemcpyHostToDevice, ctx->stream));
+  long long *slot_dev = nullptr;
+  BP5_CUDA(cudaMalloc(&slot_dev, sizeof(long long) * op->n_cells));
+  BP5_CUDA(cudaMemcpyAsync(slot_dev, slot_of.data(), sizeof(long long) * op->n_cells, cudaMemcpyHostToDevice, ctx->stream));
   BP5_CUDA(cudaMalloc(&op->l2g_irr, sizeof(int) * std::max<int64_t>(n_irr, 1) * n3));
   const size_t mbytes = sizeof(double) * op->n_tiles * op->tile_doubles;
   BP5_CUDA(cudaMalloc(&op->metric, mbytes));
@@ -270,7 +299,8 @@ int operator_setup_device(bp5_operator_t op) {
   BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
   const int threads = ((n3 + 31) / 32) * 32;
   const size_t smem = sizeof(double) * 8 * n3;
-  setup_cells_kernel<<<(unsigned)op->n_cells, threads, smem, ctx->stream>>>(g, op->cell_base, op->l2g_irr, op->metric);
+  setup_cells_kernel<<<(unsigned)op->n_cells, threads, smem, ctx->stream>>>(g, op->cell_base, slot_dev, op->l2g_irr,
+                                                                            op->metric);
   BP5_CHECK_LAUNCH();
   ctx->launches++;
   const long long n_words = (op->n_owned + 31) / 32;
@@ -304,6 +334,7 @@ int operator_setup_device(bp5_operator_t op) {
     BP5_CUDA(cudaMemcpyAsync(op->constrained, cons.data(), sizeof(int) * cons.size(), cudaMemcpyHostToDevice, ctx->stream));
   }
   BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(slot_dev);
   return BP5_OK;
 }
 
@@ -333,8 +364,11 @@ int operator_export_coefficients(bp5_operator_t op, double *host_out) {
   const int P = op->metric_planes;
   std::vector<double> tmp((size_t)op->n_tiles * op->tile_doubles);
   BP5_CUDA(cudaMemcpy(tmp.data(), op->metric, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+  int64_t next_b = 0, next_i = op->n_boundary_tiles * op->cells_per_tile;
   for (int64_t c = 0; c < op->n_cells; ++c) {
-    const size_t base = (size_t)(c / op->cells_per_tile) * op->tile_doubles + (size_t)(c % op->cells_per_tile) * P * n3;
+    const int cx = (int)(c % op->lc[0]), cy = (int)((c / op->lc[0]) % op->lc[1]), cz = (int)(c / ((int64_t)op->lc[0] * op->lc[1]));
+    const int64_t sl = cell_is_boundary(op, cx, cy, cz) ? next_b++ : next_i++;   // processing-order slot, see operator_plan_tiles
+    const size_t base = (size_t)(sl / op->cells_per_tile) * op->tile_doubles + (size_t)(sl % op->cells_per_tile) * P * n3;
     for (int pl = 0; pl < 6; ++pl)
       std::copy_n(&tmp[base + (size_t)pl * n3], n3, &host_out[((size_t)pl * op->n_cells + c) * n3]);
   }

@@ -9,8 +9,13 @@ MPI_Allreduce of seven doubles (bp5/solver.h:493):
     m = 1..7 (bit d set: the owner is the lower neighbour in dimension d), each group one
     contiguous segment -> a halo message is a plain slice, no unpack on the receiving side of
     update_ghost_values and no pack on the sending side of compress(add);
-  * update_ghost_values / compress(add) move over NCCL send/recv (NVLink) in one group;
-  * the CG scalars are all-reduced on the device (no host round trip inside the loop).
+  * transport "peer" (default): every exchange of the iteration is done by the library's own kernels
+    storing into the neighbour's memory over NVLink (CUDA IPC mappings, csrc/peer.cu), the interior
+    cells overlap the halo, the seven CG scalars are summed through peer mailboxes, and the whole
+    loop is one native call (bp5_peer_cg_solve).  torch.distributed only carries the IPC handles;
+  * transport "nccl": update_ghost_values / compress(add) as NCCL send/recv groups and an
+    all_reduce of the scalars, driven step by step from here (the baseline the peer path is
+    measured against, and the path for blocks that are not in one NVLink domain).
 
 `Partition` is pure host logic (numpy) and is what the CPU `gloo` tests exercise.
 """
@@ -168,7 +173,7 @@ class DistributedPoisson:
     """One block of the partitioned BP5 problem on this rank's GPU + the exchanges around it."""
 
     def __init__(self, degree, cells_per_gpu, quadrature=B.QUAD_GLL, operator_kind=B.OP_POISSON, deformation=0,
-                 eps=0.0, device=None):
+                 eps=0.0, device=None, transport="peer", global_cells=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -176,7 +181,10 @@ class DistributedPoisson:
         self.device = torch.cuda.current_device() if device is None else device
         grid = process_grid(self.world)
         coord = (self.rank % grid[0], (self.rank // grid[0]) % grid[1], self.rank // (grid[0] * grid[1]))
-        cells = tuple(cells_per_gpu[d] * grid[d] for d in range(3))       # weak scaling: fixed block per GPU
+        if global_cells is not None:                                      # strong scaling: fixed global mesh
+            cells = tuple(int(c) for c in global_cells)
+        else:                                                             # weak scaling: fixed block per GPU
+            cells = tuple(cells_per_gpu[d] * grid[d] for d in range(3))
         self.part = Partition(degree, cells, grid, coord)
         self.ctx = B.Context(self.device)
         self.stream = torch.cuda.ExternalStream(self.ctx.stream)
@@ -190,6 +198,28 @@ class DistributedPoisson:
         self.sums = torch.zeros(8, dtype=torch.float64, device=f"cuda:{self.device}")
         torch.cuda.synchronize(self.device)
         self.n_global = self.part.n_global
+        self.transport = transport if self.world > 1 else "nccl"
+        if self.transport == "peer":
+            self._connect_peers()
+        elif self.transport != "nccl":
+            raise ValueError(f"unknown transport {transport!r}")
+
+    def _connect_peers(self):
+        """publish this block's IPC handles, map everybody else's (bp5_peer_export / bp5_peer_connect)"""
+        lib, C, dist = B.lib(), B.C, self.dist
+        info = B.PeerInfo()
+        B._check(lib.bp5_peer_export(self.op.h, self.rank, self.world, C.byref(info)))
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, bytes(info))
+        infos = (B.PeerInfo * self.world)()
+        for r, blob in enumerate(blobs):
+            C.memmove(C.byref(infos[r]), blob, C.sizeof(B.PeerInfo))
+        as_rank = lambda r: -1 if r is None else int(r)
+        upper = (C.c_int32 * 8)(*[as_rank(self.part.upper(m)) if m else -1 for m in range(8)])
+        lower = (C.c_int32 * 8)(*[as_rank(self.part.lower(m)) if m else -1 for m in range(8)])
+        B._check(lib.bp5_peer_connect(self.op.h, infos, upper, lower))
+        self.ctx.synchronize()
+        dist.barrier()          # everybody is mapped before the first exchange
 
     # -- helpers ---------------------------------------------------------------------------------
     def view(self, vec):
@@ -220,6 +250,9 @@ class DistributedPoisson:
     # -- operator --------------------------------------------------------------------------------
     def vmult(self, dst, src):
         """PoissonOperator::vmult with the exchanges of MatrixFree::cell_loop (bp5/step-64.cu:263-276)."""
+        if self.transport == "peer":
+            B._check(B.lib().bp5_peer_vmult(self.op.h, dst.h, src.h))
+            return
         self.update_ghost_values(src)
         dst.set(0.0)
         self.op.cell_loop(dst, src)
@@ -231,6 +264,16 @@ class DistributedPoisson:
         """SolverCGFullMerge::solve over the partition (x must be zero on entry)."""
         lib, op = B.lib(), self.op
         torch, dist = self.torch, self.dist
+        if self.transport == "peer":
+            its, val = B.C.c_int(0), B.C.c_double(0.0)
+            hist = np.full(control.max_its + 2, np.nan) if history else None
+            rc = lib.bp5_peer_cg_solve(op.h, x.h, b.h, diag.h if diag is not None else None, control.kind, control.tol,
+                                       control.max_its, B.C.byref(its), B.C.byref(val),
+                                       hist.ctypes.data_as(B._dp) if history else None, len(hist) if history else 0)
+            control._last_step, control._last_value = its.value, val.value
+            control.history = hist[: its.value + 1] if history else None
+            B._check(rc)
+            return
         res0 = self.l2_norm(b)
         hist_len = control.max_its + 2 if history else 0
         state = 1 if res0 <= control.tol else (0 if control.max_its > 0 else (1 if control.kind == 0 else 2))
@@ -276,6 +319,8 @@ class DistributedPoisson:
     def close(self):
         self.ctx.synchronize()
         self.torch.cuda.synchronize(self.device)
+        if self.transport == "peer":
+            self.dist.barrier()     # nobody unmaps while a neighbour may still store into this block
         self.halo = None
         self.sums = None
         self.op.close()

@@ -246,6 +246,39 @@ int bp5_cg_step_poll(bp5_operator_t op, int *state, int *last_step, double *last
 /* owed x update (solver.h:509-526); history (optional, host) receives history[1..] */
 int bp5_cg_step_finish(bp5_operator_t op, double *history);
 
+/* ---- peer-memory transport: blocks inside one NVLink / NVSwitch domain ------------------ */
+/* One process per GPU.  Instead of CUDA-aware MPI (MPI_Isend/Irecv on device pointers inside
+ * cell_loop [UPSTREAM], tests/cuda_aware_mpi.cc:29-46) and the host MPI_Allreduce of seven doubles
+ * (bp5/solver.h:489-494), every exchange is done by kernels that store into the neighbour's memory
+ * through CUDA IPC mappings and signal with flags; the cells that need no ghost data run while the
+ * halo is in flight (overlap_communication_computation, bp5/step-64.cu:241).
+ *   1. every rank: bp5_peer_export(op, rank, world, &info)      -> publish `info` to all ranks
+ *      (any byte transport: MPI_Allgather, torch.distributed.all_gather_object, a file ...)
+ *   2. every rank: bp5_peer_connect(op, all_infos, upper_rank, lower_rank)
+ *      upper_rank[m] / lower_rank[m], m = 1..7 direction mask: the rank that receives this block's
+ *      send group m / that owns its ghost group m, or -1
+ *   3. a barrier of the caller's (all ranks connected) before the first exchange, and one before destroy
+ *   4. bp5_peer_cg_solve / bp5_peer_vmult: collective calls, same arguments on every rank. */
+typedef struct bp5_peer_info {
+  unsigned char buf_handle[64];   /* cudaIpcMemHandle_t: landing zone, mailboxes, flags */
+  unsigned char dvec_handle[64];  /* cudaIpcMemHandle_t: the vector whose ghost segments receive update_ghost_values */
+  int64_t n_owned, n_ghost, n_send;
+  int64_t ghost_offset[8];        /* start of ghost group m relative to n_owned */
+  int64_t send_offset[8];         /* start of send group m in the landing zone */
+  int32_t rank, device;
+} bp5_peer_info_t;
+int bp5_peer_export(bp5_operator_t op, int rank, int world, bp5_peer_info_t *info);
+int bp5_peer_connect(bp5_operator_t op, const bp5_peer_info_t *all_infos, const int32_t *upper_rank,
+                     const int32_t *lower_rank);
+/* dst = A src over the partition (owned range of dst; vmult, bp5/step-64.cu:263-276) */
+int bp5_peer_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src);
+/* SolverCGFullMerge::solve over the partition; x must be zero on entry (the reference's use,
+ * bp5/step-64.cu:491); arguments and results as bp5_cg_solve, identical on every rank */
+int bp5_peer_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,
+                      int max_its, int *last_step, double *last_value, double *history, int history_len);
+/* in-place sum over all ranks of n <= 8 host values (l2_norm and friends, bp5/solver.h:382) */
+int bp5_peer_allreduce(bp5_operator_t op, double *values, int n);
+
 #ifdef __cplusplus
 }
 #endif

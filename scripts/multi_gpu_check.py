@@ -14,8 +14,10 @@ local_rank = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(local_rank)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 fails = 0
-for p, cpg, quad, deform in [(2, (3, 2, 2), dc.QUAD_GAUSS, 0), (4, (2, 2, 3), dc.QUAD_GLL, 1), (6, (2, 2, 2), dc.QUAD_GLL, 1), (5, (3, 3, 2), dc.QUAD_GAUSS, 0)]:
-    P = DistributedPoisson(p, cpg, quadrature=quad, deformation=deform, eps=0.1, device=local_rank)
+CASES = [(2, (3, 2, 2), dc.QUAD_GAUSS, 0), (4, (2, 2, 3), dc.QUAD_GLL, 1), (6, (2, 2, 2), dc.QUAD_GLL, 1),
+         (5, (3, 3, 2), dc.QUAD_GAUSS, 0)]
+for transport, (p, cpg, quad, deform) in [(t, c) for t in ("peer", "nccl") for c in CASES]:
+    P = DistributedPoisson(p, cpg, quadrature=quad, deformation=deform, eps=0.1, device=local_rank, transport=transport)
     cells = P.part.cells
     m = O.OracleMesh(p, cells, quad=quad, deform=deform, eps=0.1)
     gi = P.op.global_indices()
@@ -41,7 +43,7 @@ for p, cpg, quad, deform in [(2, (3, 2, 2), dc.QUAD_GAUSS, 0), (4, (2, 2, 3), dc
     good = rel <= 1e-12 and abs(ctl.last_step() - its) <= 1 and xerr <= 1e-7
     fails += 0 if good else 1
     if rank == 0:
-        print(f"{'OK  ' if good else 'FAIL'} world={world} grid={P.part.grid} p={p} cells={cells} quad={quad} deform={deform}: "
+        print(f"{'OK  ' if good else 'FAIL'} transport={transport} world={world} grid={P.part.grid} p={p} cells={cells} quad={quad} deform={deform}: "
               f"vmult rel err {rel:.2e}, CG its {ctl.last_step()} (oracle {its}), x rel err {xerr:.2e}", flush=True)
     for v in (src, dst, b, x):
         v.close()
