@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--degree", type=int, default=6)
     ap.add_argument("--cells", type=int, default=88, help="cells per direction per GPU")
     ap.add_argument("--quadrature", default="gll", choices=["gll", "gauss"])
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N>1: halo + scalar exchange through peer memory (library kernels) or NCCL")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = --cells^3 cells per GPU; strong = --cells^3 cells in total, split over the GPUs")
     ap.add_argument("--no-variants", action="store_true", help="skip the second quadrature")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells", type=int, default=0, help="cells per direction of the CPU sample (0 = auto)")

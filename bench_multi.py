@@ -1,6 +1,7 @@
-"""N>1 leg of bench.py: one rank per GPU (torchrun), weak scaling -- every GPU holds a
-cells^3 block of a P_x x P_y x P_z partition (1x1x1, 2x1x1, 2x2x1, 2x2x2), halo exchange over
-NCCL/NVLink inside every operator application and one allreduce of the 7 CG scalars per iteration."""
+"""N>1 leg of bench.py: one rank per GPU (torchrun).  Weak scaling (default): every GPU holds a cells^3
+block of a P_x x P_y x P_z partition (1x1x1, 2x1x1, 2x2x1, 2x2x2); strong scaling (--scaling strong): one
+cells^3 mesh split over the GPUs.  Halo exchange inside every operator application and one sum of the 7 CG
+scalars per iteration, through peer memory over NVLink (--transport peer, default) or NCCL (--transport nccl)."""
 import json
 import os
 import sys
@@ -30,7 +31,9 @@ def run(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
 
-    P = DistributedPoisson(args.degree, (args.cells,) * 3, quadrature=quad_ids[args.quadrature], device=local_rank)
+    strong = args.scaling == "strong"
+    P = DistributedPoisson(args.degree, (args.cells,) * 3, quadrature=quad_ids[args.quadrature], device=local_rank,
+                           transport=args.transport, global_cells=(args.cells,) * 3 if strong else None)
     op, ctx = P.op, P.ctx
     b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
     op.assemble_rhs(b)
@@ -108,14 +111,18 @@ def run(args):
         out = {
             "metric": single.METRIC, "value": n_glob * its_total / secs / 1e9, "unit": single.UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"BP5 Poisson, p={args.degree}, {args.cells}^3 cells per GPU, {grid[0]}x{grid[1]}x{grid[2]} blocks = "
+                "workload": f"BP5 Poisson, p={args.degree}, {args.cells}^3 cells {'in total' if strong else 'per GPU'}, "
+                            f"{grid[0]}x{grid[1]}x{grid[2]} blocks = "
                             f"{n_glob} DoFs, {args.quadrature} quadrature, merged CG, IterationNumberControl({single.MAX_ITS}, 1e-6|b|), "
                             f"{its_total / args.steps:.0f} iterations per step",
-                "quadrature": args.quadrature, "degree": args.degree, "cells_per_gpu": args.cells ** 3,
+                "quadrature": args.quadrature, "degree": args.degree, "cells_per_gpu": op.n_cells,
                 "dofs_global": n_glob, "dofs_per_gpu": n_glob / world,
-                "parallelism": f"domain decomposition {grid[0]}x{grid[1]}x{grid[2]}, NCCL halo (send/recv) + allreduce(7 doubles)/iteration",
+                "parallelism": f"domain decomposition {grid[0]}x{grid[1]}x{grid[2]}, " + (
+                    "peer-memory halo (P2P stores over NVLink, interior cells overlap) + mailbox sum of 7 doubles/iteration"
+                    if P.transport == "peer" else "NCCL halo (send/recv) + allreduce(7 doubles)/iteration"),
+                "transport": P.transport,
                 "iterations_per_step": its_total / args.steps,
                 "l2": "no flush: vectors and metric are far larger than the 126 MB L2", "kernel": op.kernel_name,
             },

@@ -151,16 +151,18 @@ __device__ __forceinline__ void gather_column(double (&u)[N], const double *__re
 // Rows of the outer loop handled per (rolled) iteration: U independent DFMA
 // chains for latency hiding, with U*N matrix entries (2 uniform registers each)
 // live at a time -- must stay well inside the 63-entry uniform register file.
+// Measured (profiles/r1_v3_notes.md): n <= 8 full unroll everywhere.  n = 9 (81 matrix entries do not fit the
+// uniform register file): full unroll wins where the kernel still fits 4 CTAs/SM (<= 170 registers:
+// collocation without the fused dot product, Gauss with it), chunks of 3 rows elsewhere.
 #ifndef BP5_ROW_CHUNK
-#define BP5_ROW_CHUNK(N) ((N) == 9 ? 3 : (N))
+#define BP5_ROW_CHUNK(N, QUAD, MODE) ((N) == 9 ? ((((QUAD) == 1 && (MODE) < 2) || ((QUAD) == 0 && (MODE) == 2)) ? 9 : 3) : (N))
 #endif
 
 // out[i*stride] = sum_m M[i][m] v[m], outer loop ROLLED in chunks of U rows
 // (see header comment).
-template <int N>
+template <int N, int U>
 __device__ __forceinline__ void contract_to_smem(double *out, int stride, const double *__restrict__ M,
                                                  const double (&v)[N]) {
-  constexpr int U = BP5_ROW_CHUNK(N);
 #pragma unroll 1
   for (int i0 = 0; i0 < N; i0 += U) {
     const double *row = M + i0 * N;
@@ -228,6 +230,7 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
     bp5_apply_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
   using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = Cfg::N, N2 = Cfg::N2, N3 = Cfg::N3, PLANES = 6 + HELM;
+  constexpr int RC = BP5_ROW_CHUNK(N, QUAD, OVERWRITE);     // rows per rolled iteration of a line contraction
   using L = typename Cfg::L;
   constexpr int A1 = L::A_S1, A2 = L::A_S2, B1 = L::B_S1, B2 = L::B_S2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -336,23 +339,23 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
-        contract_to_smem<N>(s1 + xA, 1, Dx, v);
+        contract_to_smem<N, RC>(s1 + xA, 1, Dx, v);
 #pragma unroll
         for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
-        contract_to_smem<N>(s2 + yB, B1, Dy, v);
+        contract_to_smem<N, RC>(s2 + yB, B1, Dy, v);
       }
       __syncthreads();
     } else {
       // ---------------- Gauss quadrature: interpolate to the q-points first
       // (1) home (i=a, j=b): z-interpolation
-      if (active) contract_to_smem<N>(s0 + hA, A2, Bz, u);
+      if (active) contract_to_smem<N, RC>(s0 + hA, A2, Bz, u);
       __syncthreads();
       // (2) x-line (j=a, qz=b): x-interpolation in place
       if (active) {
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
-        contract_to_smem<N>(s0 + xA, 1, Bx, v);
+        contract_to_smem<N, RC>(s0 + xA, 1, Bx, v);
       }
       __syncthreads();
       // (3) y-line (qx=a, qz=b): y-interpolation (values at q-points), then d/dy
@@ -363,7 +366,7 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         contract_in_regs<N>(w, By, v);
 #pragma unroll
         for (int q = 0; q < N; ++q) s0[yA + q * A1] = w[q];
-        contract_to_smem<N>(s2 + yB, B1, Dy, w);
+        contract_to_smem<N, RC>(s2 + yB, B1, Dy, w);
       }
       __syncthreads();
       // (4) x-line (qy=a, qz=b): d/dx ; home (qx=a, qy=b): d/dz in registers
@@ -371,7 +374,7 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
-        contract_to_smem<N>(s1 + xA, 1, Dx, v);
+        contract_to_smem<N, RC>(s1 + xA, 1, Dx, v);
 #pragma unroll
         for (int k = 0; k < N; ++k) v[k] = s0[hA + k * A2];
         contract_in_regs<N>(t, Dz, v);
@@ -435,10 +438,10 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s1[xA + i];
-        contract_to_smem<N>(s1 + xA, 1, DTx, v);
+        contract_to_smem<N, RC>(s1 + xA, 1, DTx, v);
 #pragma unroll
         for (int j = 0; j < N; ++j) v[j] = s2[yB + j * B1];
-        contract_to_smem<N>(s2 + yB, B1, DTy, v);
+        contract_to_smem<N, RC>(s2 + yB, B1, DTy, v);
       }
       __syncthreads();
       // (5) home: z-transpose in registers, sum the three directions, scatter
@@ -460,14 +463,14 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s1[xA + i];
-        contract_to_smem<N>(s1 + xA, 1, DTx, v);
+        contract_to_smem<N, RC>(s1 + xA, 1, DTx, v);
         if constexpr (HELM) {
           double o[N];
           contract_in_regs<N>(o, DTz, t);
 #pragma unroll
           for (int k = 0; k < N; ++k) s0[hA + k * A2] = o[k] + mv[k];
         } else {
-          contract_to_smem<N>(s0 + hA, A2, DTz, t);
+          contract_to_smem<N, RC>(s0 + hA, A2, DTz, t);
         }
       }
       __syncthreads();
@@ -479,7 +482,7 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         contract_in_regs<N>(y, DTy, v);
 #pragma unroll
         for (int q = 0; q < N; ++q) y[q] += s1[yA + q * A1] + s0[yA + q * A1];
-        contract_to_smem<N>(s0 + yA, A1, BTy, y);
+        contract_to_smem<N, RC>(s0 + yA, A1, BTy, y);
       }
       __syncthreads();
       // (7) x-line (j=a, qz=b): B^T along x in place
@@ -487,7 +490,7 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N];
 #pragma unroll
         for (int q = 0; q < N; ++q) v[q] = s0[xA + q];
-        contract_to_smem<N>(s0 + xA, 1, BTx, v);
+        contract_to_smem<N, RC>(s0 + xA, 1, BTx, v);
       }
       __syncthreads();
       // (8) home (i=a, j=b): B^T along z in registers, scatter

@@ -15,7 +15,7 @@ namespace bp5 {
 
 constexpr int kMaxDegree = 8;
 constexpr int kApplyPartialCap = 4096;      // per-CTA partial sums of the cell kernel's fused dot product
-constexpr int kConstrainedPartials = 148;   // blocks (= partial sums) of the Dirichlet-copy correction
+constexpr int kConstrainedPartials = 148 * 8;   // blocks (= partial sums) of the Dirichlet-copy correction
 constexpr int kMaxN = kMaxDegree + 1;
 
 // ---- error plumbing --------------------------------------------------------

@@ -249,6 +249,7 @@ int peer_export(bp5_operator_t op, int rank, int world, bp5_peer_info_t *out) {
     BP5_CUDA(cudaMemset(ps->ticket, 0, sizeof(unsigned) * 4));
     BP5_CUDA(cudaMalloc(&ps->scratch, sizeof(double) * 16));
     BP5_CUDA(cudaMemset(ps->scratch, 0, sizeof(double) * 16));
+    BP5_CUDA(cudaDeviceSynchronize());   // the memsets ran on the default stream; everything else uses ctx->stream
     op->peer = ps;
   }
   PeerState *ps = static_cast<PeerState *>(op->peer);

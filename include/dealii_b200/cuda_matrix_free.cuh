@@ -75,7 +75,11 @@ template <typename Number> class Vector {
   void reinit(std::size_t n) {
     cudaFree(data); data = nullptr; n_elements = n;
     b200::check_cuda(cudaMalloc(&data, sizeof(Number) * (n ? n : 1)), "cudaMalloc");
-    b200::check_cuda(cudaMemset(data, 0, sizeof(Number) * (n ? n : 1)), "cudaMemset");
+    // zero on the library's (non-blocking) stream: everything that touches this array later runs there, and a
+    // memset on the legacy default stream would not be ordered with it
+    cudaStream_t stream = static_cast<cudaStream_t>(bp5_context_stream(b200::Context::get()));
+    b200::check_cuda(cudaMemsetAsync(data, 0, sizeof(Number) * (n ? n : 1), stream), "cudaMemsetAsync");
+    b200::check_cuda(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
   }
   Number *get_values() const { return data; }
   std::size_t size() const { return n_elements; }
