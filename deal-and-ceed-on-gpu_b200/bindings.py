@@ -106,7 +106,7 @@ ABI = [
     ("bp5_vector_zero_out_ghosts", C.c_int, [_vp]),
     ("bp5_cg_solve", C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _dp,
                                _dp, C.c_int]),
-    ("bp5_cg_solve_host", C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
+    ("bp5_cg_solve_host", C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.POINTER(C.c_int), _dp]),
     ("bp5_operator_matrix_free_data", C.c_int, [_vp, _vp]),
     ("bp5_operator_halo_info", C.c_int, [_vp] + [C.POINTER(C.c_int64)] * 4),
@@ -392,10 +392,11 @@ class SolverCG(_SolverBase):
     variant = CG_STANDARD
 
 
-def cg_solve_host(A, x_host, b_host, control, variant=CG_MERGED):
-    """End-to-end entry point with HOST buffers (copies inside)."""
+def cg_solve_host(A, x_host, b_host, control, variant=CG_MERGED, x0_is_zero=False):
+    """End-to-end entry point with HOST buffers (copies inside).  x0_is_zero: zero initial guess, x_host output only."""
     its, val = C.c_int(0), C.c_double(0.0)
-    rc = lib().bp5_cg_solve_host(A.h, x_host.ctypes.data, b_host.ctypes.data, x_host.size, variant, control.kind,
+    rc = lib().bp5_cg_solve_host(A.h, x_host.ctypes.data, b_host.ctypes.data, x_host.size, int(x0_is_zero), variant,
+                                 control.kind,
                                  control.tol, control.max_its, C.byref(its), C.byref(val))
     control._last_step, control._last_value = its.value, val.value
     _check(rc)

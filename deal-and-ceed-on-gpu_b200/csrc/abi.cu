@@ -473,8 +473,8 @@ int bp5_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t
   BP5_ABI_GUARD_END
 }
 
-int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, int64_t n, int variant, int control,
-                      double tol, int max_its, int *last_step, double *last_value) {
+int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, int64_t n, int x0_is_zero, int variant,
+                      int control, double tol, int max_its, int *last_step, double *last_value) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && x_host && b_host, "null argument");
   BP5_REQUIRE(n == op->n_owned && op->n_ghost == 0, "host solve needs a single block and n == n_dofs");
@@ -486,7 +486,8 @@ int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, i
     if ((rc = bp5_vector_create(ctx, n, 0, &op->bh))) return rc;
   }
   BP5_CUDA(cudaMemcpyAsync(op->bh->d, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-  BP5_CUDA(cudaMemcpyAsync(op->xh->d, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (x0_is_zero) BP5_CUDA(cudaMemsetAsync(op->xh->d, 0, sizeof(double) * n, ctx->stream));
+  else BP5_CUDA(cudaMemcpyAsync(op->xh->d, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
   const int rc = cg_solve(op, op->xh, op->bh, nullptr, variant, control, tol, max_its, last_step, last_value, nullptr, 0);
   if (rc != BP5_OK && rc != BP5_ERR_NO_CONVERGENCE) return rc;
   BP5_CUDA(cudaMemcpyAsync(x_host, op->xh->d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));

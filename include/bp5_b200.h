@@ -174,8 +174,10 @@ int bp5_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t
                  int control, double tol, int max_its, int *last_step, double *last_value,
                  double *history, int history_len);
 /* same, with HOST buffers: copies b (and x0) to the device, solves, copies x
- * back -- the end-to-end entry point a host-side caller uses. */
-int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, int64_t n, int variant,
+ * back -- the end-to-end entry point a host-side caller uses.
+ *   x0_is_zero != 0: the initial guess is zero, as in the reference's drivers (solution = 0 before every
+ *   solve, bp5/step-64.cu:449,491); x_host is then output only and is not uploaded. */
+int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, int64_t n, int x0_is_zero, int variant,
                       int control, double tol, int max_its, int *last_step, double *last_value);
 
 /* ---- user-written cell functors (generic MatrixFree path) ------------------- */

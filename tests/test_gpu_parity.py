@@ -266,3 +266,29 @@ def test_vector_ops(gpu_ctx):
     A.set(3.0)
     assert np.all(A.to_host() == 3.0)
     A.close(); B.close()
+
+
+def test_host_buffer_solve_matches_device_solve(gpu_ctx):
+    """bp5_cg_solve_host (the end-to-end entry point bench.py times): zero-start flag and explicit x0 agree with
+    the device-vector solve and the oracle"""
+    dc = _dc()
+    import oracle as O
+    p, cells = 3, (4, 3, 3)
+    op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=dc.QUAD_GLL, deformation=1, eps=0.1))
+    m = O.OracleMesh(p, cells, quad=O.GLL, deform=1, eps=0.1)
+    bh = m.rhs()
+    tol = 1e-8 * np.linalg.norm(bh)
+    xo, its, _, _, _ = m.cg(bh, variant=1, control=1, tol=tol, max_its=500)
+    op.do_zero_out = False
+    for zero_flag in (True, False):
+        x = np.full(op.n_owned, 123.0) if zero_flag else np.zeros(op.n_owned)   # garbage must be ignored with the flag
+        ctl = dc.SolverControl(500, tol)
+        dc.cg_solve_host(op, x, bh, ctl, x0_is_zero=zero_flag)
+        assert abs(ctl.last_step() - its) <= 1
+        assert relerr(x, xo) <= 1e-7
+    # a non-zero initial guess: start from the solution, expect immediate convergence
+    x = xo.copy()
+    ctl = dc.SolverControl(500, 1e-6 * np.linalg.norm(bh))
+    dc.cg_solve_host(op, x, bh, ctl, x0_is_zero=False)
+    assert ctl.last_step() <= 1
+    op.close()
