@@ -1,13 +1,8 @@
-# usage: bash scripts/job_multi.sh <ngpus> ; writes gpurun_out/multi_<n>_<transport>_<scaling>.json
 N=$1
 run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 3 --warmup 2 "$@"; }
 run --transport peer --scaling weak   > gpurun_out/multi_${N}_peer_weak.json   2> gpurun_out/multi_${N}_peer_weak.err
-run --transport nccl --scaling weak   > gpurun_out/multi_${N}_nccl_weak.json   2> gpurun_out/multi_${N}_nccl_weak.err
 run --transport peer --scaling strong > gpurun_out/multi_${N}_peer_strong.json 2> gpurun_out/multi_${N}_peer_strong.err
-run --transport nccl --scaling strong > gpurun_out/multi_${N}_nccl_strong.json 2> gpurun_out/multi_${N}_nccl_strong.err
-# small mesh (44^3 cells, 18.6 M DoFs in total): the latency-bound end of strong scaling
 run --transport peer --scaling strong --cells 44 > gpurun_out/multi_${N}_peer_strong44.json 2> gpurun_out/multi_${N}_peer_strong44.err
-run --transport nccl --scaling strong --cells 44 > gpurun_out/multi_${N}_nccl_strong44.json 2> gpurun_out/multi_${N}_nccl_strong44.err
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("gpurun_out/multi_${N}_*.json")):
