@@ -362,6 +362,70 @@ static void launch_dots(bool has_diag, bool lean, cudaStream_t s, CgState *st, c
 #undef BP5_DOTS
 }
 
+// Iteration loop shared by cg_solve() and cg_solve_peer().  `enqueue(cur)` puts iteration `cur` (1-based) on the
+// stream.  The first kWarm iterations are enqueued directly (they also trigger the one-time kernel attribute
+// set-up); after that one batch of kBatch iterations is captured into a CUDA graph and replayed, which removes
+// most of the launch latency that dominates small blocks (everything an iteration needs -- alpha, beta, epochs,
+// the "converged, do nothing" word -- lives in device memory, so the replay needs no new arguments).  After each
+// batch the state word of the batch before last is polled, so the GPU never waits for the host; iterations
+// enqueued past convergence or past max_its are no-ops.
+template <typename Enqueue>
+static int run_iterations(bp5_operator_t op, CgState *st, int max_its, Enqueue enqueue) {
+  bp5_context_t ctx = op->ctx;
+  cudaStream_t s = ctx->stream;
+  constexpr int kBatch = 8, kWarm = 3;                  // kWarm odd, kBatch even: a batch starts on an even iteration
+  const bool use_graph = !op->profile && max_its >= kWarm + 2 * kBatch && getenv("BP5_NO_GRAPH") == nullptr;
+  volatile int *poll_host = reinterpret_cast<volatile int *>(ctx->scratch_host + 8);   // two slots
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  BP5_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  BP5_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  poll_host[0] = poll_host[1] = 0;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int64_t launches_per_graph = 0;
+  int it = 0, nbatch = 0, rc = BP5_OK;
+  bool done = false;
+  while (!done && it < max_its && rc == BP5_OK) {
+    if (use_graph && it >= kWarm) {
+      if (!gexec) {
+        const int64_t l0 = ctx->launches;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
+        for (int k = 0; k < kBatch && rc == BP5_OK; ++k) rc = enqueue(it + 1 + k);
+        const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+        if (rc != BP5_OK) break;
+        if (ee != cudaSuccess || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+          set_error("CUDA graph capture of the CG batch failed: %s", cudaGetErrorString(cudaGetLastError()));
+          rc = BP5_ERR_CUDA;
+          break;
+        }
+        launches_per_graph = ctx->launches - l0;
+        ctx->launches = l0;
+      }
+      if (cudaGraphLaunch(gexec, s) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
+      ctx->launches += launches_per_graph;
+      it += kBatch;
+    } else {
+      const int upto = std::min(max_its, it + (it < kWarm ? kWarm - it : kBatch));
+      for (; it < upto && rc == BP5_OK; ++it) rc = enqueue(it + 1);
+    }
+    if (rc != BP5_OK) break;
+    const int slot = nbatch & 1;
+    if (cudaMemcpyAsync((void *)&poll_host[slot], &st->state, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaEventRecord(ev[slot], s) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
+    if (nbatch >= 1) {
+      if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
+      if (poll_host[slot ^ 1] != 0) done = true;
+    }
+    ++nbatch;
+  }
+  if (rc == BP5_ERR_CUDA && get_error()[0] == 0) set_error("CUDA error in the CG loop: %s", cudaGetErrorString(cudaGetLastError()));
+  if (gexec) { cudaStreamSynchronize(s); cudaGraphExecDestroy(gexec); }
+  if (graph) cudaGraphDestroy(graph);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  return rc;
+}
+
 int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diagv, int variant, int control,
              double tol, int max_its, int *last_step, double *last_value, double *history, int history_len) {
   bp5_context_t ctx = op->ctx;
@@ -440,62 +504,41 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
   }
   BP5_CUDA(cudaMemcpyAsync(st, &init, sizeof(CgState), cudaMemcpyHostToDevice, s));
 
-  // Iteration loop.  The host enqueues batches of iterations and looks at the
-  // state word of the batch before last, so the GPU never waits for the host.
-  constexpr int kBatch = 8;
-  volatile int *poll_host = reinterpret_cast<volatile int *>(ctx->scratch_host + 8);   // two slots
-  cudaEvent_t ev[2];
-  BP5_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  BP5_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-  poll_host[0] = poll_host[1] = 0;
   op->skip_flag = &st->state;
-  int it = 0, nbatch = 0;
-  bool done = false;
-  rc = BP5_OK;
-  while (!done && it < max_its && rc == BP5_OK) {
-    const int upto = std::min(max_its, it + kBatch);
-    for (; it < upto && rc == BP5_OK; ++it) {
-      const int cur = it + 1;
-      if (variant == BP5_CG_MERGED) {
-        // 1) update region (solver.h:413-448), with the parity-correct x update
-        //    (+ r.r, r.Dr of the new residual as per-block partials)
-        if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
-        else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
-        else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
-        ctx->launches++;
-        // 2) h = A d with do_zero_out = false (solver.h:475; h's skeleton zeroed by the update kernel,
-        //    its cell-interior entries are overwritten by the cell kernel) + d.h as per-CTA partials
-        if ((rc = apply_cell_loop(op, h, d, true, cb.ph))) break;
-        if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + op->apply_grid))) break;
-        // 3)+4) the remaining dots (h.h, r.h, r.Dh, h.Dh) and the scalars (solver.h:478-533)
-        launch_dots<true>(has_diag, /*lean=*/true, s, st, d, g, h, diag, n, cb, nullptr, op->apply_grid + n_corr,
-                          (int)grid);
-        ctx->launches++;
+  auto enqueue = [&](int cur) -> int {
+    int rc = BP5_OK;
+    if (variant == BP5_CG_MERGED) {
+      // 1) update region (solver.h:413-448), with the parity-correct x update
+      //    (+ r.r, r.Dr of the new residual as per-block partials)
+      if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+      else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+      else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+      ctx->launches++;
+      // 2) h = A d with do_zero_out = false (solver.h:475; h's skeleton zeroed by the update kernel,
+      //    its cell-interior entries are overwritten by the cell kernel) + d.h as per-CTA partials
+      if ((rc = apply_cell_loop(op, h, d, true, cb.ph))) return rc;
+      if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + op->apply_grid))) return rc;
+      // 3)+4) the remaining dots (h.h, r.h, r.Dh, h.Dh) and the scalars (solver.h:478-533)
+      launch_dots<true>(has_diag, /*lean=*/true, s, st, d, g, h, diag, n, cb, nullptr, op->apply_grid + n_corr,
+                        (int)grid);
+      ctx->launches++;
+    } else {
+      if ((rc = apply_zero_skeleton(op, h))) return rc;
+      if ((rc = apply_cell_loop(op, h, d, true, cb.ph))) return rc;
+      if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + op->apply_grid))) return rc;
+      std_alpha_kernel<<<1, kCgThreads, 0, s>>>(st, cb.ph, op->apply_grid + n_corr);   // alpha = gh / (d.h)
+      if (has_diag) {
+        std_xg_kernel<true><<<kCgBlocks, kCgThreads, 0, s>>>(st, x->d, g, d, h, diag, n, partials, hist_dev);
+        std_d_kernel<true><<<grid, 256, 0, s>>>(st, d, g, diag, n);
       } else {
-        if ((rc = apply_zero_skeleton(op, h))) break;
-        if ((rc = apply_cell_loop(op, h, d, true, cb.ph))) break;
-        if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + op->apply_grid))) break;
-        std_alpha_kernel<<<1, kCgThreads, 0, s>>>(st, cb.ph, op->apply_grid + n_corr);   // alpha = gh / (d.h)
-        if (has_diag) {
-          std_xg_kernel<true><<<kCgBlocks, kCgThreads, 0, s>>>(st, x->d, g, d, h, diag, n, partials, hist_dev);
-          std_d_kernel<true><<<grid, 256, 0, s>>>(st, d, g, diag, n);
-        } else {
-          std_xg_kernel<false><<<kCgBlocks, kCgThreads, 0, s>>>(st, x->d, g, d, h, diag, n, partials, hist_dev);
-          std_d_kernel<false><<<grid, 256, 0, s>>>(st, d, g, diag, n);
-        }
-        ctx->launches += 3;
+        std_xg_kernel<false><<<kCgBlocks, kCgThreads, 0, s>>>(st, x->d, g, d, h, diag, n, partials, hist_dev);
+        std_d_kernel<false><<<grid, 256, 0, s>>>(st, d, g, diag, n);
       }
+      ctx->launches += 3;
     }
-    if (rc != BP5_OK) break;
-    const int slot = nbatch & 1;
-    if (cudaMemcpyAsync((void *)&poll_host[slot], &st->state, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaEventRecord(ev[slot], s) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
-    if (nbatch >= 1) {
-      if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
-      if (poll_host[slot ^ 1] != 0) done = true;
-    }
-    ++nbatch;
-  }
+    return BP5_OK;
+  };
+  rc = run_iterations(op, st, max_its, enqueue);
   op->skip_flag = nullptr;
   if (rc == BP5_OK && variant == BP5_CG_MERGED) {
     if (has_diag) cg_finish_kernel<true><<<grid, 256, 0, s>>>(st, x->d, d, g, diag, n);
@@ -505,8 +548,6 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
   CgState fin{};
   cudaError_t e1 = cudaMemcpyAsync(&fin, st, sizeof(CgState), cudaMemcpyDeviceToHost, s);
   cudaError_t e2 = cudaStreamSynchronize(s);
-  cudaEventDestroy(ev[0]);
-  cudaEventDestroy(ev[1]);
   if (rc != BP5_OK) return rc;
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     set_error("CG loop failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -727,49 +768,30 @@ int cg_solve_peer(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_
   BP5_REQUIRE(grid <= (unsigned)kUpdatePartialCap, "update grid exceeds the partial-sum buffer");
   const int n_corr = op->n_constrained > 0 ? kConstrainedPartials : 0;
 
-  constexpr int kBatch = 8;
-  volatile int *poll_host = reinterpret_cast<volatile int *>(ctx->scratch_host + 8);
-  cudaEvent_t ev[2];
-  BP5_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  BP5_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-  poll_host[0] = poll_host[1] = 0;
   op->skip_flag = &st->state;
-  int it = 0, nbatch = 0;
-  bool done = false;
-  rc = BP5_OK;
-  while (!done && it < max_its && rc == BP5_OK) {
-    const int upto = std::min(max_its, it + kBatch);
-    for (; it < upto && rc == BP5_OK; ++it) {
-      const int cur = it + 1;
-      if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
-      else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
-      else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
-      ctx->launches++;
-      if (op->n_ghost && cudaMemsetAsync(h + n, 0, sizeof(double) * op->n_ghost, s) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
-      if ((rc = peer_forward(op, d))) break;
-      if ((rc = apply_cell_loop(op, h, d, true, cb.ph, 1))) break;
-      const int grid_b = op->apply_grid;
-      if ((rc = peer_reverse(op, h))) break;
-      if ((rc = apply_cell_loop(op, h, d, true, cb.ph + grid_b, 2))) break;
-      const int n_ph = grid_b + op->apply_grid;
-      if ((rc = peer_wait_add(op, h))) break;
-      if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + n_ph))) break;
-      launch_dots<false>(has_diag, /*lean=*/true, s, st, d, g, h, diag, n, cb, sums, n_ph + n_corr, (int)grid);
-      ctx->launches++;
-      if ((rc = peer_allreduce(op, sums, sums + 8, 7, true))) break;
-      cg_scalars_kernel<<<1, 32, 0, s>>>(st, sums + 8, cb.hist);
-      ctx->launches++;
-    }
-    if (rc != BP5_OK) break;
-    const int slot = nbatch & 1;
-    if (cudaMemcpyAsync((void *)&poll_host[slot], &st->state, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaEventRecord(ev[slot], s) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
-    if (nbatch >= 1) {
-      if (cudaEventSynchronize(ev[slot ^ 1]) != cudaSuccess) { rc = BP5_ERR_CUDA; break; }
-      if (poll_host[slot ^ 1] != 0) done = true;
-    }
-    ++nbatch;
-  }
+  auto enqueue = [&](int cur) -> int {
+    int rc = BP5_OK;
+    if (cur == 1) launch_update<0>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+    else if (cur % 2 == 0) launch_update<1>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+    else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
+    ctx->launches++;
+    if (op->n_ghost) BP5_CUDA(cudaMemsetAsync(h + n, 0, sizeof(double) * op->n_ghost, s));
+    if ((rc = peer_forward(op, d))) return rc;
+    if ((rc = apply_cell_loop(op, h, d, true, cb.ph, 1))) return rc;
+    const int grid_b = op->apply_grid;
+    if ((rc = peer_reverse(op, h))) return rc;
+    if ((rc = apply_cell_loop(op, h, d, true, cb.ph + grid_b, 2))) return rc;
+    const int n_ph = grid_b + op->apply_grid;
+    if ((rc = peer_wait_add(op, h))) return rc;
+    if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + n_ph))) return rc;
+    launch_dots<false>(has_diag, /*lean=*/true, s, st, d, g, h, diag, n, cb, sums, n_ph + n_corr, (int)grid);
+    ctx->launches++;
+    if ((rc = peer_allreduce(op, sums, sums + 8, 7, true))) return rc;
+    cg_scalars_kernel<<<1, 32, 0, s>>>(st, sums + 8, cb.hist);
+    ctx->launches++;
+    return BP5_OK;
+  };
+  rc = run_iterations(op, st, max_its, enqueue);
   op->skip_flag = nullptr;
   if (rc == BP5_OK) {
     if (has_diag) cg_finish_kernel<true><<<grid, 256, 0, s>>>(st, x->d, d, g, diag, n);
@@ -779,8 +801,6 @@ int cg_solve_peer(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_
   CgState fin{};
   cudaError_t e1 = cudaMemcpyAsync(&fin, st, sizeof(CgState), cudaMemcpyDeviceToHost, s);
   cudaError_t e2 = cudaStreamSynchronize(s);
-  cudaEventDestroy(ev[0]);
-  cudaEventDestroy(ev[1]);
   if (rc != BP5_OK) return rc;
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     set_error("CG loop failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
