@@ -46,6 +46,9 @@ def parse():
                     help="N>1: halo + scalar exchange through peer memory (library kernels) or NCCL")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = --cells^3 cells per GPU; strong = --cells^3 cells in total, split over the GPUs")
+    ap.add_argument("--geometry", default="stored", choices=["stored", "otf"],
+                    help="stored metric tensor (headline) or geometry recomputed in the kernel (config 5; gll only)")
+    ap.add_argument("--deformation", type=float, default=0.0, help="eps of the smooth mesh deformation (config 5: 0.1)")
     ap.add_argument("--no-variants", action="store_true", help="skip the second quadrature")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells", type=int, default=0, help="cells per direction of the CPU sample (0 = auto)")
@@ -257,7 +260,10 @@ def run_b200(args):
     order = [args.quadrature] + ([] if args.no_variants else [q for q in ("gll", "gauss") if q != args.quadrature])
     results = {}
     for qi, qname in enumerate(order):
-        op = dc.PoissonOperator(ctx, dc.make_problem(args.degree, (args.cells,) * 3, quadrature=quad_ids[qname]))
+        geom = dc.GEOM_ON_THE_FLY if (args.geometry == "otf" and qname == "gll") else dc.GEOM_STORED
+        op = dc.PoissonOperator(ctx, dc.make_problem(args.degree, (args.cells,) * 3, quadrature=quad_ids[qname],
+                                                     deformation=1 if args.deformation else 0, eps=args.deformation,
+                                                     geometry_mode=geom))
         sampler = ClockSampler(local_rank) if qi == 0 else None
         r = measure_solver(dc, torch, ctx, stream, op, args.steps, args.warmup, sampler)
         bytes_vmult, bytes_cg = op.algorithmic_bytes()
@@ -293,6 +299,7 @@ def run_b200(args):
                         f"{args.quadrature} quadrature (p+1 points), merged CG, IterationNumberControl({MAX_ITS}, 1e-6|b|), "
                         f"{head['its_per_step']:.0f} iterations per step",
             "quadrature": args.quadrature, "degree": args.degree, "cells_per_gpu": args.cells ** 3,
+            "geometry": "on-the-fly" if args.geometry == "otf" else "stored metric tensor", "deformation_eps": args.deformation,
             "dofs_per_gpu": head["n"], "parallelism": "1 block", "iterations_per_step": head["its_per_step"],
             "l2": "no flush: every vector (8 B x DoFs) and the metric are larger than the 126 MB L2",
             "kernel": head["kernel"],

@@ -33,7 +33,9 @@ def run(args):
 
     strong = args.scaling == "strong"
     P = DistributedPoisson(args.degree, (args.cells,) * 3, quadrature=quad_ids[args.quadrature], device=local_rank,
-                           transport=args.transport, global_cells=(args.cells,) * 3 if strong else None)
+                           transport=args.transport, global_cells=(args.cells,) * 3 if strong else None,
+                           deformation=1 if args.deformation else 0, eps=args.deformation,
+                           geometry_mode=dc.GEOM_ON_THE_FLY if args.geometry == "otf" else dc.GEOM_STORED)
     op, ctx = P.op, P.ctx
     b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
     op.assemble_rhs(b)
@@ -118,6 +120,8 @@ def run(args):
                             f"{n_glob} DoFs, {args.quadrature} quadrature, merged CG, IterationNumberControl({single.MAX_ITS}, 1e-6|b|), "
                             f"{its_total / args.steps:.0f} iterations per step",
                 "quadrature": args.quadrature, "degree": args.degree, "cells_per_gpu": op.n_cells,
+                "geometry": "on-the-fly" if args.geometry == "otf" else "stored metric tensor",
+                "deformation_eps": args.deformation,
                 "dofs_global": n_glob, "dofs_per_gpu": n_glob / world,
                 "parallelism": f"domain decomposition {grid[0]}x{grid[1]}x{grid[2]}, " + (
                     "peer-memory halo (P2P stores over NVLink, interior cells overlap) + mailbox sum of 7 doubles/iteration"

@@ -89,7 +89,12 @@ int bp5_operator_create(bp5_context_t ctx, const bp5_problem_t *pr, bp5_operator
   BP5_REQUIRE(pr->degree >= 1 && pr->degree <= kMaxDegree, "degree must be in 1..8");
   BP5_REQUIRE(pr->quadrature == BP5_QUAD_GAUSS || pr->quadrature == BP5_QUAD_GLL, "unknown quadrature");
   BP5_REQUIRE(pr->operator_kind == BP5_OP_POISSON || pr->operator_kind == BP5_OP_HELMHOLTZ, "unknown operator");
-  BP5_REQUIRE(pr->geometry_mode == BP5_GEOM_STORED, "only stored-metric geometry is implemented");
+  BP5_REQUIRE(pr->geometry_mode == BP5_GEOM_STORED || pr->geometry_mode == BP5_GEOM_ON_THE_FLY, "unknown geometry mode");
+  if (pr->geometry_mode == BP5_GEOM_ON_THE_FLY &&
+      (pr->quadrature != BP5_QUAD_GLL || pr->operator_kind != BP5_OP_POISSON)) {
+    set_error("on-the-fly geometry is implemented for the Poisson operator with Gauss-Lobatto collocation");
+    return BP5_ERR_UNSUPPORTED;
+  }
   BP5_REQUIRE(pr->deformation == 0 || pr->deformation == 1, "unknown deformation");
   for (int d = 0; d < 3; ++d) {
     BP5_REQUIRE(pr->cells[d] >= 1, "cells must be >= 1");
@@ -160,6 +165,7 @@ int bp5_operator_destroy(bp5_operator_t op) {
   cudaFree(op->mf_l2g); cudaFree(op->mf_constraint_mask); cudaFree(op->mf_inv_jacobian);
   cudaFree(op->mf_jxw); cudaFree(op->mf_q_points);
   cudaFree(op->metric);
+  cudaFree(op->coords);
   cudaFree(op->constrained);
   cudaFree(op->cg_scalars);
   for (cudaEvent_t e : op->prof_events) cudaEventDestroy(e);
@@ -262,6 +268,7 @@ int bp5_operator_assemble_rhs(bp5_operator_t op, bp5_vector_t b) {
 int bp5_operator_export_coefficients(bp5_operator_t op, double *host_out) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && host_out, "null argument");
+  if (!op->metric) { set_error("this operator computes its geometry on the fly: no stored coefficient"); return BP5_ERR_UNSUPPORTED; }
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   BP5_CUDA(cudaStreamSynchronize(op->ctx->stream));
   return operator_export_coefficients(op, host_out);
@@ -299,7 +306,10 @@ int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *per_vmult, double 
   // per DoF 8 (read src) + 8 (write dst) + 8*planes per q-point;
   // CG: read {x,r,p,h,diag} + write {x,r,p,h} = 72, plus the metric.
   const double n3 = (double)op->n * op->n * op->n;
-  const double metric = 8.0 * op->metric_planes * n3 * (double)op->n_cells;
+  // stored metric: 8 bytes per plane per quadrature point; on the fly: three coordinates per local DoF
+  const double metric = op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY
+                            ? 24.0 * (double)(op->n_owned + op->n_ghost)
+                            : 8.0 * op->metric_planes * n3 * (double)op->n_cells;
   if (per_vmult) *per_vmult = 16.0 * (double)op->n_owned + metric;
   if (per_cg_it) *per_cg_it = 72.0 * (double)op->n_owned + metric;
   return BP5_OK;

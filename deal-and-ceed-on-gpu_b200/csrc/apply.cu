@@ -4,45 +4,9 @@
 #include <cstdlib>
 
 #include "apply.cuh"
+#include "tile_cells.h"
 
 namespace bp5 {
-
-// cells per tile for each degree: fills the CTA's warps ((p+1)^2 threads per
-// cell) while keeping >= 2-4 CTAs resident per SM.
-// (-DBP5_CPT_Pn=... overrides one entry for tuning builds, scripts/tune_cpt.sh)
-#ifndef BP5_CPT_P1
-#define BP5_CPT_P1 32
-#endif
-#ifndef BP5_CPT_P2
-#define BP5_CPT_P2 14
-#endif
-#ifndef BP5_CPT_P3
-#define BP5_CPT_P3 8
-#endif
-#ifndef BP5_CPT_P4
-#define BP5_CPT_P4 5
-#endif
-#ifndef BP5_CPT_P5
-#define BP5_CPT_P5 3
-#endif
-#ifndef BP5_CPT_P6
-#define BP5_CPT_P6 2
-#endif
-#ifndef BP5_CPT_P7
-#define BP5_CPT_P7 3
-#endif
-#ifndef BP5_CPT_P8
-#define BP5_CPT_P8 1
-#endif
-template <int P> struct TileCells;
-template <> struct TileCells<1> { static constexpr int value = BP5_CPT_P1; };
-template <> struct TileCells<2> { static constexpr int value = BP5_CPT_P2; };
-template <> struct TileCells<3> { static constexpr int value = BP5_CPT_P3; };
-template <> struct TileCells<4> { static constexpr int value = BP5_CPT_P4; };
-template <> struct TileCells<5> { static constexpr int value = BP5_CPT_P5; };
-template <> struct TileCells<6> { static constexpr int value = BP5_CPT_P6; };
-template <> struct TileCells<7> { static constexpr int value = BP5_CPT_P7; };
-template <> struct TileCells<8> { static constexpr int value = BP5_CPT_P8; };
 
 static int cells_per_tile_for(int p) {
   switch (p) {
@@ -72,6 +36,8 @@ int apply_choose(bp5_operator_t op) {
   snprintf(name, sizeof(name), "bp5_apply_kernel<p=%d,%s,%s,cells_per_tile=%d,%s>", op->p,
            op->prob.quadrature == BP5_QUAD_GLL ? "gll-collocation" : "gauss",
            op->prob.operator_kind == BP5_OP_HELMHOLTZ ? "helmholtz" : "poisson", cpt, kPath[op->metric_path]);
+  if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY)
+    snprintf(name, sizeof(name), "bp5_apply_otf_kernel<p=%d,gll-collocation,poisson,cells_per_tile=%d,geometry=on-the-fly>", op->p, cpt);
   op->kernel_name = name;
   return BP5_OK;
 }
@@ -159,6 +125,7 @@ int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool over
                     int which) {
   BP5_REQUIRE(dot_partials == nullptr || overwrite_interior, "the fused dot product needs the overwrite kernel");
   const int mode = dot_partials ? 2 : (overwrite_interior ? 1 : 0);
+  if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY) return apply_cell_loop_otf(op, dst, src, mode, dot_partials, which);
   switch (op->p) {
     case 1: return launch_p<1>(op, dst, src, mode, dot_partials, which);
     case 2: return launch_p<2>(op, dst, src, mode, dot_partials, which);

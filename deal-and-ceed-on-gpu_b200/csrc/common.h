@@ -124,6 +124,7 @@ struct bp5_operator_s {
   double *mf_inv_jacobian = nullptr, *mf_jxw = nullptr, *mf_q_points = nullptr;
   int mf_padding = 0;
   uint32_t *skel_mask = nullptr; // bit i set: owned dof i is shared by more than one cell (skeleton)
+  double *coords = nullptr;     // BP5_GEOM_ON_THE_FLY: nodal coordinates [3][n_owned + n_ghost] instead of the metric
   double *metric = nullptr;     // [tile][cpt][planes][n^3]; planes: 6 (Poisson) or 7 (Helmholtz: + a*JxW)
   int metric_planes = 6;
   int *constrained = nullptr;   // local owned indices of Dirichlet dofs
@@ -163,6 +164,7 @@ int apply_choose(bp5_operator_t op);                 // picks cells_per_tile + k
 // which: 0 all tiles, 1 boundary tiles only, 2 the others
 int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior,
                     double *dot_partials = nullptr, int which = 0);
+int apply_cell_loop_otf(bp5_operator_t op, double *dst, const double *src, int mode, double *dot_partials, int which);
 int apply_copy_constrained_dot(bp5_operator_t op, double *dst, const double *src, double *partials);
 int apply_zero_skeleton(bp5_operator_t op, double *dst);
 int apply_copy_constrained(bp5_operator_t op, double *dst, const double *src);

@@ -136,6 +136,7 @@ __global__ void setup_cells_kernel(BlockGeom g, const int *__restrict__ cell_bas
   if (t < n3 && base < 0)
     l2g_irr[(long long)(-(base + 1)) * n3 + t] =
         (int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
+  if (metric == nullptr) return;     // geometry on the fly: only the index tables are needed (uniform per block)
   double J[3][3], xr[3];
   cell_jacobian(g, c_tab.B, c_tab.Dg, sm, g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz, J, xr);
   if (t >= n3) return;
@@ -200,8 +201,9 @@ __global__ void rhs_kernel(BlockGeom g, int ex, int ey, int ez, double *__restri
   }
 }
 
-// coordinates + global lexicographic index of every local dof (owned, then ghost)
-__global__ void dof_info_kernel(BlockGeom g, double *__restrict__ xyz, long long *__restrict__ gidx) {
+// coordinates + global lexicographic index of every local dof (owned, then ghost); soa: coordinate planes
+// x[], y[], z[] of n_local entries each (what the on-the-fly kernel gathers) instead of xyz triples
+__global__ void dof_info_kernel(BlockGeom g, double *__restrict__ xyz, long long *__restrict__ gidx, long long soa = 0) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long tot = (long long)g.ld[0] * g.ld[1] * g.ld[2];
   if (t >= tot) return;
@@ -217,7 +219,8 @@ __global__ void dof_info_kernel(BlockGeom g, double *__restrict__ xyz, long long
     gl[d] = (long long)g.c0[d] * g.p + loc[d];
   }
   map_point(g, x, y);
-  if (xyz) { xyz[3 * li] = y[0]; xyz[3 * li + 1] = y[1]; xyz[3 * li + 2] = y[2]; }
+  if (xyz && soa) { xyz[li] = y[0]; xyz[soa + li] = y[1]; xyz[2 * soa + li] = y[2]; }
+  else if (xyz) { xyz[3 * li] = y[0]; xyz[3 * li + 1] = y[1]; xyz[3 * li + 2] = y[2]; }
   if (gidx) gidx[li] = gl[0] + ((long long)g.gc[0] * g.p + 1) * (gl[1] + ((long long)g.gc[1] * g.p + 1) * gl[2]);
 }
 
@@ -293,10 +296,21 @@ int operator_setup_device(bp5_operator_t op) {
   BP5_CUDA(cudaMalloc(&slot_dev, sizeof(long long) * op->n_cells));
   BP5_CUDA(cudaMemcpyAsync(slot_dev, slot_of.data(), sizeof(long long) * op->n_cells, cudaMemcpyHostToDevice, ctx->stream));
   BP5_CUDA(cudaMalloc(&op->l2g_irr, sizeof(int) * std::max<int64_t>(n_irr, 1) * n3));
-  const size_t mbytes = sizeof(double) * op->n_tiles * op->tile_doubles;
-  BP5_CUDA(cudaMalloc(&op->metric, mbytes));
-  BP5_CUDA(cudaMemsetAsync(op->metric, 0, mbytes, ctx->stream));
+  const bool otf = op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY;
   BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  if (!otf) {
+    const size_t mbytes = sizeof(double) * op->n_tiles * op->tile_doubles;
+    BP5_CUDA(cudaMalloc(&op->metric, mbytes));
+    BP5_CUDA(cudaMemsetAsync(op->metric, 0, mbytes, ctx->stream));
+  } else {
+    // nodal coordinates of every local DoF (the mapped support points), three planes
+    const long long n_local = op->n_owned + op->n_ghost;
+    BP5_CUDA(cudaMalloc(&op->coords, sizeof(double) * 3 * n_local));
+    const long long tot = (long long)op->ld[0] * op->ld[1] * op->ld[2];
+    dof_info_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(g, op->coords, nullptr, n_local);
+    BP5_CHECK_LAUNCH();
+    ctx->launches++;
+  }
   const int threads = ((n3 + 31) / 32) * 32;
   const size_t smem = sizeof(double) * 8 * n3;
   setup_cells_kernel<<<(unsigned)op->n_cells, threads, smem, ctx->stream>>>(g, op->cell_base, slot_dev, op->l2g_irr,

@@ -173,7 +173,7 @@ class DistributedPoisson:
     """One block of the partitioned BP5 problem on this rank's GPU + the exchanges around it."""
 
     def __init__(self, degree, cells_per_gpu, quadrature=B.QUAD_GLL, operator_kind=B.OP_POISSON, deformation=0,
-                 eps=0.0, device=None, transport="peer", global_cells=None):
+                 eps=0.0, device=None, transport="peer", global_cells=None, geometry_mode=B.GEOM_STORED):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -189,7 +189,8 @@ class DistributedPoisson:
         self.ctx = B.Context(self.device)
         self.stream = torch.cuda.ExternalStream(self.ctx.stream)
         prob = B.make_problem(degree, cells, quadrature=quadrature, operator_kind=operator_kind,
-                              deformation=deformation, eps=eps, part_grid=grid, part_coord=coord)
+                              deformation=deformation, eps=eps, part_grid=grid, part_coord=coord,
+                              geometry_mode=geometry_mode)
         self.op = B.PoissonOperator(self.ctx, prob)
         assert (self.op.n_owned, self.op.n_ghost) == (self.part.n_owned, self.part.n_ghost)
         # buffers are allocated on torch's default stream (the caching allocator must not tie them to

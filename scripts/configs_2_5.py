@@ -49,4 +49,7 @@ run("config5_bp5_p5_deformed_stored_metric_gauss", dc.make_problem(5, (60, 60, 6
     lambda bn, n: dc.IterationNumberControl(200, 1e-6 * bn))
 run("config5_bp5_p5_deformed_stored_metric_gll", dc.make_problem(5, (60, 60, 60), quadrature=dc.QUAD_GLL, deformation=1, eps=0.1),
     lambda bn, n: dc.IterationNumberControl(200, 1e-6 * bn))
+run("config5_bp5_p5_deformed_on_the_fly_geometry_gll",
+    dc.make_problem(5, (60, 60, 60), quadrature=dc.QUAD_GLL, deformation=1, eps=0.1, geometry_mode=dc.GEOM_ON_THE_FLY),
+    lambda bn, n: dc.IterationNumberControl(200, 1e-6 * bn))
 ctx.close()

@@ -14,10 +14,11 @@ local_rank = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(local_rank)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 fails = 0
-CASES = [(2, (3, 2, 2), dc.QUAD_GAUSS, 0), (4, (2, 2, 3), dc.QUAD_GLL, 1), (6, (2, 2, 2), dc.QUAD_GLL, 1),
-         (5, (3, 3, 2), dc.QUAD_GAUSS, 0)]
-for transport, (p, cpg, quad, deform) in [(t, c) for t in ("peer", "nccl") for c in CASES]:
-    P = DistributedPoisson(p, cpg, quadrature=quad, deformation=deform, eps=0.1, device=local_rank, transport=transport)
+CASES = [(2, (3, 2, 2), dc.QUAD_GAUSS, 0, 0), (4, (2, 2, 3), dc.QUAD_GLL, 1, 0), (6, (2, 2, 2), dc.QUAD_GLL, 1, 0),
+         (5, (3, 3, 2), dc.QUAD_GAUSS, 0, 0), (5, (2, 3, 2), dc.QUAD_GLL, 1, 1)]      # last: geometry on the fly
+for transport, (p, cpg, quad, deform, geom) in [(t, c) for t in ("peer", "nccl") for c in CASES]:
+    P = DistributedPoisson(p, cpg, quadrature=quad, deformation=deform, eps=0.1, device=local_rank, transport=transport,
+                           geometry_mode=geom)
     cells = P.part.cells
     m = O.OracleMesh(p, cells, quad=quad, deform=deform, eps=0.1)
     gi = P.op.global_indices()
@@ -43,7 +44,7 @@ for transport, (p, cpg, quad, deform) in [(t, c) for t in ("peer", "nccl") for c
     good = rel <= 1e-12 and abs(ctl.last_step() - its) <= 1 and xerr <= 1e-7
     fails += 0 if good else 1
     if rank == 0:
-        print(f"{'OK  ' if good else 'FAIL'} transport={transport} world={world} grid={P.part.grid} p={p} cells={cells} quad={quad} deform={deform}: "
+        print(f"{'OK  ' if good else 'FAIL'} transport={transport} world={world} grid={P.part.grid} p={p} cells={cells} quad={quad} deform={deform} geom={geom}: "
               f"vmult rel err {rel:.2e}, CG its {ctl.last_step()} (oracle {its}), x rel err {xerr:.2e}", flush=True)
     for v in (src, dst, b, x):
         v.close()

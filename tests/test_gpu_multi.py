@@ -20,4 +20,4 @@ def test_two_rank_parity_against_oracle():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "scripts", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "FAIL" not in r.stdout and r.stdout.count("OK  ") >= 8      # 4 cases x (peer, nccl) transports
+    assert "FAIL" not in r.stdout and r.stdout.count("OK  ") >= 10     # 5 cases x (peer, nccl) transports

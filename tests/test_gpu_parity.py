@@ -292,3 +292,48 @@ def test_host_buffer_solve_matches_device_solve(gpu_ctx):
     dc.cg_solve_host(op, x, bh, ctl, x0_is_zero=False)
     assert ctl.last_step() <= 1
     op.close()
+
+
+@pytest.mark.parametrize("p", range(1, 9))
+def test_on_the_fly_geometry_matches_stored_metric_and_oracle(gpu_ctx, p):
+    """BASELINE config 5: geometry recomputed in the kernel from the nodal coordinates vs the stored metric tensor:
+    both <= 1e-12 from the oracle (SURVEY 8c.3 asks 1e-13 between them on small meshes), affine and deformed cells,
+    ragged tile counts; CG iteration parity"""
+    dc = _dc()
+    import oracle as O
+    for cells, deform in (((3, 2, 2), 1), ((2, 3, 1), 0), ((1, 1, 1), 1)):
+        m = O.OracleMesh(p, cells, quad=O.GLL, deform=deform, eps=0.1)
+        u = np.random.default_rng(10 + p).standard_normal(m.n_dofs)
+        ref = m.vmult(u)
+        outs = {}
+        for mode in (dc.GEOM_STORED, dc.GEOM_ON_THE_FLY):
+            op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=dc.QUAD_GLL, deformation=deform, eps=0.1,
+                                                             geometry_mode=mode))
+            outs[mode] = _vmult(gpu_ctx, op, u)
+            assert relerr(outs[mode], ref) <= TOL, (p, cells, deform, mode)
+            if mode == dc.GEOM_ON_THE_FLY:
+                assert "on-the-fly" in op.kernel_name
+                with pytest.raises(dc.Bp5Error):
+                    op.coefficients()                       # nothing stored
+                b = op.initialize_dof_vector(); x = op.initialize_dof_vector()
+                op.assemble_rhs(b)
+                bh = b.to_host()
+                tol = 1e-8 * np.linalg.norm(bh)
+                ctl = dc.SolverControl(1000, tol)
+                op.do_zero_out = False
+                dc.SolverCGFullMerge(ctl).solve(op, x, b)
+                xo, its, _, _, _ = m.cg(bh, variant=1, control=1, tol=tol, max_its=1000)
+                assert abs(ctl.last_step() - its) <= 1
+                if np.linalg.norm(xo) > 0:
+                    assert relerr(x.to_host(), xo) <= 1e-7
+                b.close(); x.close()
+            op.close()
+        assert relerr(outs[dc.GEOM_ON_THE_FLY], outs[dc.GEOM_STORED]) <= 1e-13
+
+
+def test_on_the_fly_geometry_rejects_unsupported_combinations(gpu_ctx):
+    dc = _dc()
+    for kw in (dict(quadrature=dc.QUAD_GAUSS), dict(quadrature=dc.QUAD_GLL, operator_kind=dc.OP_HELMHOLTZ)):
+        with pytest.raises(dc.Bp5Error) as e:
+            dc.PoissonOperator(gpu_ctx, dc.make_problem(3, (2, 2, 2), geometry_mode=dc.GEOM_ON_THE_FLY, **kw))
+        assert e.value.code == dc.ERR_UNSUPPORTED
