@@ -28,6 +28,11 @@ struct ApplyOtfParams {
   KernelTables<N> tab;          // D / DT used (B is the identity)
 };
 
+// ZSMEM: where d/dzeta of the three coordinate fields waits for the quadrature phase: in shared memory
+// (3 more arrays per cell) or in 6(p+1) registers per thread.  Measured per degree (profiles/r1_v3_notes.md 7):
+// registers win except at p = 5, 6, where they cost the third CTA per SM.
+template <int P> struct OtfZInSmem { static constexpr bool value = (P == 5 || P == 6); };
+
 template <int P, int CPT>
 struct ApplyOtfCfg {
   static constexpr int N = P + 1, N2 = N * N, N3 = N2 * N;
@@ -35,7 +40,10 @@ struct ApplyOtfCfg {
   static constexpr int ACTIVE = CPT * N2;
   static constexpr int NT = ((ACTIVE + 31) / 32) * 32;
   static constexpr int FIELD_DOUBLES = CPT * (2 * L::A_CS + L::B_CS);   // values + d/dxi (layout A), d/deta (layout B)
-  static constexpr size_t SMEM_BYTES = (size_t)4 * FIELD_DOUBLES * 8;   // fields: u, x, y, z
+  // fields u, x, y, z; plus d/dzeta of x, y, z (written and read by the home thread only: keeping them in
+  // registers across the line phase costs 6(p+1) registers and a CTA per SM)
+  static constexpr bool ZSMEM = OtfZInSmem<P>::value;
+  static constexpr size_t SMEM_BYTES = ((size_t)4 * FIELD_DOUBLES + (ZSMEM ? (size_t)3 * CPT * L::A_CS : 0)) * 8;
 };
 
 // OVERWRITE as in bp5_apply_kernel: 0 add, 1 store cell-interior DoFs, 2 = 1 + per-CTA partials of src.(A src)
@@ -50,6 +58,8 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *F = reinterpret_cast<double *>(smem_raw);      // [field][S0 | S1 | S2]
   constexpr int FS = Cfg::FIELD_DOUBLES, OS1 = CPT * L::A_CS, OS2 = 2 * CPT * L::A_CS;
+  double *Z = F + 4 * FS;                                  // [3][CPT * A_CS]: d/dzeta of the coordinates
+  constexpr int ZS = CPT * L::A_CS;
 
   if (prm.skip != nullptr && *prm.skip != 0) return;
   const int tid = threadIdx.x;
@@ -79,7 +89,8 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
     const int base = active ? __ldg(cell_base + tile * CPT + c) : kNoCell;
     int idx[N];
     column_indices<N>(idx, l2g_irr, base, ab_off, ab_irr, sz);
-    double t[4][N];          // d/dzeta of (u, x, y, z) along this thread's column, kept for the quadrature phase
+    double t[N];             // d/dzeta of u along this thread's column, kept in registers to the end
+    [[maybe_unused]] double tc[3][N];   // d/dzeta of x, y, z when they stay in registers
     // (1) home (i=a, j=b): gather the four columns, publish them, z-derivatives in registers
     {
       const double *__restrict__ fields[4] = {prm.src, prm.cx, prm.cy, prm.cz};
@@ -92,7 +103,9 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
           double *s0 = F + f * FS + cA;
 #pragma unroll
           for (int k = 0; k < N; ++k) s0[hA + k * A2] = col[k];
-          contract_in_regs<N>(t[f], Dz, col);
+          if (f == 0) contract_in_regs<N>(t, Dz, col);
+          else if constexpr (Cfg::ZSMEM) contract_to_smem<N, RC>(Z + (f - 1) * ZS + cA + hA, A2, Dz, col);
+          else contract_in_regs<N>(tc[f > 0 ? f - 1 : 0], Dz, col);
         }
       }
     }
@@ -124,7 +137,8 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
         for (int d = 0; d < 3; ++d) {
           J[d][0] = F[(d + 1) * FS + OS1 + cA + wA];
           J[d][1] = F[(d + 1) * FS + OS2 + cB + wB];
-          J[d][2] = t[d + 1][k];
+          if constexpr (Cfg::ZSMEM) J[d][2] = Z[d * ZS + cA + wA];
+          else J[d][2] = tc[d][k];
         }
         // adj = det * J^-1 (rows: d xi_d / d x_f times det)
         const double a00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], a01 = J[0][2] * J[2][1] - J[0][1] * J[2][2],
@@ -139,13 +153,13 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
                      g2 = sc * (a20 * a20 + a21 * a21 + a22 * a22);
         const double g3 = sc * (a00 * a10 + a01 * a11 + a02 * a12), g4 = sc * (a00 * a20 + a01 * a21 + a02 * a22),
                      g5 = sc * (a10 * a20 + a11 * a21 + a12 * a22);
-        const double ur = s1[wA], us = s2[wB], ut = t[0][k];
+        const double ur = s1[wA], us = s2[wB], ut = t[k];
         const double vr = ur * g0 + us * g3 + ut * g4;
         const double vs = ur * g3 + us * g1 + ut * g5;
         const double vt = ur * g4 + us * g5 + ut * g2;
         s1[wA] = vr;
         s2[wB] = vs;
-        t[0][k] = vt;
+        t[k] = vt;
         if constexpr (OVERWRITE == 2) dot_acc += ur * vr + us * vs + ut * vt;
       }
     }
@@ -165,7 +179,7 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
     if (base != kNoCell) {
       const bool col_interior = OVERWRITE != 0 && a > 0 && a < P && b > 0 && b < P;
       double o[N];
-      contract_in_regs<N>(o, DTz, t[0]);
+      contract_in_regs<N>(o, DTz, t);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const double s = o[k] + s1[hA + k * A2] + s2[hB + k * B2];

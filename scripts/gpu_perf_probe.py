@@ -14,7 +14,12 @@ HBM = 6548.2
 for p in degrees:
     nc = max(2, round((target ** (1 / 3) - 1) / p))
     for quad in quads:
-        op = dc.PoissonOperator(ctx, dc.make_problem(p, (nc, nc, nc), quadrature=quad))
+        geom = int(os.environ.get('PROBE_GEOM', '0'))         # 1: geometry on the fly (gll only)
+        eps = float(os.environ.get('PROBE_EPS', '0'))
+        if geom and quad != 1:
+            continue
+        op = dc.PoissonOperator(ctx, dc.make_problem(p, (nc, nc, nc), quadrature=quad, geometry_mode=geom,
+                                                     deformation=1 if eps else 0, eps=eps))
         n = op.n_owned
         src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
         src.import_host(np.random.default_rng(0).standard_normal(n))
