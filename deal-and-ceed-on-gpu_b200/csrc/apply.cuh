@@ -46,16 +46,55 @@ namespace bp5 {
 constexpr int kNoCell = INT_MIN;
 
 // Shape tables as they travel to the kernel (by value, parameter constant bank).
+// Even-odd form of a 1D matrix (deal.II's CPU evaluator uses the same decomposition [UPSTREAM
+// evaluate_evenodd]): nodes and quadrature points are symmetric about the cell centre, so
+// M[N-1-i][N-1-m] = S M[i][m] with S = +1 for values, -1 for derivatives (and their transposes).  With
+// e[m] = v[m] + v[N-1-m], o[m] = v[m] - v[N-1-m] (m < H = N/2) only the first H1 = ceil(N/2) rows are needed:
+//   pe = sum_m E[i][m] e[m] (+ C[i] v[H], N odd),  po = sum_m O[i][m] o[m],  out[i] = pe + po,  out[N-1-i] = S (pe - po)
+// -- about N^2/2 + 2N fp64 operations and half the matrix operands instead of N^2.  Packed as E | O | C.
+#ifndef BP5_EVENODD
+#define BP5_EVENODD 1
+#endif
+template <int N>
+struct EoShape {
+  static constexpr int H = N / 2, H1 = (N + 1) / 2;
+  static constexpr int SIZE = BP5_EVENODD ? 2 * H1 * H + H1 : N * N;
+};
+// host: M is N x N row-major
+template <int N>
+inline void pack_matrix(double *dst, const double *M) {
+  if (!BP5_EVENODD) { for (int i = 0; i < N * N; ++i) dst[i] = M[i]; return; }
+  constexpr int H = EoShape<N>::H, H1 = EoShape<N>::H1;
+  for (int i = 0; i < H1; ++i) {
+    for (int m = 0; m < H; ++m) {
+      dst[i * H + m] = 0.5 * (M[i * N + m] + M[i * N + (N - 1 - m)]);
+      dst[H1 * H + i * H + m] = 0.5 * (M[i * N + m] - M[i * N + (N - 1 - m)]);
+    }
+    dst[2 * H1 * H + i] = (N % 2) ? M[i * N + H] : 0.0;
+  }
+}
+
 template <int N>
 struct KernelTables {
   // One private copy per coordinate direction (x, y, z): every unrolled contraction
   // then reads matrix entries nobody else reads, so ptxas has no cross-contraction
   // reuse to cache in (and spill from) the 63 uniform registers.
-  double B[3][N * N];     // B[q][i]: basis i at quadrature point q (identity for GLL)
-  double BT[3][N * N];    // transpose
-  double D[3][N * N];     // D[q][r]: derivative of the Lagrange basis through the QUADRATURE points
-  double DT[3][N * N];    // transpose
+  double B[3][EoShape<N>::SIZE];     // B[q][i]: basis i at quadrature point q (identity for GLL)
+  double BT[3][EoShape<N>::SIZE];    // transpose
+  double D[3][EoShape<N>::SIZE];     // D[q][r]: derivative of the Lagrange basis through the QUADRATURE points
+  double DT[3][EoShape<N>::SIZE];    // transpose
 };
+// host: fill all twelve copies from B[q][i] and D[q][r] (row-major N x N)
+template <int N>
+inline void fill_kernel_tables(KernelTables<N> &t, const double *B, const double *D) {
+  double BT[N * N], DT[N * N];
+  for (int q = 0; q < N; ++q)
+    for (int i = 0; i < N; ++i) { BT[i * N + q] = B[q * N + i]; DT[i * N + q] = D[q * N + i]; }
+  for (int d = 0; d < 3; ++d) {
+    pack_matrix<N>(t.B[d], B); pack_matrix<N>(t.BT[d], BT);
+    pack_matrix<N>(t.D[d], D); pack_matrix<N>(t.DT[d], DT);
+  }
+}
 
 template <int N>
 struct ApplyParams {
@@ -158,11 +197,41 @@ __device__ __forceinline__ void gather_column(double (&u)[N], const double *__re
 #define BP5_ROW_CHUNK(N, QUAD, MODE) ((N) == 9 ? ((((QUAD) == 1 && (MODE) < 2) || ((QUAD) == 0 && (MODE) == 2)) ? 9 : 3) : (N))
 #endif
 
-// out[i*stride] = sum_m M[i][m] v[m], outer loop ROLLED in chunks of U rows
+// w = M v for a matrix with symmetry sign S (see EoShape); fully unrolled, result in registers
+template <int N, int S>
+__device__ __forceinline__ void eo_matvec(double (&w)[N], const double *__restrict__ M, const double (&v)[N]) {
+  constexpr int H = EoShape<N>::H, H1 = EoShape<N>::H1;
+  const double *__restrict__ E = M, *__restrict__ O = M + H1 * H, *__restrict__ C = M + 2 * H1 * H;
+  double e[H > 0 ? H : 1], o[H > 0 ? H : 1];
+#pragma unroll
+  for (int m = 0; m < H; ++m) { e[m] = v[m] + v[N - 1 - m]; o[m] = v[m] - v[N - 1 - m]; }
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    double pe = (N % 2) ? C[i] * v[H] : 0.0, po = 0.0;
+#pragma unroll
+    for (int m = 0; m < H; ++m) { pe += E[i * H + m] * e[m]; po += O[i * H + m] * o[m]; }
+    w[i] = pe + po;
+    w[N - 1 - i] = S > 0 ? pe - po : po - pe;
+  }
+  if (N % 2) {
+    double mid = S > 0 ? C[H] * v[H] : 0.0;
+#pragma unroll
+    for (int m = 0; m < H; ++m) mid += (S > 0 ? E[H * H + m] * e[m] : O[H * H + m] * o[m]);
+    w[H] = mid;
+  }
+}
+
+// out[i*stride] = sum_m M[i][m] v[m].  Plain form (BP5_EVENODD == 0): outer loop ROLLED in chunks of U rows
 // (see header comment).
-template <int N, int U>
+template <int N, int U, int S>
 __device__ __forceinline__ void contract_to_smem(double *out, int stride, const double *__restrict__ M,
                                                  const double (&v)[N]) {
+#if BP5_EVENODD
+  double w[N];
+  eo_matvec<N, S>(w, M, v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i * stride] = w[i];
+#else
 #pragma unroll 1
   for (int i0 = 0; i0 < N; i0 += U) {
     const double *row = M + i0 * N;
@@ -178,11 +247,15 @@ __device__ __forceinline__ void contract_to_smem(double *out, int stride, const 
     for (int u = 0; u < U; ++u)
       if (N % U == 0 || i0 + u < N) out[(i0 + u) * stride] = s[u];
   }
+#endif
 }
 
 // w[i] = sum_m M[i][m] v[m] in registers, fully unrolled (result indexed statically)
-template <int N>
+template <int N, int S>
 __device__ __forceinline__ void contract_in_regs(double (&w)[N], const double *__restrict__ M, const double (&v)[N]) {
+#if BP5_EVENODD
+  eo_matvec<N, S>(w, M, v);
+#else
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     double s = 0.0;
@@ -190,6 +263,7 @@ __device__ __forceinline__ void contract_in_regs(double (&w)[N], const double *_
     for (int m = 0; m < N; ++m) s += M[i * N + m] * v[m];
     w[i] = s;
   }
+#endif
 }
 
 // MLOAD: how the metric reaches the quadrature phase.
@@ -327,7 +401,7 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
       if (active) {
 #pragma unroll
         for (int k = 0; k < N; ++k) s0[hA + k * A2] = u[k];
-        contract_in_regs<N>(t, Dz, u);
+        contract_in_regs<N, -1>(t, Dz, u);
         if constexpr (HELM) {
 #pragma unroll
           for (int k = 0; k < N; ++k) mv[k] = u[k];
@@ -339,23 +413,23 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
-        contract_to_smem<N, RC>(s1 + xA, 1, Dx, v);
+        contract_to_smem<N, RC, -1>(s1 + xA, 1, Dx, v);
 #pragma unroll
         for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
-        contract_to_smem<N, RC>(s2 + yB, B1, Dy, v);
+        contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, v);
       }
       __syncthreads();
     } else {
       // ---------------- Gauss quadrature: interpolate to the q-points first
       // (1) home (i=a, j=b): z-interpolation
-      if (active) contract_to_smem<N, RC>(s0 + hA, A2, Bz, u);
+      if (active) contract_to_smem<N, RC, 1>(s0 + hA, A2, Bz, u);
       __syncthreads();
       // (2) x-line (j=a, qz=b): x-interpolation in place
       if (active) {
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
-        contract_to_smem<N, RC>(s0 + xA, 1, Bx, v);
+        contract_to_smem<N, RC, 1>(s0 + xA, 1, Bx, v);
       }
       __syncthreads();
       // (3) y-line (qx=a, qz=b): y-interpolation (values at q-points), then d/dy
@@ -363,10 +437,10 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N], w[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
-        contract_in_regs<N>(w, By, v);
+        contract_in_regs<N, 1>(w, By, v);
 #pragma unroll
         for (int q = 0; q < N; ++q) s0[yA + q * A1] = w[q];
-        contract_to_smem<N, RC>(s2 + yB, B1, Dy, w);
+        contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, w);
       }
       __syncthreads();
       // (4) x-line (qy=a, qz=b): d/dx ; home (qx=a, qy=b): d/dz in registers
@@ -374,10 +448,10 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
-        contract_to_smem<N, RC>(s1 + xA, 1, Dx, v);
+        contract_to_smem<N, RC, -1>(s1 + xA, 1, Dx, v);
 #pragma unroll
         for (int k = 0; k < N; ++k) v[k] = s0[hA + k * A2];
-        contract_in_regs<N>(t, Dz, v);
+        contract_in_regs<N, -1>(t, Dz, v);
         if constexpr (HELM) {
 #pragma unroll
           for (int k = 0; k < N; ++k) mv[k] = v[k];
@@ -438,16 +512,16 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s1[xA + i];
-        contract_to_smem<N, RC>(s1 + xA, 1, DTx, v);
+        contract_to_smem<N, RC, -1>(s1 + xA, 1, DTx, v);
 #pragma unroll
         for (int j = 0; j < N; ++j) v[j] = s2[yB + j * B1];
-        contract_to_smem<N, RC>(s2 + yB, B1, DTy, v);
+        contract_to_smem<N, RC, -1>(s2 + yB, B1, DTy, v);
       }
       __syncthreads();
       // (5) home: z-transpose in registers, sum the three directions, scatter
       if (do_scatter) {
         double o[N];
-        contract_in_regs<N>(o, DTz, t);
+        contract_in_regs<N, -1>(o, DTz, t);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           double s = o[k] + s1[hA + k * A2] + s2[hB + k * B2];
@@ -463,14 +537,14 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s1[xA + i];
-        contract_to_smem<N, RC>(s1 + xA, 1, DTx, v);
+        contract_to_smem<N, RC, -1>(s1 + xA, 1, DTx, v);
         if constexpr (HELM) {
           double o[N];
-          contract_in_regs<N>(o, DTz, t);
+          contract_in_regs<N, -1>(o, DTz, t);
 #pragma unroll
           for (int k = 0; k < N; ++k) s0[hA + k * A2] = o[k] + mv[k];
         } else {
-          contract_to_smem<N, RC>(s0 + hA, A2, DTz, t);
+          contract_to_smem<N, RC, -1>(s0 + hA, A2, DTz, t);
         }
       }
       __syncthreads();
@@ -479,10 +553,10 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N], y[N];
 #pragma unroll
         for (int q = 0; q < N; ++q) v[q] = s2[yB + q * B1];
-        contract_in_regs<N>(y, DTy, v);
+        contract_in_regs<N, -1>(y, DTy, v);
 #pragma unroll
         for (int q = 0; q < N; ++q) y[q] += s1[yA + q * A1] + s0[yA + q * A1];
-        contract_to_smem<N, RC>(s0 + yA, A1, BTy, y);
+        contract_to_smem<N, RC, 1>(s0 + yA, A1, BTy, y);
       }
       __syncthreads();
       // (7) x-line (j=a, qz=b): B^T along x in place
@@ -490,7 +564,7 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N];
 #pragma unroll
         for (int q = 0; q < N; ++q) v[q] = s0[xA + q];
-        contract_to_smem<N, RC>(s0 + xA, 1, BTx, v);
+        contract_to_smem<N, RC, 1>(s0 + xA, 1, BTx, v);
       }
       __syncthreads();
       // (8) home (i=a, j=b): B^T along z in registers, scatter
@@ -498,7 +572,7 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
         double v[N], o[N];
 #pragma unroll
         for (int q = 0; q < N; ++q) v[q] = s0[hA + q * A2];
-        contract_in_regs<N>(o, BTz, v);
+        contract_in_regs<N, 1>(o, BTz, v);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           double *dp = dst + idx[k];

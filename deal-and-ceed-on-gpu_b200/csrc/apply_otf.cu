@@ -29,14 +29,8 @@ static int launch_otf(bp5_operator_t op, double *dst, const double *src, double 
   prm.skip = op->skip_flag;
   prm.dot_partials = dot_partials;
   if (prm.n_tiles <= prm.tile_begin) { op->apply_grid = 0; return BP5_OK; }
-  for (int q = 0; q < N; ++q) {
-    prm.wq[q] = op->tab.wq[q];
-    for (int i = 0; i < N; ++i)
-      for (int d = 0; d < 3; ++d) {
-        prm.tab.B[d][q * N + i] = prm.tab.BT[d][i * N + q] = op->tab.B[q * N + i];
-        prm.tab.D[d][q * N + i] = prm.tab.DT[d][i * N + q] = op->tab.Dt[q * N + i];
-      }
-  }
+  for (int q = 0; q < N; ++q) prm.wq[q] = op->tab.wq[q];
+  fill_kernel_tables<N>(prm.tab, op->tab.B, op->tab.Dt);
   long long grid = (long long)blocks_per_sm * op->ctx->sm_count;
   if (grid > prm.n_tiles - prm.tile_begin) grid = prm.n_tiles - prm.tile_begin;
   if (grid < 1) grid = 1;

@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
           double *s0 = F + f * FS + cA;
 #pragma unroll
           for (int k = 0; k < N; ++k) s0[hA + k * A2] = col[k];
-          if (f == 0) contract_in_regs<N>(t, Dz, col);
-          else if constexpr (Cfg::ZSMEM) contract_to_smem<N, RC>(Z + (f - 1) * ZS + cA + hA, A2, Dz, col);
-          else contract_in_regs<N>(tc[f > 0 ? f - 1 : 0], Dz, col);
+          if (f == 0) contract_in_regs<N, -1>(t, Dz, col);
+          else if constexpr (Cfg::ZSMEM) contract_to_smem<N, RC, -1>(Z + (f - 1) * ZS + cA + hA, A2, Dz, col);
+          else contract_in_regs<N, -1>(tc[f > 0 ? f - 1 : 0], Dz, col);
         }
       }
     }
@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
-        contract_to_smem<N, RC>(s1 + xA, 1, Dx, v);
+        contract_to_smem<N, RC, -1>(s1 + xA, 1, Dx, v);
 #pragma unroll
         for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
-        contract_to_smem<N, RC>(s2 + yB, B1, Dy, v);
+        contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, v);
       }
     }
     __syncthreads();
@@ -169,17 +169,17 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
       double v[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) v[i] = s1[xA + i];
-      contract_to_smem<N, RC>(s1 + xA, 1, DTx, v);
+      contract_to_smem<N, RC, -1>(s1 + xA, 1, DTx, v);
 #pragma unroll
       for (int j = 0; j < N; ++j) v[j] = s2[yB + j * B1];
-      contract_to_smem<N, RC>(s2 + yB, B1, DTy, v);
+      contract_to_smem<N, RC, -1>(s2 + yB, B1, DTy, v);
     }
     __syncthreads();
     // (5) home: z-transpose in registers, sum the three directions, scatter
     if (base != kNoCell) {
       const bool col_interior = OVERWRITE != 0 && a > 0 && a < P && b > 0 && b < P;
       double o[N];
-      contract_in_regs<N>(o, DTz, t);
+      contract_in_regs<N, -1>(o, DTz, t);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const double s = o[k] + s1[hA + k * A2] + s2[hB + k * B2];
