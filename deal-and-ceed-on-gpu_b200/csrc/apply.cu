@@ -19,8 +19,12 @@ static int cells_per_tile_for(int p) {
 }
 
 int apply_choose(bp5_operator_t op) {
-  const int cpt = cells_per_tile_for(op->p);
+  int cpt = cells_per_tile_for(op->p);
   BP5_REQUIRE(cpt > 0, "degree must be 1..8");
+  if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY) {
+    if (op->p == 6) cpt = OtfTileCells<6>::value;
+    if (op->p == 7) cpt = OtfTileCells<7>::value;
+  }
   const int n3 = op->n * op->n * op->n;
   op->cells_per_tile = cpt;
   operator_plan_tiles(op);

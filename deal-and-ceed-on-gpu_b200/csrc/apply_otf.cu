@@ -6,7 +6,7 @@ namespace bp5 {
 
 template <int P, int OVERWRITE>
 static int launch_otf(bp5_operator_t op, double *dst, const double *src, double *dot_partials, int which) {
-  constexpr int CPT = TileCells<P>::value;
+  constexpr int CPT = OtfTileCells<P>::value;
   using Cfg = ApplyOtfCfg<P, CPT>;
   constexpr int N = P + 1;
   auto kernel = bp5_apply_otf_kernel<P, CPT, OVERWRITE>;

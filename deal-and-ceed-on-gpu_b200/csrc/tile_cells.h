@@ -20,10 +20,10 @@ namespace bp5 {
 #define BP5_CPT_P5 3
 #endif
 #ifndef BP5_CPT_P6
-#define BP5_CPT_P6 2
+#define BP5_CPT_P6 3
 #endif
 #ifndef BP5_CPT_P7
-#define BP5_CPT_P7 3
+#define BP5_CPT_P7 4
 #endif
 #ifndef BP5_CPT_P8
 #define BP5_CPT_P8 1
@@ -38,4 +38,8 @@ template <> struct TileCells<6> { static constexpr int value = BP5_CPT_P6; };
 template <> struct TileCells<7> { static constexpr int value = BP5_CPT_P7; };
 template <> struct TileCells<8> { static constexpr int value = BP5_CPT_P8; };
 
+// the on-the-fly-geometry kernel keeps 12-15 work arrays per cell in shared memory: fewer cells per tile
+template <int P> struct OtfTileCells { static constexpr int value = TileCells<P>::value; };
+template <> struct OtfTileCells<6> { static constexpr int value = 2; };
+template <> struct OtfTileCells<7> { static constexpr int value = 2; };
 }  // namespace bp5

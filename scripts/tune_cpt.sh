@@ -5,11 +5,13 @@ set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 CS=$ROOT/deal-and-ceed-on-gpu_b200/csrc
 declare -A SETS
-SETS[D]="-DBP5_ROW_CHUNK(N)=(N)"
+SETS[A]="-DBP5_CPT_P6=3 -DBP5_CPT_P5=4 -DBP5_CPT_P4=6 -DBP5_CPT_P8=2 -DBP5_CPT_P7=2"
+SETS[B]="-DBP5_CPT_P6=4 -DBP5_CPT_P5=2 -DBP5_CPT_P4=4 -DBP5_CPT_P7=4 -DBP5_CPT_P3=6"
+SETS[C]="-DBP5_CPT_P6=1 -DBP5_CPT_P5=5 -DBP5_CPT_P4=8 -DBP5_CPT_P7=1 -DBP5_CPT_P3=10"
 for name in "${!SETS[@]}"; do
   out=$ROOT/build/tune/$name; mkdir -p $out
   ( cd $CS && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ ${SETS[$name]} -c apply.cu -o $out/apply.o \
-    && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libbp5b200.so $out/apply.o abi.o setup.o cg.o vector.o halo.o peer.o tables.o -ccbin /usr/bin/g++ ) &
+    && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libbp5b200.so $out/apply.o abi.o apply_otf.o setup.o cg.o vector.o halo.o peer.o tables.o -ccbin /usr/bin/g++ ) &
 done
 wait
 ls -la $ROOT/build/tune/*/libbp5b200.so
