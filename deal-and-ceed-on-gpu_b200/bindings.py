@@ -81,6 +81,7 @@ ABI = [
     ("bp5_operator_export_dof_coordinates", C.c_int, [_vp, _dp]),
     ("bp5_operator_export_global_indices", C.c_int, [_vp, C.POINTER(C.c_int64)]),
     ("bp5_operator_l2_norm_sqr", C.c_int, [_vp, _vp, _dp]),
+    ("bp5_operator_compute_diagonal", C.c_int, [_vp, _vp, C.c_int]),
     ("bp5_operator_algorithmic_bytes", C.c_int, [_vp, _dp, _dp]),
     ("bp5_operator_profile", C.c_int, [_vp, C.c_int]),
     ("bp5_operator_profile_result", C.c_int, [_vp, C.POINTER(C.c_int64), _dp]),
@@ -302,6 +303,16 @@ class PoissonOperator:
 
     def assemble_rhs(self, b):
         _check(lib().bp5_operator_assemble_rhs(self.h, b.h))
+
+    def compute_diagonal(self, diag, invert=False):
+        """diagonal of the operator (or its reciprocal): Jacobi preconditioner for the DiagonalMatrix slot"""
+        _check(lib().bp5_operator_compute_diagonal(self.h, diag.h, int(invert)))
+
+    def l2_norm(self, u):
+        """||u||_L2 of the finite element function with QGauss(p+2) (output_results, bp5/step-64.cu:604-615)."""
+        out = C.c_double()
+        _check(lib().bp5_operator_l2_norm_sqr(self.h, u.h, C.byref(out)))
+        return float(np.sqrt(out.value))
 
     def coefficients(self):
         n3 = (self.problem.degree + 1) ** 3

@@ -301,6 +301,16 @@ int bp5_operator_l2_norm_sqr(bp5_operator_t op, bp5_vector_t u, double *out) {
   BP5_ABI_GUARD_END
 }
 
+int bp5_operator_compute_diagonal(bp5_operator_t op, bp5_vector_t diag, int invert) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op, "null operator");
+  int rc;
+  if ((rc = check_vec(op, diag))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  return operator_diagonal(op, diag->d, invert != 0);
+  BP5_ABI_GUARD_END
+}
+
 int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *per_vmult, double *per_cg_it) {
   BP5_REQUIRE(op, "null operator");
   // per DoF 8 (read src) + 8 (write dst) + 8*planes per q-point;

@@ -156,6 +156,7 @@ int operator_setup_device(bp5_operator_t op);
 int operator_assemble_rhs(bp5_operator_t op, double *b_dev);
 int operator_l2_norm_sqr(bp5_operator_t op, const double *u_dev, double *out);
 int operator_generic_data(bp5_operator_t op);
+int operator_diagonal(bp5_operator_t op, double *diag_dev, bool invert);
 int operator_export_coefficients(bp5_operator_t op, double *host_out);
 int operator_export_coords(bp5_operator_t op, double *host_out);
 int operator_export_global_indices(bp5_operator_t op, int64_t *host_out);

@@ -478,9 +478,187 @@ int operator_generic_data(bp5_operator_t op) {
   return BP5_OK;
 }
 
-int operator_l2_norm_sqr(bp5_operator_t, const double *, double *) {
-  set_error("l2 norm with QGauss(p+2) not implemented yet");
-  return BP5_ERR_UNSUPPORTED;
+// ---------------------------------------------------------------------------
+// Diagonal of the operator, for a Jacobi preconditioner in the DiagonalMatrix slot of the solver
+// (bp5/step-64.cu:428-432 passes a vector of ones).  Per cell and node i:
+//   sum_q  grad phi_i(q)^T G(q) grad phi_i(q)  (+ a JxW phi_i(q)^2 for Helmholtz)
+// evaluated directly from the stored metric (one CTA per cell slot, one thread per node; set-up cost only),
+// accumulated over the cells sharing the node; Dirichlet rows are 1 (vmult copies them, bp5/step-64.cu:275).
+__global__ void diagonal_kernel(int n, int planes, int cpt, long long tile_doubles, const int *__restrict__ cell_base,
+                                const int *__restrict__ l2g_irr, const double *__restrict__ metric, int sy, int sz,
+                                double *__restrict__ diag) {
+  const int n2 = n * n, n3 = n2 * n;
+  const long long slot = blockIdx.x;
+  const int base = cell_base[slot];
+  const int t = threadIdx.x;
+  if (base == INT_MIN || t >= n3) return;
+  const int a = t % n, b = (t / n) % n, c = t / n2;
+  const double *G = metric + (slot / cpt) * tile_doubles + (slot % cpt) * (long long)planes * n3;
+  double s = 0.0;
+  for (int qz = 0; qz < n; ++qz) {
+    const double bz = c_tab.B[qz * n + c], dz = c_tab.Dg[qz * n + c];
+    for (int qy = 0; qy < n; ++qy) {
+      const double by = c_tab.B[qy * n + b], dy = c_tab.Dg[qy * n + b];
+      if (bz == 0.0 && dz == 0.0) continue;
+      for (int qx = 0; qx < n; ++qx) {
+        const double bx = c_tab.B[qx * n + a], dx = c_tab.Dg[qx * n + a];
+        const double gx = dx * by * bz, gy = bx * dy * bz, gz = bx * by * dz;
+        if (gx == 0.0 && gy == 0.0 && gz == 0.0 && planes == 6) continue;
+        const int q = (qz * n + qy) * n + qx;
+        s += G[q] * gx * gx + G[n3 + q] * gy * gy + G[2 * n3 + q] * gz * gz +
+             2.0 * (G[3 * n3 + q] * gx * gy + G[4 * n3 + q] * gx * gz + G[5 * n3 + q] * gy * gz);
+        if (planes == 7) { const double v = bx * by * bz; s += G[6 * n3 + q] * v * v; }
+      }
+    }
+  }
+  const long long idx = base >= 0 ? (long long)base + a + (long long)b * sy + (long long)c * sz
+                                  : (long long)l2g_irr[(long long)(-(base + 1)) * n3 + t];
+  atomicAdd(&diag[idx], s);
+}
+
+__global__ void set_constrained_kernel(const int *__restrict__ list, long long n, double value, double *__restrict__ v) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < n) v[list[t]] = value;
+}
+
+__global__ void reciprocal_kernel(double *__restrict__ v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    v[i] = 1.0 / v[i];
+}
+
+int operator_diagonal(bp5_operator_t op, double *diag_dev, bool invert) {
+  bp5_context_t ctx = op->ctx;
+  if (!op->metric) { set_error("the diagonal needs the stored metric (geometry mode BP5_GEOM_STORED)"); return BP5_ERR_UNSUPPORTED; }
+  if (invert && op->n_ghost > 0) {
+    set_error("partitioned mesh: compress(add) the diagonal over the blocks first, then invert it");
+    return BP5_ERR_UNSUPPORTED;
+  }
+  const int n = op->n, n3 = n * n * n;
+  BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(diag_dev, 0, sizeof(double) * (op->n_owned + op->n_ghost), ctx->stream));
+  const long long slots = op->n_tiles * op->cells_per_tile;
+  const int threads = ((n3 + 31) / 32) * 32;
+  diagonal_kernel<<<(unsigned)slots, threads, 0, ctx->stream>>>(n, op->metric_planes, op->cells_per_tile, op->tile_doubles,
+                                                              op->cell_base, op->l2g_irr, op->metric, op->od[0],
+                                                              op->od[0] * op->od[1], diag_dev);
+  BP5_CHECK_LAUNCH();
+  ctx->launches++;
+  if (op->n_constrained > 0) {
+    set_constrained_kernel<<<(unsigned)((op->n_constrained + 255) / 256), 256, 0, ctx->stream>>>(op->constrained,
+                                                                                              op->n_constrained, 1.0, diag_dev);
+    BP5_CHECK_LAUNCH();
+    ctx->launches++;
+  }
+  if (invert) {
+    reciprocal_kernel<<<148 * 8, 256, 0, ctx->stream>>>(diag_dev, op->n_owned);
+    BP5_CHECK_LAUNCH();
+    ctx->launches++;
+  }
+  return BP5_OK;
+}
+
+// ---------------------------------------------------------------------------
+// ||u||_L2^2 of the finite element function with QGauss(p+2), this block's cells
+// (VectorTools::integrate_difference(..., L2_norm) with a zero reference in output_results,
+// bp5/step-64.cu:604-615, step-64/step-64.cu:590-601).  One CTA per cell, one thread per quadrature point;
+// values and the Jacobian of the degree-p mapping are evaluated directly (not sum-factorised: this runs
+// once per solve).  Per-cell norms are rounded to float like the reference's Vector<float> cellwise_norm and
+// added in a fixed order.
+struct L2Tables {
+  int nq;
+  double B[(kMaxN + 1) * kMaxN];    // B[q][i] = phi_i(x_q), x_q Gauss(p+2) points
+  double D[(kMaxN + 1) * kMaxN];    // phi_i'(x_q)
+  double w[kMaxN + 1];
+};
+
+__global__ void l2_norm_kernel(BlockGeom g, L2Tables tb, const double *__restrict__ u, double *__restrict__ partial) {
+  extern __shared__ double sm[];
+  const int n = g.n, n2 = n * n, n3 = n2 * n, nq = tb.nq;
+  double *U = sm, *X = sm + n3;                      // X[3][n3]
+  double *red = X + 3 * n3;                          // [32]
+  const long long cell = blockIdx.x;
+  const int lcx = cell % g.lc[0], lcy = (cell / g.lc[0]) % g.lc[1], lcz = cell / ((long long)g.lc[0] * g.lc[1]);
+  const int c[3] = {g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz};
+  for (int t = threadIdx.x; t < n3; t += blockDim.x) {
+    const int loc[3] = {t % n, (t / n) % n, t / n2};
+    U[t] = u[local_dof_index(g, lcx * g.p + loc[0], lcy * g.p + loc[1], lcz * g.p + loc[2])];
+    double x[3], y[3];
+    for (int d = 0; d < 3; ++d) x[d] = g.lo[d] + g.h[d] * (c[d] + c_tab.xi[loc[d]]);
+    map_point(g, x, y);
+    for (int d = 0; d < 3; ++d) X[d * n3 + t] = y[d];
+  }
+  __syncthreads();
+  double contrib = 0.0;
+  const int t = threadIdx.x;
+  if (t < nq * nq * nq) {
+    const int qx = t % nq, qy = (t / nq) % nq, qz = t / (nq * nq);
+    double val = 0.0, J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < n; ++k) {
+      const double bz = tb.B[qz * n + k], dz = tb.D[qz * n + k];
+      for (int j = 0; j < n; ++j) {
+        const double by = tb.B[qy * n + j], dy = tb.D[qy * n + j];
+        for (int i = 0; i < n; ++i) {
+          const double bx = tb.B[qx * n + i], dx = tb.D[qx * n + i];
+          const int a = (k * n + j) * n + i;
+          val += bx * by * bz * U[a];
+          for (int d = 0; d < 3; ++d) {
+            const double xd = X[d * n3 + a];
+            J[d][0] += dx * by * bz * xd; J[d][1] += bx * dy * bz * xd; J[d][2] += bx * by * dz * xd;
+          }
+        }
+      }
+    }
+    contrib = val * val * det3(J) * tb.w[qx] * tb.w[qy] * tb.w[qz];
+  }
+  // block sum, fixed order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+  if ((t & 31) == 0) red[t >> 5] = contrib;
+  __syncthreads();
+  if (t == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) s += red[w];
+    // the reference stores the per-cell norms in a Vector<float> before compute_global_error squares and adds
+    // them (bp5/step-64.cu:603-613): same rounding here, so the printed norm agrees to the last digit
+    const float cell_norm = (float)sqrt(fmax(s, 0.0));
+    partial[cell] = (double)cell_norm * (double)cell_norm;
+  }
+}
+
+__global__ void sum_in_order_kernel(const double *__restrict__ partial, long long n, double *__restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < 256; ++i) t += sh[i]; *out = t; }
+}
+
+int operator_l2_norm_sqr(bp5_operator_t op, const double *u_dev, double *out) {
+  bp5_context_t ctx = op->ctx;
+  const int n = op->n, n3 = n * n * n, nq = op->p + 2;
+  const BlockGeom g = make_geom(op);
+  L2Tables tb{};
+  tb.nq = nq;
+  double xq[kMaxN + 1], val[kMaxN], der[kMaxN];
+  gauss_rule01(nq, xq, tb.w);
+  for (int q = 0; q < nq; ++q) {
+    lagrange_eval(n, op->tab.xi, xq[q], val, der);
+    for (int i = 0; i < n; ++i) { tb.B[q * n + i] = val[i]; tb.D[q * n + i] = der[i]; }
+  }
+  double *partial = nullptr;
+  BP5_CUDA(cudaMalloc(&partial, sizeof(double) * (op->n_cells + 1)));
+  BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = ((nq * nq * nq + 31) / 32) * 32;
+  l2_norm_kernel<<<(unsigned)op->n_cells, threads, sizeof(double) * (4 * n3 + 32), ctx->stream>>>(g, tb, u_dev, partial);
+  BP5_CHECK_LAUNCH();
+  sum_in_order_kernel<<<1, 256, 0, ctx->stream>>>(partial, op->n_cells, partial + op->n_cells);
+  BP5_CHECK_LAUNCH();
+  ctx->launches += 2;
+  BP5_CUDA(cudaMemcpyAsync(out, partial + op->n_cells, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(partial);
+  return BP5_OK;
 }
 
 }  // namespace bp5

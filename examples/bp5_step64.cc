@@ -50,6 +50,8 @@ class PoissonProblem {
             << std::endl;
       system_matrix_dev->assemble_rhs(system_rhs_dev);   // assemble_rhs(), on the device
       solve();
+      // output_results (bp5/step-64.cu:565-616): VTU output is disabled there (:569); the L2 norm is printed
+      pcout << "  solution norm: " << system_matrix_dev->l2_norm(solution_dev) << std::endl;
       pcout << std::endl;
     }
   }

@@ -38,7 +38,8 @@ template <int dim, int fe_degree> void run(bool use_merged, unsigned n_cycles) {
       cg.solve(system_matrix_dev, solution_dev, system_rhs_dev, preconditioner);
     }
     std::cout << "  Solved in " << solver_control.last_step() << " iterations." << std::endl;
-    std::cout << "  solution l2 norm: " << solution_dev.l2_norm() << std::endl << std::endl;
+    std::cout << "  solution l2 norm: " << solution_dev.l2_norm() << std::endl;
+    std::cout << "  solution norm: " << system_matrix_dev.l2_norm(solution_dev) << std::endl << std::endl;   // output_results, :590-601
   }
 }
 

@@ -119,6 +119,11 @@ int bp5_operator_export_global_indices(bp5_operator_t op, int64_t *host_out);
 /* ||u||_L2 with QGauss(p+2), this block's contribution squared
  * (output_results, bp5/step-64.cu:604-615) */
 int bp5_operator_l2_norm_sqr(bp5_operator_t op, bp5_vector_t u, double *out);
+/* diagonal of the operator (Dirichlet rows: 1), or its reciprocal when invert != 0 -- the vector for a
+ * Jacobi preconditioner in the DiagonalMatrix slot of the solvers (the reference passes ones,
+ * bp5/step-64.cu:428-432).  Stored-metric operators.  On a partitioned mesh the ghost entries hold the
+ * contributions for the neighbouring owners (compress(add) them, then invert). */
+int bp5_operator_compute_diagonal(bp5_operator_t op, bp5_vector_t diag, int invert);
 /* algorithmic bytes of one vmult over this block (16 + 48 r per DoF) */
 int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *bytes_per_vmult, double *bytes_per_cg_it);
 /* live timing of the cell kernel: when enabled, every launch of the hot kernel

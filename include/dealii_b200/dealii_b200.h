@@ -305,6 +305,18 @@ template <int dim, int fe_degree, int operator_kind> class MatrixFreeOperator {
   }
   // assemble_rhs of the drivers (bp5/step-64.cu:372-418), done on the device
   void assemble_rhs(VectorType &b) const { check(bp5_operator_assemble_rhs(h, b.handle())); b.mark_modified(); }
+  // MatrixFreeOperators-style compute_diagonal(): fills a DiagonalMatrix's vector with the inverse diagonal
+  void compute_inverse_diagonal(VectorType &diag) const {
+    check(bp5_operator_compute_diagonal(h, diag.handle(), 1));
+    diag.mark_modified();
+  }
+  // VectorTools::integrate_difference(..., L2_norm) + compute_global_error of output_results
+  // (bp5/step-64.cu:604-615), on the device
+  double l2_norm(const VectorType &u) const {
+    double v = 0.0;
+    check(bp5_operator_l2_norm_sqr(h, u.handle(), &v));
+    return std::sqrt(v);
+  }
   bp5_operator_t handle() const { return h; }
 
  private:

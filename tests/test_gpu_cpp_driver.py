@@ -48,3 +48,5 @@ def test_step64_driver_reproduces_tutorial_iterations():
     assert len(its) == 4                        # (SolverCG, merged) x 2 cycles
     for got, ref in zip(its, (27, 60, 27, 60)):  # deal.II step-64 tutorial: 343 DoFs -> 27, 2197 -> 60
         assert abs(got - ref) <= 1
+    norms = re.findall(r"solution norm: (\S+)", out.stdout)    # tutorial output: 0.0205439, 0.0205269
+    assert [f"{float(v):.6g}" for v in norms] == ["0.0205439", "0.0205269", "0.0205439", "0.0205269"]

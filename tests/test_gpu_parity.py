@@ -175,6 +175,8 @@ def test_step64_helmholtz_known_answers_on_gpu(gpu_ctx, refine, its_ref, norm_re
         assert abs(ctl.last_step() - its_ref) <= 1
         m = O.OracleMesh(3, (c, c, c), quad=O.GAUSS, upper=(1., 1., 1.))
         assert f"{m.l2_norm(x.to_host()):.6g}" == f"{norm_ref:.6g}"
+        assert f"{op.l2_norm(x):.6g}" == f"{norm_ref:.6g}"                 # the same integral on the device
+        assert op.l2_norm(x) == pytest.approx(m.l2_norm(x.to_host()), rel=1e-7)    # per-cell norms are float-rounded
     b.close(); x.close(); op.close()
 
 
@@ -337,3 +339,49 @@ def test_on_the_fly_geometry_rejects_unsupported_combinations(gpu_ctx):
         with pytest.raises(dc.Bp5Error) as e:
             dc.PoissonOperator(gpu_ctx, dc.make_problem(3, (2, 2, 2), geometry_mode=dc.GEOM_ON_THE_FLY, **kw))
         assert e.value.code == dc.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("p,quad,kind", [(2, 0, 0), (3, 1, 0), (4, 0, 1), (5, 1, 0)])
+def test_diagonal_and_jacobi_preconditioner(gpu_ctx, p, quad, kind):
+    """bp5_operator_compute_diagonal against the dense numpy assembly; Jacobi-preconditioned merged CG against the
+    oracle's preconditioned CG (the diag slot of solver.h:421 with something other than ones)"""
+    dc = _dc()
+    import oracle as O
+    import bp5_numpy as NP
+    cells = (2, 2, 1) if p > 3 else (3, 2, 2)
+    op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=quad, operator_kind=kind, deformation=1, eps=0.1))
+    A = NP.NumpyBP5(p, cells, quad="gll" if quad else "gauss", deform=1, eps=0.1).assemble(helmholtz=bool(kind), apply_bc=True)
+    dref = np.asarray(A.diagonal() if hasattr(A, "diagonal") else np.diag(A)).ravel()
+    d = op.initialize_dof_vector()
+    op.compute_diagonal(d)
+    assert relerr(d.to_host(), dref) <= 1e-12
+    op.compute_diagonal(d, invert=True)
+    assert relerr(d.to_host(), 1.0 / dref) <= 1e-12
+    m = O.OracleMesh(p, cells, quad=quad, deform=1, eps=0.1)
+    b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+    op.assemble_rhs(b)
+    bh = b.to_host()
+    tol = 1e-9 * np.linalg.norm(bh)
+    ctl = dc.SolverControl(2000, tol)
+    op.do_zero_out = False
+    dc.SolverCGFullMerge(ctl).solve(op, x, b, preconditioner=d)
+    xo, its, _, _, ok = m.cg(bh, kind=kind, variant=1, control=1, tol=tol, max_its=2000, diag=1.0 / dref)
+    assert ok and abs(ctl.last_step() - its) <= 1
+    assert relerr(x.to_host(), xo) <= 1e-7
+    for v in (d, b, x):
+        v.close()
+    op.close()
+
+
+def test_l2_norm_on_deformed_mesh(gpu_ctx):
+    dc = _dc()
+    import oracle as O
+    for p, quad in ((2, 0), (4, 1), (7, 0)):
+        cells = (3, 2, 2) if p < 7 else (2, 1, 1)
+        op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=quad, deformation=1, eps=0.1))
+        m = O.OracleMesh(p, cells, quad=quad, deform=1, eps=0.1)
+        u = np.random.default_rng(p).standard_normal(m.n_dofs)
+        v = op.initialize_dof_vector()
+        v.import_host(u)
+        assert op.l2_norm(v) == pytest.approx(m.l2_norm(u), rel=1e-7)    # Vector<float> cellwise_norm, bp5/step-64.cu:603
+        v.close(); op.close()
