@@ -300,8 +300,7 @@ struct ApplyCfg {
 // 1 = cell-interior DoFs are stored, not added (dst's skeleton must be
 // zero on entry, its interior may hold anything); 0 = dst += A src everywhere.
 template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0>
-__global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
-    bp5_apply_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
+__device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = Cfg::N, N2 = Cfg::N2, N3 = Cfg::N3, PLANES = 6 + HELM;
   constexpr int RC = BP5_ROW_CHUNK(N, QUAD, OVERWRITE);     // rows per rolled iteration of a line contraction
@@ -599,6 +598,12 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
       if (tid == 0) prm.dot_partials[blockIdx.x] = v;
     }
   }
+}
+
+template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0>
+__global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
+    bp5_apply_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
+  bp5_apply_body<P, QUAD, HELM, CPT, OVERWRITE, MLOAD>(prm);
 }
 
 }  // namespace bp5

@@ -5,9 +5,7 @@ set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 CS=$ROOT/deal-and-ceed-on-gpu_b200/csrc
 declare -A SETS
-SETS[A]="-DBP5_CPT_P6=3 -DBP5_CPT_P5=4 -DBP5_CPT_P4=6 -DBP5_CPT_P8=2 -DBP5_CPT_P7=2"
-SETS[B]="-DBP5_CPT_P6=4 -DBP5_CPT_P5=2 -DBP5_CPT_P4=4 -DBP5_CPT_P7=4 -DBP5_CPT_P3=6"
-SETS[C]="-DBP5_CPT_P6=1 -DBP5_CPT_P5=5 -DBP5_CPT_P4=8 -DBP5_CPT_P7=1 -DBP5_CPT_P3=10"
+SETS[N]="-DBP5_NO_MIN_BLOCKS"
 for name in "${!SETS[@]}"; do
   out=$ROOT/build/tune/$name; mkdir -p $out
   ( cd $CS && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ ${SETS[$name]} -c apply.cu -o $out/apply.o \
