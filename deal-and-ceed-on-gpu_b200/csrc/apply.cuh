@@ -374,17 +374,22 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   // software pipeline of the gather: cell descriptors two tiles ahead, values one tile ahead
   int base_cur = (active && tile0 < n_tiles) ? __ldg(cell_base + tile0 * CPT + c) : kNoCell;
   int base_nxt = (active && tile0 + tstride < n_tiles) ? __ldg(cell_base + (tile0 + tstride) * CPT + c) : kNoCell;
-  double u_nxt[N];
-  gather_column<N>(u_nxt, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
+#ifndef BP5_PREFETCH_GATHER
+#define BP5_PREFETCH_GATHER(P) 1
+#endif
+  constexpr bool kPrefetch = BP5_PREFETCH_GATHER(P) != 0;   // values of the next tile in registers one tile ahead
+  [[maybe_unused]] double u_nxt[N];
+  if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
 
   uint32_t parity = 0;
   [[maybe_unused]] double dot_acc = 0.0;
   for (long long tile = tile0; tile < n_tiles; tile += tstride) {
     double u[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) u[k] = u_nxt[k];
+    for (int k = 0; k < N; ++k) u[k] = kPrefetch ? u_nxt[k] : 0.0;
+    if constexpr (!kPrefetch) gather_column<N>(u, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
     // issue next tile's gather and the descriptor load of the tile after it
-    gather_column<N>(u_nxt, src, l2g_irr, base_nxt, ab_off, ab_irr, sz);
+    if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_nxt, ab_off, ab_irr, sz);
     const int base_n2 =
         (active && tile + 2 * tstride < n_tiles) ? __ldg(cell_base + (tile + 2 * tstride) * CPT + c) : kNoCell;
 
