@@ -161,7 +161,6 @@ int bp5_operator_destroy(bp5_operator_t op) {
   peer_destroy(op);
   cudaFree(op->cell_base);
   cudaFree(op->l2g_irr);
-  cudaFree(op->skel_mask);
   cudaFree(op->mf_l2g); cudaFree(op->mf_constraint_mask); cudaFree(op->mf_inv_jacobian);
   cudaFree(op->mf_jxw); cudaFree(op->mf_q_points);
   cudaFree(op->metric);

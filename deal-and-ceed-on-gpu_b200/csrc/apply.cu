@@ -142,20 +142,10 @@ int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool over
   return BP5_ERR_UNSUPPORTED;
 }
 
-// dst = 0 on the skeleton only: owned DoFs shared by more than one cell (bit set
-// in skel_mask) and all ghost DoFs.  Cell-interior DoFs are left alone; the
-// OVERWRITE kernel stores them.  One 32-bit mask word serves a whole warp.
-__global__ void zero_skeleton_kernel(double *__restrict__ dst, const uint32_t *__restrict__ mask, long long n_owned,
-                                     long long n_total) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_total;
-       i += (long long)gridDim.x * blockDim.x) {
-    if (i >= n_owned || ((__ldg(mask + (i >> 5)) >> (i & 31)) & 1u)) dst[i] = 0.0;
-  }
-}
-
-// Measured (profiles/r1_v2_notes.md): zeroing only the skeleton through the bit mask is SLOWER
-// than a full memset (scattered partial-sector writes) and saves no DRAM traffic, because L2
-// fills partially written sectors anyway.  So "dst = 0" is a plain memset.
+// "dst = 0" (bp5/step-64.cu:270-271) only has to reach the skeleton -- DoFs shared by several cells and the
+// ghosts; cell-interior DoFs are stored by the OVERWRITE kernel.  Measured (profiles/r1_v2_notes.md): zeroing
+// only the skeleton through a bit mask is SLOWER than a full memset (scattered partial-sector writes) and saves
+// no DRAM traffic, because L2 fills partially written sectors anyway.  So it is a plain memset.
 int apply_zero_skeleton(bp5_operator_t op, double *dst) {
   BP5_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (op->n_owned + op->n_ghost), op->ctx->stream));
   return BP5_OK;

@@ -23,11 +23,11 @@
 //    "home" (owns the z-column (i,j,*)), "x-line" and "y-line" roles, holding a
 //    whole line in registers, so one 1D contraction costs one shared-memory load
 //    and one store per point instead of n loads; the z direction never leaves
-//    registers.  Shape matrices are kernel parameters (constant bank).  Line
-//    contractions whose result goes to shared memory or straight to the scatter
-//    keep their OUTER loop rolled: one matrix row (uniform-indexed LDCU) is live
-//    at a time.  Fully unrolled, ptxas caches matrix entries across contractions
-//    in the 63 uniform registers and spills them (MOV.SPILL / R2UR.FILL per DFMA).
+//    registers.  Every contraction is done in even-odd form (EoShape below):
+//    half the matrix operands and ~25-30 % fewer fp64 operations.  Shape matrices
+//    are kernel parameters (constant bank), one private packed copy per direction,
+//    so that ptxas has no cross-contraction reuse to cache in (and spill from) the
+//    63 uniform registers (MOV.SPILL / R2UR.FILL per DFMA, measured 2x slower).
 //  * scatter: DoFs interior to a cell have exactly one contribution: with
 //    OVERWRITE they are written with a plain store (no zero-fill before, no
 //    read-modify-write); only the skeleton (faces/edges/vertices) uses

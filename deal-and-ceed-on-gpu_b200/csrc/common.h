@@ -65,14 +65,6 @@ void gauss_rule01(int n, double *x, double *w);
 void lobatto_rule01(int n, double *x, double *w);
 void lagrange_eval(int n, const double *nodes, double x, double *val, double *der);
 
-// Shape tables as they travel to a kernel (by value, in the parameter constant
-// bank, so that fully unrolled loops read them as immediate constant operands).
-template <int N>
-struct ShapeTables {
-  double B[N * N];
-  double Dt[N * N];
-};
-
 // ---- handles ---------------------------------------------------------------
 }  // namespace bp5
 
@@ -123,7 +115,6 @@ struct bp5_operator_s {
   unsigned int *mf_l2g = nullptr, *mf_constraint_mask = nullptr;
   double *mf_inv_jacobian = nullptr, *mf_jxw = nullptr, *mf_q_points = nullptr;
   int mf_padding = 0;
-  uint32_t *skel_mask = nullptr; // bit i set: owned dof i is shared by more than one cell (skeleton)
   double *coords = nullptr;     // BP5_GEOM_ON_THE_FLY: nodal coordinates [3][n_owned + n_ghost] instead of the metric
   double *metric = nullptr;     // [tile][cpt][planes][n^3]; planes: 6 (Poisson) or 7 (Helmholtz: + a*JxW)
   int metric_planes = 6;

@@ -103,23 +103,6 @@ __device__ __forceinline__ double det3(const double J[3][3]) {
          J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
 }
 
-// bit i of mask: owned dof i lies on a cell face (shared by more than one cell,
-// or by a cell of a neighbouring block): the "skeleton".  One thread per word.
-__global__ void skeleton_mask_kernel(BlockGeom g, uint32_t *__restrict__ mask, long long n_words) {
-  const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (w >= n_words) return;
-  uint32_t bits = 0;
-  for (int bit = 0; bit < 32; ++bit) {
-    const long long idx = w * 32 + bit;
-    if (idx >= g.n_owned) break;
-    const int i = (int)(idx % g.od[0]) + g.hlo[0];
-    const int j = (int)((idx / g.od[0]) % g.od[1]) + g.hlo[1];
-    const int k = (int)(idx / ((long long)g.od[0] * g.od[1])) + g.hlo[2];
-    if (i % g.p == 0 || j % g.p == 0 || k % g.p == 0) bits |= 1u << bit;
-  }
-  mask[w] = bits;
-}
-
 // One block per local cell (lexicographic); `slot` is the cell's position in the processing order
 // (cell_slot()).  Writes metric[tile][cell in tile][planes][n3] at that position and, for
 // irregular cells (cell_base < 0), the explicit index table l2g_irr[table][n3].
@@ -315,11 +298,6 @@ int operator_setup_device(bp5_operator_t op) {
   const size_t smem = sizeof(double) * 8 * n3;
   setup_cells_kernel<<<(unsigned)op->n_cells, threads, smem, ctx->stream>>>(g, op->cell_base, slot_dev, op->l2g_irr,
                                                                             op->metric);
-  BP5_CHECK_LAUNCH();
-  ctx->launches++;
-  const long long n_words = (op->n_owned + 31) / 32;
-  BP5_CUDA(cudaMalloc(&op->skel_mask, sizeof(uint32_t) * std::max<long long>(n_words, 1)));
-  skeleton_mask_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, ctx->stream>>>(g, op->skel_mask, n_words);
   BP5_CHECK_LAUNCH();
   ctx->launches++;
 

@@ -16,7 +16,11 @@ dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 fails = 0
 CASES = [(2, (3, 2, 2), dc.QUAD_GAUSS, 0, 0), (4, (2, 2, 3), dc.QUAD_GLL, 1, 0), (6, (2, 2, 2), dc.QUAD_GLL, 1, 0),
          (5, (3, 3, 2), dc.QUAD_GAUSS, 0, 0), (5, (2, 3, 2), dc.QUAD_GLL, 1, 1)]      # last: geometry on the fly
-for transport, (p, cpg, quad, deform, geom) in [(t, c) for t in ("peer", "nccl") for c in CASES]:
+# CHECK_TRANSPORTS=peer,nccl  CHECK_CASES=0,1,4  restrict the run (large boxes are charged per GPU)
+TRANSPORTS = os.environ.get("CHECK_TRANSPORTS", "peer,nccl").split(",")
+if "CHECK_CASES" in os.environ:
+    CASES = [CASES[int(i)] for i in os.environ["CHECK_CASES"].split(",")]
+for transport, (p, cpg, quad, deform, geom) in [(t, c) for t in TRANSPORTS for c in CASES]:
     P = DistributedPoisson(p, cpg, quadrature=quad, deformation=deform, eps=0.1, device=local_rank, transport=transport,
                            geometry_mode=geom)
     cells = P.part.cells
