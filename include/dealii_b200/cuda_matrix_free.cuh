@@ -108,7 +108,6 @@ template <int dim, typename Number> struct SharedData {
 template <int dim, typename Number = double> class MatrixFree {
   static_assert(dim == 3 && sizeof(Number) == sizeof(double), "the hot path is 3D fp64");
  public:
-  using jacobian_type = Tensor<2, dim, Tensor<1, 1, Number>>;
   enum ParallelizationScheme { parallel_in_elem, parallel_over_elem };
 
   struct AdditionalData {
