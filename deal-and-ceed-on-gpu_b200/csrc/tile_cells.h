@@ -23,7 +23,7 @@ namespace bp5 {
 #define BP5_CPT_P6 3
 #endif
 #ifndef BP5_CPT_P7
-#define BP5_CPT_P7 4
+#define BP5_CPT_P7 2
 #endif
 #ifndef BP5_CPT_P8
 #define BP5_CPT_P8 1

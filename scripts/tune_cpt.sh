@@ -5,7 +5,8 @@ set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 CS=$ROOT/deal-and-ceed-on-gpu_b200/csrc
 declare -A SETS
-SETS[P]="-DBP5_PREFETCH_GATHER(P)=((P)!=6&&(P)!=5)"
+SETS[S3]="-DBP5_CPT_P7=3"
+SETS[S2]="-DBP5_CPT_P7=2"
 for name in "${!SETS[@]}"; do
   out=$ROOT/build/tune/$name; mkdir -p $out
   ( cd $CS && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ ${SETS[$name]} -c apply.cu -o $out/apply.o \
