@@ -52,3 +52,30 @@ def test_problem_struct_layout_matches_header():
     import dealceed_b200 as dc
     # int32 x4, int32 x3, (pad), double x3, double x3, int32, (pad), double, int32 x3, int32 x3, int32 x8
     assert ctypes.sizeof(dc.bindings.Problem) == 16 + 12 + 4 + 24 + 24 + 4 + 4 + 8 + 12 + 12 + 32
+
+
+def test_header_is_plain_c_and_struct_sizes_match_the_ctypes_mirror(tmp_path):
+    """include/bp5_b200.h must compile as C99 (it is the FFI surface: no C++, no CUDA, no torch types), and the
+    structs that cross the boundary by value/pointer must have the layout the ctypes bindings assume"""
+    import subprocess
+    import dealceed_b200 as dc
+    src = tmp_path / "abi_probe.c"
+    src.write_text('#include <stdio.h>\n#include "bp5_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu\\n", sizeof(bp5_problem_t), sizeof(bp5_peer_info_t), '
+                   'sizeof(bp5_matrix_free_data_t)); return 0; }\n')
+    exe = tmp_path / "abi_probe"
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    assert sizes[0] == ctypes.sizeof(dc.bindings.Problem)
+    assert sizes[1] == ctypes.sizeof(dc.bindings.PeerInfo)
+    assert sizes[2] == 5 * 8 + 4 * 4 + 3 * 81 * 8
+
+
+def test_facade_headers_compile_without_cuda(tmp_path):
+    """the host facade is header-only C++17 and must not need nvcc or the CUDA headers"""
+    import subprocess
+    src = tmp_path / "facade_probe.cc"
+    src.write_text('#include "dealii_b200/dealii_b200.h"\nint main() { dealii::Triangulation<3> t; '
+                   'dealii::GridGenerator::hyper_cube(t); t.refine_global(2); return t.n_global_active_cells() == 64 ? 0 : 1; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
