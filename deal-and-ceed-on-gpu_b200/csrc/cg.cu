@@ -807,6 +807,7 @@ int cg_solve_peer(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_
     return BP5_ERR_CUDA;
   }
   BP5_CHECK_LAUNCH();
+  if ((rc = peer_check(op))) return rc;
   if (history && hist_len > 1) {
     const int cnt = std::min(hist_len, fin.it + 1) - 1;
     if (cnt > 0) BP5_CUDA(cudaMemcpy(history + 1, cb.hist + 1, sizeof(double) * cnt, cudaMemcpyDeviceToHost));

@@ -180,6 +180,7 @@ int peer_allreduce(bp5_operator_t op, const double *local_dev, double *out_dev, 
 int peer_allreduce_host(bp5_operator_t op, double *vals, int n);
 int peer_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src);
 double *peer_scratch(bp5_operator_t op);
+int peer_check(bp5_operator_t op);
 int cg_solve_peer(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,
                   int max_its, int *last_step, double *last_value, double *history, int history_len);
 // cg.cu

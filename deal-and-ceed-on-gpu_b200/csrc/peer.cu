@@ -52,7 +52,7 @@ struct PeerState {
   double *rev_dst[8] = {nullptr};                 // where ghost group m lands: lower(m)'s recv_rev segment
   int *rev_flag[8] = {nullptr};                   // lower(m)'s rev flag m
   // device words: [0],[1] tickets for "last block" detection; [2] halo epoch = exchanges executed;
-  // [3] sum epoch = allreduces executed.  The epochs live on the device and only advance when the kernel
+  // [3] sum epoch = allreduces executed; [4] error latch (a wait timed out).  The epochs live on the device and only advance when the kernel
   // really runs (not when the CG has converged and every kernel is a no-op), so they stay equal on all
   // ranks even though the hosts may enqueue different numbers of no-op iterations.
   unsigned *ticket = nullptr;
@@ -70,6 +70,25 @@ __device__ __forceinline__ int ld_acquire_sys(const int *p) {
   int v;
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+
+// Wait until *flag has reached `epoch`.  A neighbour that died (or a caller that broke the collective call
+// order) must not hang this GPU: after kPeerTimeoutNs the wait gives up, latches *err, and every later wait
+// returns at once; the host reports the failure when the solve ends (peer_check).
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ void spin_until(const int *flag, int epoch, unsigned *err) {
+  if (*reinterpret_cast<volatile unsigned *>(err) != 0) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  unsigned spins = 0;
+  while (ld_acquire_sys(flag) - epoch < 0) {
+    __nanosleep(64);
+    if ((++spins & 1023u) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > kPeerTimeoutNs) { atomicExch(err, 1u); return; }
+    }
+  }
 }
 
 struct PeerSendGeom {
@@ -143,21 +162,21 @@ __global__ void peer_reverse_kernel(PeerSendGeom g, const double *__restrict__ v
 }
 
 // wait until the lower neighbours' forward data of this epoch has landed (one thread per group)
-__global__ void peer_wait_forward_kernel(PeerSendGeom g, const int *flags, const unsigned *epoch_word, const int *skip) {
+__global__ void peer_wait_forward_kernel(PeerSendGeom g, const int *flags, const unsigned *epoch_word, unsigned *err,
+                                         const int *skip) {
   if (skip != nullptr && *skip != 0) return;
   const int m = threadIdx.x;
   const int epoch = (int)*epoch_word;
-  if (m >= 1 && m < 8 && g.gcount[m] > 0)
-    while (ld_acquire_sys(flags + m) - epoch < 0) __nanosleep(64);
+  if (m >= 1 && m < 8 && g.gcount[m] > 0) spin_until(flags + m, epoch, err);
 }
 
 // wait for the upper neighbours' contributions, then vec[owned upper faces] += landing zone
 __global__ void peer_wait_add_kernel(PeerSendGeom g, double *__restrict__ vec, const double *__restrict__ recv,
-                                     long long total, const int *flags, const unsigned *epoch_word, const int *skip) {
+                                     long long total, const int *flags, const unsigned *epoch_word, unsigned *err,
+                                     const int *skip) {
   if (skip != nullptr && *skip != 0) return;
   const int epoch = (int)*epoch_word;
-  if (threadIdx.x >= 1 && threadIdx.x < 8 && g.count[threadIdx.x] > 0)
-    while (ld_acquire_sys(flags + 8 + threadIdx.x) - epoch < 0) __nanosleep(64);
+  if (threadIdx.x >= 1 && threadIdx.x < 8 && g.count[threadIdx.x] > 0) spin_until(flags + 8 + threadIdx.x, epoch, err);
   __syncthreads();
   // different groups can hit the same owned DoF (a corner is in the face, edge and corner groups)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -176,7 +195,8 @@ struct PeerSumPtrs {
 // One block.  Stores `n_vals` (<= 8) local sums into slot [parity][rank] of every rank's mailbox, raises the
 // flags, waits for everybody's, and leaves the rank-ordered total in out[0..n_vals).
 __global__ void peer_allreduce_kernel(PeerSumPtrs pp, const double *__restrict__ local, double *__restrict__ out,
-                                      int n_vals, int rank, int world, unsigned *epoch_word, const int *skip) {
+                                      int n_vals, int rank, int world, unsigned *epoch_word, unsigned *err,
+                                      const int *skip) {
   if (skip != nullptr && *skip != 0) return;
   __shared__ int epoch_sh;
   if (threadIdx.x == 0) epoch_sh = (int)(++*epoch_word);
@@ -193,8 +213,7 @@ __global__ void peer_allreduce_kernel(PeerSumPtrs pp, const double *__restrict__
   __syncthreads();
   if (t < world) st_release_sys(pp.sumflag[t] + parity * kPeerMaxWorld + rank, epoch);
   if (t < world) {
-    const int *f = pp.sumflag[rank] + parity * kPeerMaxWorld + t;
-    while (ld_acquire_sys(f) - epoch < 0) __nanosleep(32);
+    spin_until(pp.sumflag[rank] + parity * kPeerMaxWorld + t, epoch, err);
   }
   __syncthreads();
   if (t < n_vals) {
@@ -245,8 +264,8 @@ int peer_export(bp5_operator_t op, int rank, int world, bp5_peer_info_t *out) {
     ps->rank = rank; ps->world = world;
     BP5_CUDA(cudaMalloc(&ps->buf, sizeof(double) * ps->lay.total));
     BP5_CUDA(cudaMemset(ps->buf, 0, sizeof(double) * ps->lay.total));
-    BP5_CUDA(cudaMalloc(&ps->ticket, sizeof(unsigned) * 4));
-    BP5_CUDA(cudaMemset(ps->ticket, 0, sizeof(unsigned) * 4));
+    BP5_CUDA(cudaMalloc(&ps->ticket, sizeof(unsigned) * 8));
+    BP5_CUDA(cudaMemset(ps->ticket, 0, sizeof(unsigned) * 8));
     BP5_CUDA(cudaMalloc(&ps->scratch, sizeof(double) * 16));
     BP5_CUDA(cudaMemset(ps->scratch, 0, sizeof(double) * 16));
     BP5_CUDA(cudaDeviceSynchronize());   // the memsets ran on the default stream; everything else uses ctx->stream
@@ -337,7 +356,7 @@ int peer_forward(bp5_operator_t op, const double *vec_owned_of_d) {
   BP5_CHECK_LAUNCH();
   op->ctx->launches++;
   if (op->n_ghost > 0) {
-    peer_wait_forward_kernel<<<1, 32, 0, s>>>(g, flag_ptr(ps->buf, ps->lay), ps->ticket + 2, op->skip_flag);
+    peer_wait_forward_kernel<<<1, 32, 0, s>>>(g, flag_ptr(ps->buf, ps->lay), ps->ticket + 2, ps->ticket + 4, op->skip_flag);
     BP5_CHECK_LAUNCH();
     op->ctx->launches++;
   }
@@ -362,7 +381,8 @@ int peer_wait_add(bp5_operator_t op, double *vec) {
   if (ps->n_send == 0) return BP5_OK;
   const PeerSendGeom g = make_geom(op, ps);
   peer_wait_add_kernel<<<copy_grid(ps->n_send), 256, 0, op->ctx->stream>>>(
-      g, vec, ps->buf + ps->lay.recv_rev, ps->n_send, flag_ptr(ps->buf, ps->lay), ps->ticket + 2, op->skip_flag);
+      g, vec, ps->buf + ps->lay.recv_rev, ps->n_send, flag_ptr(ps->buf, ps->lay), ps->ticket + 2, ps->ticket + 4,
+      op->skip_flag);
   BP5_CHECK_LAUNCH();
   op->ctx->launches++;
   return BP5_OK;
@@ -381,7 +401,8 @@ int peer_allreduce(bp5_operator_t op, const double *local_dev, double *out_dev, 
   }
   const int threads = ((ps->world * 8 + 31) / 32) * 32;
   peer_allreduce_kernel<<<1, threads, 0, op->ctx->stream>>>(pp, local_dev, out_dev, n_vals, ps->rank, ps->world,
-                                                           ps->ticket + 3, honour_skip ? op->skip_flag : nullptr);
+                                                           ps->ticket + 3, ps->ticket + 4,
+                                                           honour_skip ? op->skip_flag : nullptr);
   BP5_CHECK_LAUNCH();
   op->ctx->launches++;
   return BP5_OK;
@@ -391,6 +412,19 @@ int peer_allreduce(bp5_operator_t op, const double *local_dev, double *out_dev, 
 
 namespace bp5 {
 double *peer_scratch(bp5_operator_t op) { return static_cast<PeerState *>(op->peer)->scratch; }
+
+// after a collective call has been synchronised: did any wait give up?
+int peer_check(bp5_operator_t op) {
+  PeerState *ps = static_cast<PeerState *>(op->peer);
+  unsigned err = 0;
+  BP5_CUDA(cudaMemcpyAsync(&err, ps->ticket + 4, sizeof(unsigned), cudaMemcpyDeviceToHost, op->ctx->stream));
+  BP5_CUDA(cudaStreamSynchronize(op->ctx->stream));
+  if (err != 0) {
+    set_error("peer exchange timed out: a neighbouring rank did not reach the same collective call");
+    return BP5_ERR_CUDA;
+  }
+  return BP5_OK;
+}
 
 // sum over all ranks of n host values (norms, parity checks): host -> device -> peers -> host
 int peer_allreduce_host(bp5_operator_t op, double *vals, int n) {
@@ -402,7 +436,7 @@ int peer_allreduce_host(bp5_operator_t op, double *vals, int n) {
   if ((rc = peer_allreduce(op, ps->scratch, ps->scratch + 8, n, false))) return rc;
   BP5_CUDA(cudaMemcpyAsync(vals, ps->scratch + 8, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
   BP5_CUDA(cudaStreamSynchronize(s));
-  return BP5_OK;
+  return peer_check(op);
 }
 
 // PoissonOperator::vmult over the partition through the peer transport (bp5/step-64.cu:263-276 with the
