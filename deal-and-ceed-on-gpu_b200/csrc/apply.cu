@@ -52,7 +52,10 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
   using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = P + 1;
   auto kernel = bp5_apply_kernel<P, QUAD, HELM, CPT, OVERWRITE, MLOAD>;
-  static int blocks_per_sm = 0;   // per instantiation
+  // per instantiation and per device: function attributes belong to the device's context, and the C ABI allows
+  // contexts on several devices in one process
+  static int blocks_per_sm_of[64] = {0};
+  int &blocks_per_sm = blocks_per_sm_of[op->ctx->device & 63];
   if (blocks_per_sm == 0) {
     BP5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     // all of the L1/shared array as shared memory (the kernel's working set is its tiles; the gathers are

@@ -10,7 +10,10 @@ static int launch_otf(bp5_operator_t op, double *dst, const double *src, double 
   using Cfg = ApplyOtfCfg<P, CPT>;
   constexpr int N = P + 1;
   auto kernel = bp5_apply_otf_kernel<P, CPT, OVERWRITE>;
-  static int blocks_per_sm = 0;   // per instantiation
+  // per instantiation and per device: function attributes belong to the device's context, and the C ABI allows
+  // contexts on several devices in one process
+  static int blocks_per_sm_of[64] = {0};
+  int &blocks_per_sm = blocks_per_sm_of[op->ctx->device & 63];
   if (blocks_per_sm == 0) {
     BP5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     int nb = 0;

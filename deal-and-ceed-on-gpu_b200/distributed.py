@@ -201,7 +201,21 @@ class DistributedPoisson:
         self.n_global = self.part.n_global
         self.transport = transport if self.world > 1 else "nccl"
         if self.transport == "peer":
-            self._connect_peers()
+            # all ranks or none: a rank that cannot map its neighbours (no peer access between two devices, IPC
+            # disabled in a container) sends everybody to the NCCL transport
+            try:
+                self._connect_peers()
+                ok = 1
+            except B.Bp5Error as e:
+                ok, self._peer_error = 0, str(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{self.device}")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if self.rank == 0:
+                    import sys
+                    print("dealceed_b200: peer-memory transport unavailable, using NCCL "
+                          f"({getattr(self, '_peer_error', 'a neighbour failed to connect')})", file=sys.stderr)
+                self.transport = "nccl"
         elif self.transport != "nccl":
             raise ValueError(f"unknown transport {transport!r}")
 
@@ -209,9 +223,15 @@ class DistributedPoisson:
         """publish this block's IPC handles, map everybody else's (bp5_peer_export / bp5_peer_connect)"""
         lib, C, dist = B.lib(), B.C, self.dist
         info = B.PeerInfo()
-        B._check(lib.bp5_peer_export(self.op.h, self.rank, self.world, C.byref(info)))
+        try:
+            B._check(lib.bp5_peer_export(self.op.h, self.rank, self.world, C.byref(info)))
+            blob = bytes(info)
+        except B.Bp5Error as e:          # still take part in the gather: nobody may be left waiting
+            blob, self._peer_error = None, str(e)
         blobs = [None] * self.world
-        dist.all_gather_object(blobs, bytes(info))
+        dist.all_gather_object(blobs, blob)
+        if any(b is None for b in blobs):
+            raise B.Bp5Error(B.ERR_UNSUPPORTED, "a rank could not export its peer buffers")
         infos = (B.PeerInfo * self.world)()
         for r, blob in enumerate(blobs):
             C.memmove(C.byref(infos[r]), blob, C.sizeof(B.PeerInfo))
@@ -220,7 +240,6 @@ class DistributedPoisson:
         lower = (C.c_int32 * 8)(*[as_rank(self.part.lower(m)) if m else -1 for m in range(8)])
         B._check(lib.bp5_peer_connect(self.op.h, infos, upper, lower))
         self.ctx.synchronize()
-        dist.barrier()          # everybody is mapped before the first exchange
 
     # -- helpers ---------------------------------------------------------------------------------
     def view(self, vec):
