@@ -230,6 +230,34 @@ def measure_e2e(dc, torch, ctx, stream, op, steps, warmup):
     return dict(secs=secs, its_total=its_total, h2d=n * 8, d2h=n * 8, xnorm=float(np.linalg.norm(xnp)))
 
 
+def measure_helmholtz(dc, torch, ctx, stream):
+    """BASELINE configs[1]: step-64 variable-coefficient Helmholtz, p=4, 64^3 cells = 257^3 DoFs, merged CG with
+    SolverControl(n_dofs, 1e-12|b|) (step-64/step-64.cu:513-514).  Reported under "variants"; never fatal."""
+    try:
+        op = dc.PoissonOperator(ctx, dc.make_problem(4, (64, 64, 64), operator_kind=dc.OP_HELMHOLTZ, upper=(1., 1., 1.)))
+        b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+        op.assemble_rhs(b)
+        n = op.n_owned
+        op.do_zero_out = False
+        control = dc.SolverControl(n, 1e-12 * b.l2_norm())
+        secs = None
+        for rep in range(2):                      # warm-up, then timed
+            x.set(0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            dc.SolverCGFullMerge(control).solve(op, x, b, history=False)
+            e1.record(stream)
+            e1.synchronize()
+            secs = e0.elapsed_time(e1) * 1e-3
+        out = {"workload": "step-64 Helmholtz, p=4, 64^3 cells, SolverControl(n_dofs, 1e-12|b|), QGauss(5)", "dofs": n,
+               "iterations": control.last_step(), "value": n * control.last_step() / secs / 1e9, "unit": UNIT,
+               "ms_per_solve": secs * 1e3, "kernel": op.kernel_name, "solution_norm_L2": op.l2_norm(x)}
+        b.close(); x.close(); op.close()
+        return out
+    except Exception as e:                        # a side measurement must not cost the headline line
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -272,6 +300,9 @@ def run_b200(args):
             r["e2e"] = measure_e2e(dc, torch, ctx, stream, op, max(1, min(args.steps, 3)), args.warmup)
         results[qname] = r
         op.close()
+    helm = None
+    if not args.no_variants:
+        helm = measure_helmholtz(dc, torch, ctx, stream)
     ctx.close()
 
     def summarize(r):
@@ -330,6 +361,8 @@ def run_b200(args):
                            "kernel": r["kernel"], "roofline_achieved": a, "roofline_frac": a / hbm_peak,
                            "avg_launch_ms": ks * 1e3, "iterations_per_step": r["its_per_step"],
                            "cg_frac": r["bytes_cg"] * r["its_total"] / r["secs"] / 1e9 / hbm_peak, "x_l2": r["xnorm"]}
+    if helm is not None:
+        variants["helmholtz_config2"] = helm
     out["variants"] = variants
     if not args.no_cpu_baseline:
         cells = args.cpu_cells or auto_cpu_cells(args.degree)
