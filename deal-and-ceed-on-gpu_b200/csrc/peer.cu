@@ -121,7 +121,10 @@ __device__ __forceinline__ bool grid_last_block(unsigned *ticket) {
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(ticket, 1u);
     last = (t == gridDim.x - 1);
-    if (last) *ticket = 0;
+    if (last) {
+      *ticket = 0;
+      __threadfence_system();     // acquire side: the other blocks' fenced stores are ordered before what follows
+    }
   }
   __syncthreads();
   return last;
