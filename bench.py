@@ -115,15 +115,22 @@ def cpu_arm(degree, quad_name, cells, iterations, repeats=1):
     m = O.OracleMesh(degree, (cells,) * 3, quad=quad)
     b = m.rhs()
     best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        x, its, res, hist, ok = m.cg(b, variant=1, control=0, tol=0.0, max_its=iterations)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
+    # timing only: the vectorisable collocation cell operator for GLL (same results to 1e-16, tests pin it);
+    # Gauss quadrature runs the general evaluator
+    O.lib().orc_set_fast_path(1)
+    try:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            x, its, res, hist, ok = m.cg(b, variant=1, control=0, tol=0.0, max_its=iterations)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    finally:
+        O.lib().orc_set_fast_path(0)
     return {"value": m.n_dofs * its / best / 1e9, "unit": UNIT, "cores": O.lib().orc_num_threads(),
             "kind": "port", "seconds": best,
             "sample": f"BP5 p={degree} {quad_name}, {cells}^3 cells = {m.n_dofs} DoFs, {its} merged-CG iterations "
-                      f"(OpenMP oracle, restatement of the deal.II CPU path, not deal.II itself)"}, m.n_dofs
+                      f"(OpenMP oracle, restatement of the deal.II CPU path, not deal.II itself"
+                      f"{'; vectorisable collocation cell operator' if quad_name == 'gll' else ''})"}, m.n_dofs
 
 
 def auto_cpu_cells(degree):

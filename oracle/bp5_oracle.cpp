@@ -359,6 +359,73 @@ void cell_apply(const Mesh &m, int64_t c, int kind, const double *u, double *v) 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Timing-only variant of the Poisson cell operator for Gauss-Lobatto collocation (what deal.II's CPU
+// FEEvaluation does for FE_Q + QGaussLobatto(p+1): no interpolation, three collocation derivatives, merged
+// coefficient, three transposed derivatives) with unit-stride inner loops the compiler vectorises.  Used by
+// bench.py's CPU arm when orc_set_fast_path(1) was called, so that the CPU baseline is not a strawman; the
+// checker path (everything the tests compare the GPU with) stays cell_apply() above.
+// tests/test_oracle_vs_numpy.py pins fast == general to 1e-13.
+static int g_fast_path = 0;
+
+template <int N>
+void cell_apply_gll(const Mesh &m, int64_t c, const double *u, double *v) {
+  constexpr int N2 = N * N, N3 = N2 * N;
+  const double *D = m.T.Dg.data();               // D[q][i]; nodes == quadrature points
+  double DT[N * N];
+  for (int q = 0; q < N; ++q)
+    for (int i = 0; i < N; ++i) DT[i * N + q] = D[q * N + i];
+  double gx[N3], gy[N3], gz[N3];
+  for (int a = 0; a < N3; ++a) gx[a] = gy[a] = gz[a] = 0.0;
+  // d/dx: gx[kj][q] += D[q][i] u[kj][i]
+  for (int kj = 0; kj < N2; ++kj)
+    for (int i = 0; i < N; ++i) {
+      const double ui = u[kj * N + i];
+      for (int q = 0; q < N; ++q) gx[kj * N + q] += DT[i * N + q] * ui;
+    }
+  // d/dy: gy[k][q][i] += D[q][j] u[k][j][i]
+  for (int k = 0; k < N; ++k)
+    for (int q = 0; q < N; ++q)
+      for (int j = 0; j < N; ++j) {
+        const double d = D[q * N + j];
+        for (int i = 0; i < N; ++i) gy[(k * N + q) * N + i] += d * u[(k * N + j) * N + i];
+      }
+  // d/dz: gz[q][ji] += D[q][k] u[k][ji]
+  for (int q = 0; q < N; ++q)
+    for (int k = 0; k < N; ++k) {
+      const double d = D[q * N + k];
+      for (int ji = 0; ji < N2; ++ji) gz[q * N2 + ji] += d * u[k * N2 + ji];
+    }
+  const int64_t nc = m.n_cells;
+  const double *G0 = &m.G[((size_t)0 * nc + c) * N3], *G1 = &m.G[((size_t)1 * nc + c) * N3],
+               *G2 = &m.G[((size_t)2 * nc + c) * N3], *G3 = &m.G[((size_t)3 * nc + c) * N3],
+               *G4 = &m.G[((size_t)4 * nc + c) * N3], *G5 = &m.G[((size_t)5 * nc + c) * N3];
+  for (int q = 0; q < N3; ++q) {
+    const double g0 = gx[q], g1 = gy[q], g2 = gz[q];
+    gx[q] = g0 * G0[q] + g1 * G3[q] + g2 * G4[q];
+    gy[q] = g0 * G3[q] + g1 * G1[q] + g2 * G5[q];
+    gz[q] = g0 * G4[q] + g1 * G5[q] + g2 * G2[q];
+  }
+  for (int a = 0; a < N3; ++a) v[a] = 0.0;
+  // transposes: v[kj][i] += D[q][i] gx[kj][q] ; v[k][j][i] += D[q][j] gy[k][q][i] ; v[k][ji] += D[q][k] gz[q][ji]
+  for (int kj = 0; kj < N2; ++kj)
+    for (int q = 0; q < N; ++q) {
+      const double g = gx[kj * N + q];
+      for (int i = 0; i < N; ++i) v[kj * N + i] += D[q * N + i] * g;
+    }
+  for (int k = 0; k < N; ++k)
+    for (int j = 0; j < N; ++j)
+      for (int q = 0; q < N; ++q) {
+        const double d = D[q * N + j];
+        for (int i = 0; i < N; ++i) v[(k * N + j) * N + i] += d * gy[(k * N + q) * N + i];
+      }
+  for (int k = 0; k < N; ++k)
+    for (int q = 0; q < N; ++q) {
+      const double d = D[q * N + k];
+      for (int ji = 0; ji < N2; ++ji) v[k * N2 + ji] += d * gz[q * N2 + ji];
+    }
+}
+
 template <int N>
 void apply_all(const Mesh &m, int kind, const double *src, double *dst) {
   constexpr int N3 = N * N * N;
@@ -377,7 +444,8 @@ void apply_all(const Mesh &m, int kind, const double *src, double *dst) {
         for (int j = 0; j < N; ++j)
           for (int i = 0; i < N; ++i)
             u[(k * N + j) * N + i] = src[m.dof(cx * p + i, cy * p + j, cz * p + k)];
-      cell_apply<N>(m, c, kind, u, v);
+      if (g_fast_path && kind == 0 && m.quad_kind == 1) cell_apply_gll<N>(m, c, u, v);
+      else cell_apply<N>(m, c, kind, u, v);
       for (int k = 0; k < N; ++k)
         for (int j = 0; j < N; ++j)
           for (int i = 0; i < N; ++i)
@@ -658,6 +726,7 @@ int orc_cg(void *h, int kind, int variant, int control, double tol, int max_its,
       ++it;
       // 1) update region (update_a0 / update_a / update_a1, solver.h:48-140)
       if (alpha == 0.0) {
+#pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < N; ++i) { d[i] = -diag[i] * g[i]; hh[i] = 0.0; }
       } else {
         bool two_step;
@@ -666,6 +735,7 @@ int orc_cg(void *h, int kind, int variant, int control, double tol, int max_its,
         const bool skip_x = (variant == 2) ? (alpha_old == 0.0) : (it % 2 == 0);
         const double apa = two_step && beta_old != 0.0 ? alpha + alpha_old / beta_old : 0.0;
         const double aob = two_step && beta_old != 0.0 ? alpha_old / beta_old : 0.0;
+#pragma omp parallel for schedule(static)      // element-wise: identical results for any thread count
         for (int64_t i = 0; i < N; ++i) {
           const double r_old = g[i], r_new = r_old + alpha * hh[i], pst = d[i];
           if (two_step) x[i] += apa * pst + aob * diag[i] * r_old;
@@ -713,6 +783,10 @@ int orc_cg(void *h, int kind, int variant, int control, double tol, int max_its,
   *its_out = it; *res_out = res;
   return conv == 1 ? 0 : 1;
 }
+
+// 1: bench.py's CPU arm uses the vectorisable collocation cell operator (Poisson, GLL); 0 (default): the
+// general evaluator everywhere, which is what every test compares against
+void orc_set_fast_path(int on) { g_fast_path = on; }
 
 int orc_num_threads(void) {
 #ifdef _OPENMP

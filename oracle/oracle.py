@@ -56,6 +56,7 @@ def lib():
         L.orc_shape.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.orc_gauss01.argtypes = [C.c_int, _dp, _dp]
         L.orc_lobatto01.argtypes = [C.c_int, _dp, _dp]
+        L.orc_set_fast_path.argtypes = [C.c_int]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
         _LIB = L

@@ -82,3 +82,26 @@ def test_cg_matches_scipy_free_textbook_cg():
     x, its, res, hist, ok = m.cg(b, variant=1, control=1, tol=tol, max_its=500)
     assert ok and abs(its - itr) <= 1
     assert np.linalg.norm(x - xr) <= 1e-7 * np.linalg.norm(xr)
+
+
+def test_timing_variant_of_the_cell_operator_equals_the_general_one():
+    """orc_set_fast_path(1) (bench.py's CPU arm only: collocation derivatives with unit-stride loops) changes nothing
+    but the speed: <= 1e-13 against the general evaluator every test uses, p = 1..8, deformed mesh"""
+    L = O.lib()
+    try:
+        for p in range(1, 9):
+            m = O.OracleMesh(p, (3, 2, 2), quad=O.GLL, deform=1, eps=0.1)
+            u = np.random.default_rng(p).standard_normal(m.n_dofs)
+            L.orc_set_fast_path(0)
+            ref = m.vmult(u)
+            L.orc_set_fast_path(1)
+            fast = m.vmult(u)
+            assert np.linalg.norm(fast - ref) <= 1e-13 * np.linalg.norm(ref)
+            # Gauss quadrature and Helmholtz are not affected by the switch
+            mg = O.OracleMesh(p, (2, 2, 1), quad=O.GAUSS)
+            ug = np.random.default_rng(p).standard_normal(mg.n_dofs)
+            a = mg.vmult(ug, kind=O.HELMHOLTZ)
+            L.orc_set_fast_path(0)
+            assert np.array_equal(a, mg.vmult(ug, kind=O.HELMHOLTZ))
+    finally:
+        L.orc_set_fast_path(0)
