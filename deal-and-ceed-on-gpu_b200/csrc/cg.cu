@@ -147,9 +147,12 @@ __device__ __forceinline__ void cg_scalar_step(CgState *st, const double (&rr)[7
   st->it = it;
   if (rr[0] == 0.0) { st->state = 3; return; }                 // ExcDivideByZero, solver.h:501
   const double alpha = rr[6] / rr[0];                         // solver.h:502
-  // solver.h:504-505; clamped at 0 (deviation): at exact convergence the three-term
-  // expression can round slightly negative and the unguarded sqrt would report NaN.
-  const double res = sqrt(fmax(0.0, rr[3] + 2 * alpha * rr[2] + alpha * alpha * rr[1]));
+  // solver.h:504-505; finite negatives are clamped at 0 (deviation): at exact convergence the
+  // three-term expression can round slightly negative and the unguarded sqrt would report NaN.
+  // A NaN expression (overflow, indefinite operator, inf in diag) must stay NaN so that the
+  // stopping test fails like the reference's (fmax(0, NaN) would turn it into "converged").
+  const double res_sq = rr[3] + 2 * alpha * rr[2] + alpha * alpha * rr[1];
+  const double res = (res_sq < 0.0) ? 0.0 : sqrt(res_sq);
   st->alpha = alpha;
   st->res = res;
   if (history && it < st->history_len) history[it] = res;

@@ -208,8 +208,11 @@ class DistributedPoisson:
                 ok = 1
             except B.Bp5Error as e:
                 ok, self._peer_error = 0, str(e)
-            flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{self.device}")
+            flag = torch.tensor([ok], dtype=torch.int32, device=self._plumbing_device())
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0 and dist.get_backend() != "nccl":
+                raise B.Bp5Error(B.ERR_UNSUPPORTED, "peer-memory transport unavailable and the process group is not "
+                                 f"NCCL: {getattr(self, '_peer_error', 'a neighbour failed to connect')}")
             if int(flag.item()) == 0:
                 if self.rank == 0:
                     import sys
@@ -242,6 +245,11 @@ class DistributedPoisson:
         self.ctx.synchronize()
 
     # -- helpers ---------------------------------------------------------------------------------
+    def _plumbing_device(self):
+        """where the few scalars that travel through torch.distributed live: the GPU under NCCL, the host under
+        gloo (ranks sharing one device in tests)"""
+        return f"cuda:{self.device}" if self.dist.get_backend() == "nccl" else "cpu"
+
     def view(self, vec):
         return device_view(self.torch, vec.get_values(), vec.n_owned + vec.n_ghost, self.device)
 
@@ -260,7 +268,7 @@ class DistributedPoisson:
             self.halo.compress_add(self.view(vec), self._unpack(vec))
 
     def allreduce_scalar(self, value, op=None):
-        t = self.torch.tensor([value], dtype=self.torch.float64, device=f"cuda:{self.device}")
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self._plumbing_device())
         self.dist.all_reduce(t, op=op or self.dist.ReduceOp.SUM)
         return float(t.item())
 

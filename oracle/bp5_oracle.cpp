@@ -693,8 +693,11 @@ int orc_cg(void *h, int kind, int variant, int control, double tol, int max_its,
   int it = 0;
   if (history && history_len > 0) history[0] = res;
   auto check = [&](int step, double value) -> int {  // 0 iterate, 1 success, 2 failure
+    // IterationNumberControl::check / SolverControl::check [UPSTREAM]: reaching max_its is success for the
+    // former only; a NaN residual is a failure for both
+    if (control == 0 && step >= max_its) return 1;
     if (value <= tol) return 1;
-    if (step >= max_its || std::isnan(value)) return control == 0 ? 1 : 2;
+    if (step >= max_its || std::isnan(value)) return 2;
     return 0;
   };
   int conv = check(0, res);
@@ -765,7 +768,11 @@ int orc_cg(void *h, int kind, int variant, int control, double tol, int max_its,
       // solver.h:504-505.  Deviation: clamped at 0 -- at exact (finite-termination)
       // convergence the three-term expression can round to -1e-30 and the
       // unguarded sqrt would turn a converged solve into NaN / NoConvergence.
-      res = std::sqrt(std::max(0.0, r[3] + 2 * alpha * r[2] + alpha * alpha * r[1]));
+      // Only finite negatives are clamped: a NaN must stay NaN (std::max(0.0, NaN) == 0.0 would report convergence).
+      {
+        const double res_sq = r[3] + 2 * alpha * r[2] + alpha * alpha * r[1];
+        res = (res_sq < 0.0) ? 0.0 : std::sqrt(res_sq);
+      }
       if (history && it < history_len) history[it] = res;
       conv = check(it, res);
       if (conv != 0) {

@@ -11,13 +11,23 @@ import oracle as O
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local_rank = int(os.environ.get("LOCAL_RANK", rank))
+# CHECK_SAME_DEVICE=1: every rank uses cuda:0 (a 1-GPU box still exercises the peer transport: CUDA IPC works
+# between processes on one device; the processes time-slice, so the flag waits are slow but finite).  NCCL
+# refuses two ranks on one device, so the plumbing (handle exchange, scalar sums of the checks) is gloo then and
+# only the peer transport runs.
+SAME_DEVICE = os.environ.get("CHECK_SAME_DEVICE", "0") == "1"
+if SAME_DEVICE:
+    local_rank = 0
 torch.cuda.set_device(local_rank)
-dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+if SAME_DEVICE:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 fails = 0
 CASES = [(2, (3, 2, 2), dc.QUAD_GAUSS, 0, 0), (4, (2, 2, 3), dc.QUAD_GLL, 1, 0), (6, (2, 2, 2), dc.QUAD_GLL, 1, 0),
          (5, (3, 3, 2), dc.QUAD_GAUSS, 0, 0), (5, (2, 3, 2), dc.QUAD_GLL, 1, 1)]      # last: geometry on the fly
 # CHECK_TRANSPORTS=peer,nccl  CHECK_CASES=0,1,4  restrict the run (large boxes are charged per GPU)
-TRANSPORTS = os.environ.get("CHECK_TRANSPORTS", "peer,nccl").split(",")
+TRANSPORTS = os.environ.get("CHECK_TRANSPORTS", "peer" if SAME_DEVICE else "peer,nccl").split(",")
 if "CHECK_CASES" in os.environ:
     CASES = [CASES[int(i)] for i in os.environ["CHECK_CASES"].split(",")]
 for transport, (p, cpg, quad, deform, geom) in [(t, c) for t in TRANSPORTS for c in CASES]:

@@ -385,3 +385,25 @@ def test_l2_norm_on_deformed_mesh(gpu_ctx):
         v.import_host(u)
         assert op.l2_norm(v) == pytest.approx(m.l2_norm(u), rel=1e-7)    # Vector<float> cellwise_norm, bp5/step-64.cu:603
         v.close(); op.close()
+
+
+@pytest.mark.parametrize("variant", ["merged", "standard"])
+def test_nan_residual_is_reported_as_no_convergence(gpu_ctx, variant):
+    """A non-finite right-hand side makes alpha and the residual estimate NaN.  The reference's sqrt(NaN) fails
+    SolverControl::check and solve() throws NoConvergence (bp5/solver.h:504-507,539); a clamp that swallowed the
+    NaN would report success with a garbage x."""
+    dc = _dc()
+    op = dc.PoissonOperator(gpu_ctx, dc.make_problem(3, (3, 3, 2), quadrature=1))
+    b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+    op.assemble_rhs(b)
+    bh = b.to_host()
+    bh[op.n_owned // 2] = np.inf
+    b.import_host(bh)
+    op.do_zero_out = False
+    solver = dc.SolverCGFullMerge if variant == "merged" else dc.SolverCG
+    for control in (dc.IterationNumberControl(50, 1e-6), dc.SolverControl(50, 1e-6)):
+        x.set(0.0)
+        with pytest.raises(dc.NoConvergence):
+            solver(control).solve(op, x, b)
+        assert control.last_step() < 50 and not np.isfinite(control.last_value())
+    b.close(); x.close(); op.close()
