@@ -39,6 +39,7 @@
 #include <cstdint>
 
 #include "common.h"
+#include "fused.cuh"
 #include "smem_layout.h"
 
 namespace bp5 {
@@ -107,6 +108,7 @@ struct ApplyParams {
   int sy, sz;             // affine strides of the owned box
   const int *skip;        // optional device flag: non-zero => nothing to do (CG already converged)
   double *dot_partials;   // OVERWRITE == 2: [gridDim.x] per-CTA parts of src . (A src), summed by the CG dots kernel
+  FusedParams fz;         // FUSED kernels only (fused.cuh)
   KernelTables<N> tab;
 };
 
@@ -178,13 +180,15 @@ __device__ __forceinline__ void column_indices(int (&idx)[N], const int *__restr
   }
 }
 
-template <int N>
+// COHERENT: the values were written by other CTAs of the same launch (fused kernel): L2 loads, not the
+// non-coherent L1 path
+template <int N, bool COHERENT = false>
 __device__ __forceinline__ void gather_column(double (&u)[N], const double *__restrict__ src,
                                               const int *__restrict__ l2g_irr, int base, int ab_off, int ab_irr, int sz) {
   int idx[N];
   column_indices<N>(idx, l2g_irr, base, ab_off, ab_irr, sz);
 #pragma unroll
-  for (int k = 0; k < N; ++k) u[k] = __ldg(src + idx[k]);
+  for (int k = 0; k < N; ++k) u[k] = COHERENT ? __ldcg(src + idx[k]) : __ldg(src + idx[k]);
 }
 
 // Rows of the outer loop handled per (rolled) iteration: U independent DFMA
@@ -288,6 +292,12 @@ struct ApplyCfg {
   static constexpr int WORK_DOUBLES = CPT * (2 * L::A_CS + L::B_CS);   // S0, S1 (layout A) and S2 (layout B)
   static constexpr int STAGE_DOUBLES = MLOAD == 0 ? METRIC_DOUBLES : 0;   // shared-memory staging of the metric
   static constexpr size_t SMEM_BYTES = (size_t)STAGE_DOUBLES * 8 + (size_t)WORK_DOUBLES * 8 + 16;
+#ifdef BP5_FZ_NO_STREAM   // tuning builds: no streaming warp at all (timing of the cell path only)
+  static constexpr int NT_FUSED = NT;
+#else
+  static constexpr int NT_FUSED = NT + kFzStreamThreads;   // fused kernel: the cell warps and one streaming warp
+#endif
+  static constexpr size_t SMEM_BYTES_FUSED = ((SMEM_BYTES + 15) & ~(size_t)15) + kFzStageBytes;   // + its staging
   static_assert(METRIC_BYTES % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
 };
 
@@ -299,8 +309,15 @@ struct ApplyCfg {
 // (bp5/solver.h:231,303) without reading either vector again;
 // 1 = cell-interior DoFs are stored, not added (dst's skeleton must be
 // zero on entry, its interior may hold anything); 0 = dst += A src everywhere.
-template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0>
+// FUSED: one CG iteration / one vmult in this launch (fused.cuh): update rows ahead of the cells, finish rows behind
+template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0, int FUSED = 0>
 __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
+  static_assert(!FUSED || (OVERWRITE == 2 && MLOAD == 0), "the fused kernel builds on the overwrite + dot product variant");
+#ifdef BP5_FZ_LDG         // tuning builds: non-coherent gathers in the fused kernel (wrong results, timing only)
+  constexpr bool kCoherent = false;
+#else
+  constexpr bool kCoherent = FUSED != 0;
+#endif
   using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = Cfg::N, N2 = Cfg::N2, N3 = Cfg::N3, PLANES = 6 + HELM;
   constexpr int RC = BP5_ROW_CHUNK(N, QUAD, OVERWRITE);     // rows per rolled iteration of a line contraction
@@ -314,6 +331,9 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   uint64_t *bar = reinterpret_cast<uint64_t *>(S2 + CPT * L::B_CS);
 
   if (prm.skip != nullptr && *prm.skip != 0) return;
+#ifdef BP5_FZ_DEBUG
+  const long long dbg_kernel_t0 = clock64();
+#endif
   const int tid = threadIdx.x;
   const bool active = tid < Cfg::ACTIVE;
   const int c = active ? tid / N2 : 0;      // cell within the tile
@@ -371,6 +391,32 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
     if (active && tile0 < n_tiles) load_metric(tile0);
   }
 
+  // fused kernel (fused.cuh): the streaming warp leaves for its own loop here; the cell warps synchronise among
+  // themselves with a named barrier from now on and meet the streaming warps only through the counter rings
+  [[maybe_unused]] const FusedParams &fz = prm.fz;
+  [[maybe_unused]] unsigned *u_ring = nullptr, *c_ring = nullptr, *fz_err = nullptr;
+  [[maybe_unused]] int fz_S = 1, fz_it = 0, fz_n_it = 0;
+  [[maybe_unused]] double dot_acc = 0.0;
+  auto cell_sync = [&]() {
+#ifdef BP5_FZ_SYNCTHREADS
+    __syncthreads();
+#else
+    if constexpr (FUSED) asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NT) : "memory");
+    else __syncthreads();
+#endif
+  };
+  const bool cell_role = !FUSED || tid < Cfg::NT;
+  if (!cell_role) {
+    if constexpr (FUSED)
+      fz_stream_role(fz, const_cast<double *>(src), dst, make_evict_first_policy(),
+                     reinterpret_cast<double *>(smem_raw + ((Cfg::SMEM_BYTES + 15) & ~(size_t)15)));
+  } else {
+  if constexpr (FUSED) {
+    u_ring = fz.sync; c_ring = fz.sync + kFzRing; fz_err = fz.sync + kFzErr;
+    fz_S = fz.tiles_per_step; fz_n_it = fz.n_steps * fz_S;
+    if (tid == 0 && !(fz.debug & 8)) fz_wait(u_ring, 0, fz_err);      // U(0) complete everywhere: the first gather may start
+    cell_sync();
+  }
   // software pipeline of the gather: cell descriptors two tiles ahead, values one tile ahead
   int base_cur = (active && tile0 < n_tiles) ? __ldg(cell_base + tile0 * CPT + c) : kNoCell;
   int base_nxt = (active && tile0 + tstride < n_tiles) ? __ldg(cell_base + (tile0 + tstride) * CPT + c) : kNoCell;
@@ -379,17 +425,25 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
 #endif
   constexpr bool kPrefetch = BP5_PREFETCH_GATHER(P) != 0;   // values of the next tile in registers one tile ahead
   [[maybe_unused]] double u_nxt[N];
-  if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
+  if constexpr (kPrefetch) gather_column<N, kCoherent>(u_nxt, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
 
   uint32_t parity = 0;
-  [[maybe_unused]] double dot_acc = 0.0;
-  for (long long tile = tile0; tile < n_tiles; tile += tstride) {
+  for (long long tile = tile0; FUSED ? fz_it < fz_n_it : tile < n_tiles; tile += tstride, ++fz_it) {
+    if constexpr (FUSED) {
+      if (fz_it % fz_S == 0) {
+        // start of macro step K: this step's tiles prefetch one tile into the next step, so the rows of step
+        // K + 1 must be updated everywhere (the streaming warps signalled that ua - 1 >= 1 steps ago)
+        { FZ_DBG_T0(); if (tid == 0 && !(fz.debug & 8)) { fz_wait(u_ring, fz_it / fz_S + 1, fz_err); FZ_DBG_ADD(fz, 0); } }
+        cell_sync();
+      }
+    }
+    if (!FUSED || tile < n_tiles) {
     double u[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) u[k] = kPrefetch ? u_nxt[k] : 0.0;
-    if constexpr (!kPrefetch) gather_column<N>(u, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
+    if constexpr (!kPrefetch) gather_column<N, kCoherent>(u, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
     // issue next tile's gather and the descriptor load of the tile after it
-    if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_nxt, ab_off, ab_irr, sz);
+    if constexpr (kPrefetch) gather_column<N, kCoherent>(u_nxt, src, l2g_irr, base_nxt, ab_off, ab_irr, sz);
     const int base_n2 =
         (active && tile + 2 * tstride < n_tiles) ? __ldg(cell_base + (tile + 2 * tstride) * CPT + c) : kNoCell;
 
@@ -411,7 +465,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
           for (int k = 0; k < N; ++k) mv[k] = u[k];
         }
       }
-      __syncthreads();
+      cell_sync();
       // (2) x-line (j=a, k=b) and y-line (i=a, k=b): derivative along the line
       if (active) {
         double v[N];
@@ -422,12 +476,12 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
         contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, v);
       }
-      __syncthreads();
+      cell_sync();
     } else {
       // ---------------- Gauss quadrature: interpolate to the q-points first
       // (1) home (i=a, j=b): z-interpolation
       if (active) contract_to_smem<N, RC, 1>(s0 + hA, A2, Bz, u);
-      __syncthreads();
+      cell_sync();
       // (2) x-line (j=a, qz=b): x-interpolation in place
       if (active) {
         double v[N];
@@ -435,7 +489,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
         contract_to_smem<N, RC, 1>(s0 + xA, 1, Bx, v);
       }
-      __syncthreads();
+      cell_sync();
       // (3) y-line (qx=a, qz=b): y-interpolation (values at q-points), then d/dy
       if (active) {
         double v[N], w[N];
@@ -446,7 +500,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int q = 0; q < N; ++q) s0[yA + q * A1] = w[q];
         contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, w);
       }
-      __syncthreads();
+      cell_sync();
       // (4) x-line (qy=a, qz=b): d/dx ; home (qx=a, qy=b): d/dz in registers
       if (active) {
         double v[N];
@@ -461,7 +515,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
           for (int k = 0; k < N; ++k) mv[k] = v[k];
         }
       }
-      __syncthreads();
+      cell_sync();
     }
 
     // ---------------- quadrature-point phase (home): g <- G g  (bp5/step-64.cu:160-188)
@@ -494,7 +548,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         }
       }
     }
-    __syncthreads();
+    cell_sync();
     if constexpr (MLOAD == 0) {
       // the metric buffer is free: fetch the next tile's metric behind the remaining work
       if (tid == 0 && tile + tstride < n_tiles) {
@@ -521,7 +575,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int j = 0; j < N; ++j) v[j] = s2[yB + j * B1];
         contract_to_smem<N, RC, -1>(s2 + yB, B1, DTy, v);
       }
-      __syncthreads();
+      cell_sync();
       // (5) home: z-transpose in registers, sum the three directions, scatter
       if (do_scatter) {
         double o[N];
@@ -551,7 +605,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
           contract_to_smem<N, RC, -1>(s0 + hA, A2, DTz, t);
         }
       }
-      __syncthreads();
+      cell_sync();
       // (6b) y-line (qx=a, qz=b): D^T along y, add x and z parts, then B^T along y
       if (active) {
         double v[N], y[N];
@@ -562,7 +616,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int q = 0; q < N; ++q) y[q] += s1[yA + q * A1] + s0[yA + q * A1];
         contract_to_smem<N, RC, 1>(s0 + yA, A1, BTy, y);
       }
-      __syncthreads();
+      cell_sync();
       // (7) x-line (j=a, qz=b): B^T along x in place
       if (active) {
         double v[N];
@@ -570,7 +624,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int q = 0; q < N; ++q) v[q] = s0[xA + q];
         contract_to_smem<N, RC, 1>(s0 + xA, 1, BTx, v);
       }
-      __syncthreads();
+      cell_sync();
       // (8) home (i=a, j=b): B^T along z in registers, scatter
       if (do_scatter) {
         double v[N], o[N];
@@ -587,7 +641,17 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
     }
     base_cur = base_nxt;
     base_nxt = base_n2;
+    }   // tile < n_tiles
+    if constexpr (FUSED) {
+      if ((fz_it + 1) % fz_S == 0) {       // this CTA's cells of the macro step are done
+        cell_sync();
+        { FZ_DBG_T0(); if (tid == 0) {
+          if (fz.debug & 4) atomicAdd(c_ring + ((fz_it / fz_S) & (kFzRing - 1)), 1u); else fz_signal(c_ring, fz_it / fz_S);
+          FZ_DBG_ADD(fz, 1); } }
+      }
+    }
   }
+  }   // cell role
   if constexpr (OVERWRITE == 2) {
     // CTA-wide sum in a fixed order (warp shuffles, then warp 0 over the per-warp sums)
     __syncthreads();
@@ -600,8 +664,18 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
       v = tid < Cfg::NT / 32 ? S0[tid] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (tid == 0) prm.dot_partials[blockIdx.x] = v;
+      if constexpr (!FUSED) {
+        if (tid == 0) prm.dot_partials[blockIdx.x] = v;
+      } else {
+        // the cell phase's p.(A p); the streaming warp stored the sums of the U / D phases
+        if (tid == 0) fz.partials[blockIdx.x * kFusedPartials + kFzSlotC] = v;
+      }
     }
+#ifdef BP5_FZ_DEBUG
+    if constexpr (FUSED) if (blockIdx.x == 0 && tid == 0)
+      atomicAdd(reinterpret_cast<unsigned long long *>(prm.fz.sync + kFzDbg) + 6, (unsigned long long)(clock64() - dbg_kernel_t0));
+#endif
+    if constexpr (FUSED) fz_finalize(fz);
   }
 }
 
@@ -609,6 +683,13 @@ template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0>
 __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
     bp5_apply_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
   bp5_apply_body<P, QUAD, HELM, CPT, OVERWRITE, MLOAD>(prm);
+}
+
+// one CG iteration / one vmult per launch (fused.cuh); grid = all co-resident CTAs
+template <int P, int QUAD, int HELM, int CPT>
+__global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, 0>::NT_FUSED), P)
+    bp5_fused_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
+  bp5_apply_body<P, QUAD, HELM, CPT, 2, 0, 1>(prm);
 }
 
 }  // namespace bp5

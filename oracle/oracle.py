@@ -151,3 +151,61 @@ class OracleMesh:
         rc = lib().orc_cg(self.h, kind, variant, control, float(tol), int(max_its), _ptr(d), _ptr(x), _ptr(b),
                           C.byref(its), C.byref(res), _ptr(hist), len(hist))
         return x, its.value, res.value, hist[: its.value + 1], rc == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# Manufactured-solution helpers (numpy, test infrastructure): an analytic anchor for the discretisation that
+# does not depend on any recalled reference output.  The right-hand side b_i = int phi_i f and the L2 error
+# ||u_h - u|| are integrated with QGauss(p+1) on the (possibly deformed) mesh, the way assemble_rhs
+# (bp5/step-64.cu:372-418) and integrate_difference (bp5/step-64.cu:604-615) do it in the reference.
+def _cell_dofs(mesh):
+    """[n_cells, n^3] global lexicographic DoF index of every cell-local DoF (x fastest)."""
+    p, n = mesh.p, mesh.n
+    nx, ny, nz = mesh.cells
+    ndx, ndy, _ = mesh.nd
+    i = np.arange(n)
+    loc = (i[None, None, :] + ndx * (i[None, :, None] + ndy * i[:, None, None])).ravel()
+    cx, cy, cz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    # cells are numbered x fastest
+    cxs, cys, czs = [a.transpose(2, 1, 0).ravel() for a in (cx, cy, cz)]
+    base = p * (cxs + ndx * (cys + ndy * czs))
+    return base[:, None] + loc[None, :]
+
+
+def _interp3(B, vals):
+    """(B x B x B) applied to [cells, n^3] nodal values (x fastest) -> values at the quadrature points."""
+    n = B.shape[0]
+    v = vals.reshape(-1, n, n, n)                       # [c, k, j, i]
+    return np.einsum("ai,bj,ck,nkji->ncba", B, B, B, v).reshape(-1, n ** 3)
+
+
+class Manufactured:
+    """u = prod_d sin(pi x_d) on the unit cube (zero on the boundary; the smooth deformation keeps the cube),
+    f = -Laplace u = 3 pi^2 u."""
+
+    def __init__(self, p, cells, deform=0, eps=0.0):
+        self.mesh = OracleMesh(p, cells, quad=GAUSS, lower=(0., 0., 0.), upper=(1., 1., 1.), deform=deform, eps=eps)
+        sh = shape(p, GAUSS)
+        self.B = sh["B"]
+        self.l2g = _cell_dofs(self.mesh)
+        X = self.mesh.dof_coords()
+        self.xq = np.stack([_interp3(self.B, X[:, d][self.l2g]) for d in range(3)], axis=-1)   # [cells, n^3, 3]
+        self.jxw = self.mesh.jxw()
+
+    @staticmethod
+    def u(x):
+        return np.prod(np.sin(np.pi * x), axis=-1)
+
+    def rhs(self):
+        m = self.mesh
+        n = m.n
+        fq = 3.0 * np.pi ** 2 * self.u(self.xq) * self.jxw                      # [cells, n^3]
+        loc = np.einsum("ai,bj,ck,ncba->nkji", self.B, self.B, self.B, fq.reshape(-1, n, n, n)).reshape(-1, n ** 3)
+        b = np.zeros(m.n_dofs)
+        np.add.at(b, self.l2g, loc)
+        b[m.boundary_mask()] = 0.0
+        return b
+
+    def l2_error(self, uh):
+        uq = _interp3(self.B, np.asarray(uh)[self.l2g])
+        return float(np.sqrt(np.sum((uq - self.u(self.xq)) ** 2 * self.jxw)))
