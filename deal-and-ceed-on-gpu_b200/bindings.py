@@ -86,7 +86,6 @@ ABI = [
     ("bp5_operator_profile", C.c_int, [_vp, C.c_int]),
     ("bp5_operator_profile_result", C.c_int, [_vp, C.POINTER(C.c_int64), _dp]),
     ("bp5_operator_kernel_name", C.c_char_p, [_vp]),
-    ("bp5_operator_cg_kernel_name", C.c_char_p, [_vp]),
     ("bp5_context_launch_count", C.c_int64, [_vp]),
     ("bp5_vector_create", C.c_int, [_vp, C.c_int64, C.c_int64, C.POINTER(_vp)]),
     ("bp5_vector_create_like", C.c_int, [_vp, C.POINTER(_vp)]),
@@ -347,10 +346,6 @@ class PoissonOperator:
     @property
     def kernel_name(self):
         return lib().bp5_operator_kernel_name(self.h).decode()
-
-    @property
-    def cg_kernel_name(self):
-        return lib().bp5_operator_cg_kernel_name(self.h).decode()
 
     def close(self):
         if self.h:

@@ -167,8 +167,6 @@ int bp5_operator_destroy(bp5_operator_t op) {
   cudaFree(op->coords);
   cudaFree(op->constrained);
   cudaFree(op->cg_scalars);
-  cudaFree(op->fz_sync);
-  cudaFree(op->fz_partials);
   for (cudaEvent_t e : op->prof_events) cudaEventDestroy(e);
   bp5_vector_destroy(op->g);
   bp5_vector_destroy(op->d);
@@ -226,19 +224,6 @@ int bp5_operator_copy_constrained_values(bp5_operator_t op, bp5_vector_t dst, bp
   return apply_copy_constrained(op, dst->d, src->d);
 }
 
-static bool single_block(bp5_operator_t op) {
-  return op->prob.part_grid[0] == 1 && op->prob.part_grid[1] == 1 && op->prob.part_grid[2] == 1;
-}
-
-// vmult as ONE launch (fused.cuh): "dst = 0" runs a few cell rows ahead of the cell loop and the Dirichlet copy a
-// few rows behind it, both on lines that are still in L2 -- no separate fill pass, no read-modify-write fill of dst
-static int fused_vmult(bp5_operator_t op, double *dst, const double *src) {
-  FusedCall fc;
-  fc.umode = 4;      // FUSE_U_ZERO
-  fc.dmode = 1;      // FUSE_D_COPY
-  return apply_fused(op, dst, src, fc);
-}
-
 int bp5_operator_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op, "null operator");
@@ -252,7 +237,6 @@ int bp5_operator_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
   // contributions for the neighbouring owners.
   // "dst = 0" only has to reach the DoFs shared between cells: cell-interior
   // DoFs receive exactly one contribution and are stored by the kernel.
-  if (op->do_zero_out && single_block(op) && apply_fused_supported(op)) return fused_vmult(op, dst->d, src->d);
   if (op->do_zero_out && (rc = apply_zero_skeleton(op, dst->d))) return rc;
   if ((rc = apply_cell_loop(op, dst->d, src->d, /*overwrite_interior=*/op->do_zero_out))) return rc;
   return apply_copy_constrained(op, dst->d, src->d);
@@ -264,7 +248,6 @@ int bp5_operator_vmult_ptr(bp5_operator_t op, double *dst, const double *src, in
   BP5_REQUIRE(op && dst && src && dst != src, "bad argument");
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   int rc;
-  if (zero_dst && single_block(op) && apply_fused_supported(op)) return fused_vmult(op, dst, src);
   if (zero_dst && (rc = apply_zero_skeleton(op, dst))) return rc;
   if ((rc = apply_cell_loop(op, dst, src, zero_dst != 0))) return rc;
   return apply_copy_constrained(op, dst, src);
@@ -365,18 +348,6 @@ int bp5_operator_profile_result(bp5_operator_t op, int64_t *launches, double *to
 }
 
 const char *bp5_operator_kernel_name(bp5_operator_t op) { return op ? op->kernel_name.c_str() : ""; }
-const char *bp5_operator_cg_kernel_name(bp5_operator_t op) {
-  if (!op) return "";
-  if (!apply_fused_supported(op)) return op->kernel_name.c_str();
-  if (op->cg_kernel_name.empty()) {
-    char name[200];
-    snprintf(name, sizeof(name), "bp5_fused_kernel<p=%d,%s,%s,cells_per_tile=%d,update+cells+dots per launch>", op->p,
-             op->prob.quadrature == BP5_QUAD_GLL ? "gll-collocation" : "gauss",
-             op->prob.operator_kind == BP5_OP_HELMHOLTZ ? "helmholtz" : "poisson", op->cells_per_tile);
-    op->cg_kernel_name = name;
-  }
-  return op->cg_kernel_name.c_str();
-}
 
 // ------------------------------------------------------------------- vector
 int bp5_vector_create(bp5_context_t ctx, int64_t n_owned, int64_t n_ghost, bp5_vector_t *out) {

@@ -21,7 +21,6 @@
 //    iteration >= 3 and returns a wrong x (SURVEY.md finding 4).  Residual
 //    history and iteration count are identical either way.
 #include "apply.cuh"
-#include "cg_state.cuh"
 #include "common.h"
 
 namespace bp5 {
@@ -30,6 +29,16 @@ constexpr int kCgBlocks = 592;
 constexpr int kCgThreads = 256;
 
 constexpr int kUpdatePartialCap = 4096;     // >= grid of the update kernel (sm_count * 16)
+
+struct CgState {
+  double alpha, beta, alpha_old, beta_old;
+  double res, tol, gh;
+  int it;          // iterations completed == SolverControl::last_step()
+  int state;       // 0 iterate, 1 success, 2 failure (max its / nan), 3 divide by zero
+  int max_its, control;
+  unsigned ticket;
+  int history_len;
+};
 
 // device scratch of one solve: [CgState | dots partials | cell-kernel p.v partials | Dirichlet correction
 // partials | update-kernel r.r partials | residual history]
@@ -82,6 +91,14 @@ __device__ __forceinline__ void block_sum_k(double (&v)[K], double *sh /*[K*32]*
   __syncthreads();
 }
 
+// SolverControl::check / IterationNumberControl::check [UPSTREAM]
+__device__ __forceinline__ int control_check(int control, int step, int max_its, double value, double tol) {
+  if (control == BP5_CONTROL_ITERATION_NUMBER && step >= max_its) return 1;
+  if (value <= tol) return 1;
+  if (step >= max_its || isnan(value)) return 2;
+  return 0;
+}
+
 // ---------------------------------------------------------------- merged CG
 // MODE 0: update_a0 (solver.h:48-72)  1: update_a<false> (:74-104)  3: update_a1 (:106-140)
 // Fused here: r.r (and r.Dr) of the residual this kernel WRITES -- two of the seven sums of update_b
@@ -119,6 +136,29 @@ __global__ void __launch_bounds__(256) cg_update_kernel(const CgState *__restric
   }
   block_sum_k<2>(s, sh);
   if (threadIdx.x == 0) { rr[2 * blockIdx.x] = s[0]; rr[2 * blockIdx.x + 1] = s[1]; }
+}
+
+// scalar recurrences of one iteration from the seven (globally summed) dot products
+// (solver.h:497-533); one thread
+__device__ __forceinline__ void cg_scalar_step(CgState *st, const double (&rr)[7], double *history) {
+  const int it = st->it + 1;
+  st->alpha_old = st->alpha;
+  st->beta_old = st->beta;
+  st->it = it;
+  if (rr[0] == 0.0) { st->state = 3; return; }                 // ExcDivideByZero, solver.h:501
+  const double alpha = rr[6] / rr[0];                         // solver.h:502
+  // solver.h:504-505; finite negatives are clamped at 0 (deviation): at exact convergence the
+  // three-term expression can round slightly negative and the unguarded sqrt would report NaN.
+  // A NaN expression (overflow, indefinite operator, inf in diag) must stay NaN so that the
+  // stopping test fails like the reference's (fmax(0, NaN) would turn it into "converged").
+  const double res_sq = rr[3] + 2 * alpha * rr[2] + alpha * alpha * rr[1];
+  const double res = (res_sq < 0.0) ? 0.0 : sqrt(res_sq);
+  st->alpha = alpha;
+  st->res = res;
+  if (history && it < st->history_len) history[it] = res;
+  const int conv = control_check(st->control, it, st->max_its, res, st->tol);
+  if (conv != 0) { st->state = conv; return; }
+  st->beta = alpha * (rr[4] + alpha * rr[5]) / rr[6];         // solver.h:533
 }
 
 // partitioned meshes: the sums come back from an allreduce over the blocks
@@ -468,18 +508,8 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
   BP5_CUDA(cudaMemcpyAsync(st, &init, sizeof(CgState), cudaMemcpyHostToDevice, s));
 
   op->skip_flag = &st->state;
-  // One launch per iteration when the fused kernel applies (stored metric): update, cell loop, Dirichlet rows,
-  // all seven sums and the scalar recurrences (fused.cuh).  BP5_NO_FUSE=1 keeps the separate kernels below.
-  const bool fused = variant == BP5_CG_MERGED && apply_fused_supported(op);
   auto enqueue = [&](int cur) -> int {
     int rc = BP5_OK;
-    if (fused) {
-      FusedCall fc;
-      fc.umode = cur == 1 ? 0 : (cur % 2 == 0 ? 1 : 3);      // FUSE_U_CG0 / CG1 / CG3
-      fc.dmode = 0;                                          // FUSE_D_CG
-      fc.r = g; fc.x = x->d; fc.diag = diag; fc.state = st; fc.history = hist_dev;
-      return apply_fused(op, h, d, fc);
-    }
     if (variant == BP5_CG_MERGED) {
       // 1) update region (solver.h:413-448), with the parity-correct x update
       //    (+ r.r, r.Dr of the new residual as per-block partials)
@@ -527,7 +557,6 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
     return BP5_ERR_CUDA;
   }
   BP5_CHECK_LAUNCH();
-  if (fused && (rc = apply_fused_check(op))) return rc;
   if (history && hist_len > 1) {
     const int cnt = std::min(hist_len, fin.it + 1) - 1;
     if (cnt > 0) BP5_CUDA(cudaMemcpy(history + 1, hist_dev + 1, sizeof(double) * cnt, cudaMemcpyDeviceToHost));

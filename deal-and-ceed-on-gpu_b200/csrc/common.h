@@ -121,7 +121,7 @@ struct bp5_operator_s {
   int *constrained = nullptr;   // local owned indices of Dirichlet dofs
   int64_t n_constrained = 0;
   bool do_zero_out = true;
-  std::string kernel_name, cg_kernel_name;
+  std::string kernel_name;
   // CG work vectors (allocated on first solve)
   bp5_vector_t g = nullptr, d = nullptr, h = nullptr;
   bp5_vector_t xh = nullptr, bh = nullptr;  // device staging of bp5_cg_solve_host
@@ -138,10 +138,6 @@ struct bp5_operator_s {
   void *peer = nullptr;          // peer-memory transport state (peer.cu), or null
   bool peer_connected = false;
   const int *skip_flag = nullptr; // device word: when non-zero the cell loop is a no-op (CG converged)
-  // fused per-iteration kernel (fused.cuh): barrier counters / error latch and per-CTA partial sums
-  unsigned *fz_sync = nullptr;
-  double *fz_partials = nullptr;
-  int fz_partials_cap = 0;        // CTAs the partial buffer holds
 };
 
 namespace bp5 {
@@ -164,19 +160,6 @@ int apply_cell_loop_otf(bp5_operator_t op, double *dst, const double *src, int m
 int apply_copy_constrained_dot(bp5_operator_t op, double *dst, const double *src, double *partials);
 int apply_zero_skeleton(bp5_operator_t op, double *dst);
 int apply_copy_constrained(bp5_operator_t op, double *dst, const double *src);
-// fused.cu: one launch = one merged-CG iteration (umode FUSE_U_CG*, see fused.cuh) or one vmult with dst = 0
-// and the Dirichlet copy folded in (FUSE_U_ZERO).  Interior tiles and non-shell rows of the block.
-struct FusedCall {
-  int umode = 0, dmode = 0;
-  double *r = nullptr, *x = nullptr;        // CG residual / solution
-  const double *diag = nullptr;
-  void *state = nullptr;                    // CgState*
-  double *history = nullptr;
-  double *sums_out = nullptr;               // partitioned blocks: local sums for the all-rank sum
-};
-bool apply_fused_supported(bp5_operator_t op);
-int apply_fused(bp5_operator_t op, double *dst, const double *src, const FusedCall &call);
-int apply_fused_check(bp5_operator_t op);   // after a synchronised solve: did a grid barrier time out?
 // vector.cu
 int vec_fill(bp5_context_t ctx, double *d, int64_t n, double v);
 int vec_axpy(bp5_context_t ctx, double *y, double s, double a, const double *x, int64_t n, int mode);

@@ -39,6 +39,7 @@
 #include <cstdint>
 
 #include "common.h"
+#include "fused.cuh"
 #include "smem_layout.h"
 
 namespace bp5 {
@@ -107,6 +108,7 @@ struct ApplyParams {
   int sy, sz;             // affine strides of the owned box
   const int *skip;        // optional device flag: non-zero => nothing to do (CG already converged)
   double *dot_partials;   // OVERWRITE == 2: [gridDim.x] per-CTA parts of src . (A src), summed by the CG dots kernel
+  FusedParams fz;         // FUSED kernels only (fused.cuh)
   KernelTables<N> tab;
 };
 
@@ -159,6 +161,27 @@ __device__ __forceinline__ double ld_stream(const double *p, uint64_t policy) {
   return v;
 }
 
+// Plain (weak, coherent) load that does not allocate in L1: for data written by another kernel that runs
+// concurrently and handed over through acquire / release signals (fused.cuh).  The read-only path (__ldg) is not
+// allowed there; a .cg / strong load would be, but compiles to LDG.STRONG.GPU, which measured slower.
+__device__ __forceinline__ double ld_weak_no_l1(const double *p) {
+  double v;
+#ifdef BP5_TRY_NOALLOC
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+#else
+  // weak load, cached in L1 like any other: the acquire of the hand-over (fz_wait) invalidates the SM's L1
+  // (CCTL.IVALL) before any value written since can be read -- that is how the memory model's guarantee for weak
+  // loads after an acquire is implemented.  L1-bypassing forms (.cg, L1::no_allocate) measured 1 ms slower.
+  asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p));
+#endif
+  return v;
+}
+// fire-and-forget fp64 reduction.  atomicAdd() with an unused result normally compiles to RED as well, but in a
+// kernel that contains fences ptxas keeps the returning form (ATOMG ... RZ), which measured slower.
+__device__ __forceinline__ void red_add_f64(double *p, double v) {
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
 // Local dof indices of the N points of one thread's z-column in a cell with
 // descriptor `base` (>= 0: affine, < 0: explicit table slot, kNoCell: no cell,
 // indices are 0 and the values are never used).  Branch-free on the common path
@@ -178,13 +201,15 @@ __device__ __forceinline__ void column_indices(int (&idx)[N], const int *__restr
   }
 }
 
-template <int N>
+// COHERENT: the values were written by other CTAs of the same launch (fused kernel): L2 loads, not the
+// non-coherent L1 path
+template <int N, bool COHERENT = false>
 __device__ __forceinline__ void gather_column(double (&u)[N], const double *__restrict__ src,
                                               const int *__restrict__ l2g_irr, int base, int ab_off, int ab_irr, int sz) {
   int idx[N];
   column_indices<N>(idx, l2g_irr, base, ab_off, ab_irr, sz);
 #pragma unroll
-  for (int k = 0; k < N; ++k) u[k] = __ldg(src + idx[k]);
+  for (int k = 0; k < N; ++k) u[k] = COHERENT ? ld_weak_no_l1(src + idx[k]) : __ldg(src + idx[k]);
 }
 
 // Rows of the outer loop handled per (rolled) iteration: U independent DFMA
@@ -299,8 +324,15 @@ struct ApplyCfg {
 // (bp5/solver.h:231,303) without reading either vector again;
 // 1 = cell-interior DoFs are stored, not added (dst's skeleton must be
 // zero on entry, its interior may hold anything); 0 = dst += A src everywhere.
-template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0>
+// FUSED: one CG iteration / one vmult in this launch (fused.cuh): update rows ahead of the cells, finish rows behind
+template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0, int FUSED = 0>
 __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
+  static_assert(!FUSED || (OVERWRITE == 2 && MLOAD == 0), "the fused kernel builds on the overwrite + dot product variant");
+#ifdef BP5_TRY_LDG
+  constexpr bool kCoherent = false;
+#else
+  constexpr bool kCoherent = FUSED != 0;   // gathered values are written by the streaming kernel while this one runs
+#endif
   using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = Cfg::N, N2 = Cfg::N2, N3 = Cfg::N3, PLANES = 6 + HELM;
   constexpr int RC = BP5_ROW_CHUNK(N, QUAD, OVERWRITE);     // rows per rolled iteration of a line contraction
@@ -314,6 +346,9 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   uint64_t *bar = reinterpret_cast<uint64_t *>(S2 + CPT * L::B_CS);
 
   if (prm.skip != nullptr && *prm.skip != 0) return;
+#ifdef BP5_FZ_DEBUG
+  const long long dbg_kernel_t0 = clock64();
+#endif
   const int tid = threadIdx.x;
   const bool active = tid < Cfg::ACTIVE;
   const int c = active ? tid / N2 : 0;      // cell within the tile
@@ -371,6 +406,19 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
     if (active && tile0 < n_tiles) load_metric(tile0);
   }
 
+  // fused iteration (fused.cuh): the cell CTAs meet the streaming kernel only through the counter rings
+  [[maybe_unused]] const FusedParams &fz = prm.fz;
+  [[maybe_unused]] unsigned *u_ring = nullptr, *c_ring = nullptr, *fz_err = nullptr;
+  [[maybe_unused]] int fz_S = 1, fz_it = 0, fz_n_it = 0;
+  [[maybe_unused]] double dot_acc = 0.0;
+  auto cell_sync = [&]() { __syncthreads(); };
+  {
+  if constexpr (FUSED) {
+    u_ring = fz.sync; c_ring = fz.sync + kFzRing; fz_err = fz.sync + kFzErr;
+    fz_S = fz.tiles_per_step; fz_n_it = fz.n_steps * fz_S;
+    if ((tid & 31) == 0 && !(fz.debug & 8)) fz_wait(u_ring, 0, fz.n_stream_ctas, fz_err);   // U(0) complete: the first gather may start
+    __syncwarp();
+  }
   // software pipeline of the gather: cell descriptors two tiles ahead, values one tile ahead
   int base_cur = (active && tile0 < n_tiles) ? __ldg(cell_base + tile0 * CPT + c) : kNoCell;
   int base_nxt = (active && tile0 + tstride < n_tiles) ? __ldg(cell_base + (tile0 + tstride) * CPT + c) : kNoCell;
@@ -379,17 +427,17 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
 #endif
   constexpr bool kPrefetch = BP5_PREFETCH_GATHER(P) != 0;   // values of the next tile in registers one tile ahead
   [[maybe_unused]] double u_nxt[N];
-  if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
+  if constexpr (kPrefetch) gather_column<N, kCoherent>(u_nxt, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
 
   uint32_t parity = 0;
-  [[maybe_unused]] double dot_acc = 0.0;
-  for (long long tile = tile0; tile < n_tiles; tile += tstride) {
+  // one tile: gather (prefetched), contractions, quadrature-point phase, transposed contractions, scatter
+  auto process_tile = [&](const long long tile) {
     double u[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) u[k] = kPrefetch ? u_nxt[k] : 0.0;
-    if constexpr (!kPrefetch) gather_column<N>(u, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
+    if constexpr (!kPrefetch) gather_column<N, kCoherent>(u, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
     // issue next tile's gather and the descriptor load of the tile after it
-    if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_nxt, ab_off, ab_irr, sz);
+    if constexpr (kPrefetch) gather_column<N, kCoherent>(u_nxt, src, l2g_irr, base_nxt, ab_off, ab_irr, sz);
     const int base_n2 =
         (active && tile + 2 * tstride < n_tiles) ? __ldg(cell_base + (tile + 2 * tstride) * CPT + c) : kNoCell;
 
@@ -411,7 +459,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
           for (int k = 0; k < N; ++k) mv[k] = u[k];
         }
       }
-      __syncthreads();
+      cell_sync();
       // (2) x-line (j=a, k=b) and y-line (i=a, k=b): derivative along the line
       if (active) {
         double v[N];
@@ -422,12 +470,12 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
         contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, v);
       }
-      __syncthreads();
+      cell_sync();
     } else {
       // ---------------- Gauss quadrature: interpolate to the q-points first
       // (1) home (i=a, j=b): z-interpolation
       if (active) contract_to_smem<N, RC, 1>(s0 + hA, A2, Bz, u);
-      __syncthreads();
+      cell_sync();
       // (2) x-line (j=a, qz=b): x-interpolation in place
       if (active) {
         double v[N];
@@ -435,7 +483,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
         contract_to_smem<N, RC, 1>(s0 + xA, 1, Bx, v);
       }
-      __syncthreads();
+      cell_sync();
       // (3) y-line (qx=a, qz=b): y-interpolation (values at q-points), then d/dy
       if (active) {
         double v[N], w[N];
@@ -446,7 +494,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int q = 0; q < N; ++q) s0[yA + q * A1] = w[q];
         contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, w);
       }
-      __syncthreads();
+      cell_sync();
       // (4) x-line (qy=a, qz=b): d/dx ; home (qx=a, qy=b): d/dz in registers
       if (active) {
         double v[N];
@@ -461,7 +509,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
           for (int k = 0; k < N; ++k) mv[k] = v[k];
         }
       }
-      __syncthreads();
+      cell_sync();
     }
 
     // ---------------- quadrature-point phase (home): g <- G g  (bp5/step-64.cu:160-188)
@@ -494,7 +542,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         }
       }
     }
-    __syncthreads();
+    cell_sync();
     if constexpr (MLOAD == 0) {
       // the metric buffer is free: fetch the next tile's metric behind the remaining work
       if (tid == 0 && tile + tstride < n_tiles) {
@@ -521,7 +569,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int j = 0; j < N; ++j) v[j] = s2[yB + j * B1];
         contract_to_smem<N, RC, -1>(s2 + yB, B1, DTy, v);
       }
-      __syncthreads();
+      cell_sync();
       // (5) home: z-transpose in registers, sum the three directions, scatter
       if (do_scatter) {
         double o[N];
@@ -532,7 +580,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
           if constexpr (HELM) s += mv[k];
           double *dp = dst + idx[k];
           if (col_interior && k > 0 && k < P) *dp = s;     // multiplicity 1: plain store
-          else atomicAdd(dp, s);                           // skeleton: red.global.add.f64
+          else red_add_f64(dp, s);                         // skeleton: red.global.add.f64
         }
       }
     } else {
@@ -551,7 +599,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
           contract_to_smem<N, RC, -1>(s0 + hA, A2, DTz, t);
         }
       }
-      __syncthreads();
+      cell_sync();
       // (6b) y-line (qx=a, qz=b): D^T along y, add x and z parts, then B^T along y
       if (active) {
         double v[N], y[N];
@@ -562,7 +610,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int q = 0; q < N; ++q) y[q] += s1[yA + q * A1] + s0[yA + q * A1];
         contract_to_smem<N, RC, 1>(s0 + yA, A1, BTy, y);
       }
-      __syncthreads();
+      cell_sync();
       // (7) x-line (j=a, qz=b): B^T along x in place
       if (active) {
         double v[N];
@@ -570,7 +618,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int q = 0; q < N; ++q) v[q] = s0[xA + q];
         contract_to_smem<N, RC, 1>(s0 + xA, 1, BTx, v);
       }
-      __syncthreads();
+      cell_sync();
       // (8) home (i=a, j=b): B^T along z in registers, scatter
       if (do_scatter) {
         double v[N], o[N];
@@ -581,13 +629,41 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int k = 0; k < N; ++k) {
           double *dp = dst + idx[k];
           if (col_interior && k > 0 && k < P) *dp = o[k];
-          else atomicAdd(dp, o[k]);
+          else red_add_f64(dp, o[k]);
         }
       }
     }
     base_cur = base_nxt;
     base_nxt = base_n2;
+  };
+  if constexpr (!FUSED) {
+    for (long long tile = tile0; tile < n_tiles; tile += tstride) process_tile(tile);
+  } else {
+    // macro steps of fz_S tiles (fused.cuh); the tile loop inside a step is the plain one
+    long long tile = tile0;
+#pragma unroll 1
+    for (int K = 0; K < fz.n_steps; ++K) {
+      // this step's tiles prefetch one tile into the next step, so the rows of step K + 1 must be updated
+      // everywhere (the streaming kernel signalled that ua - 1 >= 1 steps ago)
+#ifndef BP5_TRY_NOHOOK
+      // every warp checks the signal itself (normally up long ago): no CTA barrier
+      { FZ_DBG_T0(); if ((tid & 31) == 0 && !(fz.debug & 8)) { fz_wait(u_ring, K + 1, fz.n_stream_ctas, fz_err); if (tid == 0) FZ_DBG_ADD(fz, 0); } }
+      __syncwarp();
+#endif
+#pragma unroll 1
+      for (int s = 0; s < fz_S; ++s, tile += tstride)
+        if (tile < n_tiles) process_tile(tile);
+#ifndef BP5_TRY_NOHOOK2
+      // this warp's share of the macro step's scatter is out: every warp signals for itself (the streaming
+      // kernel waits for n_cell_ctas x warps arrivals), again without a CTA barrier
+      __syncwarp();
+      { FZ_DBG_T0(); if ((tid & 31) == 0) {
+        if (fz.debug & 4) atomicAdd(c_ring + (K & (kFzRing - 1)), 1u); else fz_signal(c_ring, K);
+        if (tid == 0) FZ_DBG_ADD(fz, 1); } }
+#endif
+    }
   }
+  }   // cell role
   if constexpr (OVERWRITE == 2) {
     // CTA-wide sum in a fixed order (warp shuffles, then warp 0 over the per-warp sums)
     __syncthreads();
@@ -600,8 +676,18 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
       v = tid < Cfg::NT / 32 ? S0[tid] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (tid == 0) prm.dot_partials[blockIdx.x] = v;
+      if constexpr (!FUSED) {
+        if (tid == 0) prm.dot_partials[blockIdx.x] = v;
+      } else {
+        // the cell phase's p.(A p); the streaming warp stored the sums of the U / D phases
+        if (tid == 0) fz.partials[blockIdx.x * kFusedPartials + kFzSlotC] = v;
+      }
     }
+#ifdef BP5_FZ_DEBUG
+    if constexpr (FUSED) if (blockIdx.x == 0 && tid == 0)
+      atomicAdd(reinterpret_cast<unsigned long long *>(prm.fz.sync + kFzDbg) + 6, (unsigned long long)(clock64() - dbg_kernel_t0));
+#endif
+    if constexpr (FUSED) fz_finalize(fz);
   }
 }
 
@@ -609,6 +695,17 @@ template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0>
 __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
     bp5_apply_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
   bp5_apply_body<P, QUAD, HELM, CPT, OVERWRITE, MLOAD>(prm);
+}
+
+// the cell half of a fused CG iteration / vmult (fused.cuh): runs concurrently with bp5_stream_kernel
+template <int P, int QUAD, int HELM, int CPT>
+__global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, 0>::NT), P)
+    bp5_fused_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
+#ifdef BP5_TRY_PLAIN
+  bp5_apply_body<P, QUAD, HELM, CPT, 2, 0, 0>(prm);
+#else
+  bp5_apply_body<P, QUAD, HELM, CPT, 2, 0, 1>(prm);
+#endif
 }
 
 }  // namespace bp5

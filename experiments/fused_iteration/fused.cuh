@@ -9,22 +9,26 @@
 // Separate kernels move 12 vector passes per iteration through HBM (h is zero-filled, read-modify-written and
 // re-read; p and r are re-read): here it is 7.
 //
-// Warp specialisation.  Every CTA has its cell warps (the n^2-threads-per-cell contraction code of apply.cuh,
-// unchanged) and ONE extra streaming warp that does nothing but U and D.  The two never meet at a CTA barrier
-// (the cell warps use a named barrier): they talk through counters in global memory, so the streaming latency
-// is hidden behind the contractions of the same SM instead of stalling them.
+// Two kernels, running concurrently on two streams of the same device.  The cell kernel is the contraction code
+// of apply.cuh with its registers and shared memory untouched (bp5_fused_kernel: 2-4 CTAs per SM); the streaming
+// kernel (bp5_stream_kernel: one small CTA per SM, 8 warps, ~60 registers, no shared memory) does nothing but U
+// and D.  They never share a CTA or a barrier: they talk through counters in global memory, so the streaming
+// latency hides behind the contractions of the same SM instead of stalling them.  (A first version put a
+// streaming warp into every cell CTA: one register budget and one instruction stream for both roles made the
+// cell path 1.5x and the streaming path 10x slower -- profiles/r2_notes.md.)
 //
 // Schedule.  The cell tiles of the launch are dealt round-robin to the persistent CTAs as before; S consecutive
 // rounds form a macro step.  In the lexicographic processing order the DoFs a cell touches FIRST are those of its
 // upper-inclusive box and the DoFs it touches LAST those of its lower-inclusive box, so (all x at once)
 //   U(K) = the DoF rows first touched by the cell rows that macro step K reaches,
 //   D(K) = the DoF rows last touched by the cell rows that are complete after macro step K.
-// Streaming warp, step K:  U(K + UA), signal; wait until all cell groups finished C(K - DL), D(K - DL).
-// Cell warps, step K:      wait until all streaming warps finished U(K + 1) (the gather prefetch reaches one
+// Streaming CTAs, tick t:  U(t), signal; wait until all cell CTAs finished C(t - UA - DL), then D(t - UA - DL).
+// Cell CTAs, step K:       wait until all streaming CTAs finished U(K + 1) (the gather prefetch reaches one
 //                          tile into the next step); tiles of step K; signal.
-// Signals are arrivals on a ring of monotone counters (slot = step mod 8, target = G per lap): a CTA can only
-// run UA + DL <= 8 steps ahead of the slowest one, so laps never mix.  All CTAs must be co-resident (grid <=
-// occupancy x SMs); a wait that cannot be satisfied gives up after ~4 s and latches an error word.
+// Signals are arrivals on a ring of monotone counters (slot = step mod 8, target = #CTAs of the signalling
+// kernel per lap): nobody can run more than UA + DL <= 8 steps ahead of the slowest CTA, so laps never mix.
+// All CTAs of both kernels must be co-resident (the host sizes the grids for that); a wait that cannot be
+// satisfied gives up after ~4 s and latches an error word.
 // The live window of r, p, h is ~(UA + DL + 1) macro steps of rows plus one DoF plane per cell layer -- tens of
 // MB, inside the 126 MB L2; the read-once streams (metric via TMA, U's loads, D's loads) carry L2::evict_first.
 //
@@ -51,7 +55,7 @@ constexpr int kFusedSyncWords = 2 * kFzRing + 2 + 16; // [0,8) update arrivals, 
 //   U: 0 r.r  1 r.Dr      D: 2 correction of p.h on Dirichlet rows  3 h.h  4 r.h  5 r.Dh  6 h.Dh      C: 7 p.(A p)
 constexpr int kFusedPartials = 8;
 constexpr int kFzSlotU = 0, kFzSlotD = 2, kFzSlotC = 7;
-constexpr int kFzStreamThreads = 32;             // one streaming warp per CTA
+constexpr int kFzStreamThreads = 192;            // streaming kernel: 6 warps per CTA, one CTA per SM
 
 // -DBP5_FZ_DEBUG: tuning builds.  CTA 0 accumulates clock64 ticks per activity in sync[kFzDbg + i]
 // (0 cell-side waits, 1 cell-side signal, 2 stream waits, 3 stream U, 4 stream D, 5 stream signals, 6 whole kernel)
@@ -76,6 +80,9 @@ struct FusedParams {
   int tiles_per_step;         // S
   int n_steps;                // macro steps of this launch
   int ua, dl;                 // update look-ahead / finish lag in macro steps (ua >= 2, dl >= 1, ua + dl <= kFzRing)
+  int n_cell_ctas, n_stream_ctas;   // grids of the two kernels
+  int n_cell_arrivals;        // cell-side arrivals per macro step: n_cell_ctas x warps per cell CTA
+  double *pvec, *hvec;        // the streaming kernel's view of p (cell kernel: src) and h (dst)
   int debug;                  // tuning builds only
   int od0, od1, od2, p;
   int ncx, nry, nrz;          // interior cells per row, interior cell rows per layer, interior layers
@@ -94,16 +101,17 @@ __device__ __forceinline__ unsigned fz_ld_acquire(const unsigned *p) {
 // arrival of this CTA's group (cell warps or streaming warp) for macro step `step`; called by ONE thread after a
 // barrier over the group (fences are cumulative: the group's earlier stores / reductions are ordered before it)
 __device__ __forceinline__ void fz_signal(unsigned *ring, int step) {
-  __threadfence();
-  atomicAdd(ring + (step & (kFzRing - 1)), 1u);
+  // release at gpu scope (MEMBAR.ALL.GPU + RED); __threadfence() would be the sequentially consistent fence
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ring + (step & (kFzRing - 1))) : "memory");
 }
 
 // one thread: wait until every CTA's group has arrived for `step`.  A CTA that never arrives (launch larger than
 // the resident capacity, a crashed CTA) must not hang the GPU: after ~4 s the wait gives up and latches the error
 // word; the host reports it when the solve ends.
-__device__ __forceinline__ void fz_wait(const unsigned *ring, int step, unsigned *err) {
+__device__ __forceinline__ void fz_wait(const unsigned *ring, int step, int n_arrivals, unsigned *err) {
   const unsigned *ctr = ring + (step & (kFzRing - 1));
-  const unsigned target = (unsigned)(step / kFzRing + 1) * gridDim.x;
+  const unsigned target = (unsigned)(step / kFzRing + 1) * (unsigned)n_arrivals;
   if (fz_ld_acquire(ctr) >= target) return;
   if (*reinterpret_cast<volatile unsigned *>(err) != 0) return;
   unsigned long long t0;
@@ -128,6 +136,11 @@ __device__ __forceinline__ double fz_ld_stream(const double *p, uint64_t pol) {
   double v;
   asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
   return v;
+}
+__device__ __forceinline__ uint64_t make_evict_first_policy_fz() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
 __device__ __forceinline__ void fz_st_stream(double *p, double v, uint64_t pol) {
   asm volatile("st.global.cg.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
@@ -174,10 +187,10 @@ struct FzCursor {
     xlo = xlo_; xhi = xhi_; jlo = jlo_; jend = jlo_ + nj; od0 = fz.od0; od1 = fz.od1; klo = klo_;
     const int nxc = (xhi_ - xlo_ + 32) >> 5;
     const int n_items = nk * nj * nxc;
-    const int G = (int)gridDim.x;
+    const int G = (int)gridDim.x * (kFzStreamThreads / 32);      // agents = warps of the streaming kernel
     const int per = (n_items + G - 1) / G;
-    // rotate the dealing with the band so that the same CTAs do not always get the short block
-    const int me = (int)((blockIdx.x + (unsigned)rot * 61u) % (unsigned)G);
+    // rotate the dealing with the band so that the same warps do not always get the short block
+    const int me = (int)((blockIdx.x * (kFzStreamThreads / 32) + (threadIdx.x >> 5) + (unsigned)rot * 61u) % (unsigned)G);
     const int first = me * per;
     rem = n_items - first;
     if (rem > per) rem = per;
@@ -202,47 +215,26 @@ struct FzCursor {
 };
 
 #ifndef BP5_FZ_BATCH
-#define BP5_FZ_BATCH 8    // items per stage of the streaming warp (memory-level parallelism without occupancy)
+#define BP5_FZ_BATCH 4    // items in flight per warp of the streaming kernel (x 8 warps per SM)
 #endif
 constexpr int kFzBatch = BP5_FZ_BATCH;
-constexpr int kFzStageVecs = 5;                                              // r, h, p, x, diag
-constexpr int kFzStageDoubles = (kFzStageVecs * kFzBatch + kFzBatch / 2) * 32;   // one stage: [vec][item][lane] + int idx[item][lane]
-constexpr size_t kFzStageBytes = 2 * (size_t)kFzStageDoubles * sizeof(double);  // double-buffered
 
-// 8-byte asynchronous copy global -> shared (LDGSTS): the update phase keeps two stages of kFzBatch items x up to
-// five vectors in flight per warp without holding a single register for them.  Through L1 (.ca is the only
-// 8-byte form): safe for what U reads -- r, h, p, x, diag of a DoF are not written by anybody else in this launch
-// before this thread reads them, and L1 starts every launch empty.
-__device__ __forceinline__ void fz_cp_async8(double *smem_dst, const double *gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
-               : "memory");
-}
-__device__ __forceinline__ void fz_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void fz_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// The loops below are deliberately ROLLED (#pragma unroll 1) and every phase has a single call site: the streaming
-// warp's code must stay a few KB.  A first version with unrolled register batches compiled to 140 KB of SASS
-// (the cell loop is 18 KB), thrashed the instruction cache and made both roles 2-3x slower.
-
-// U(K): see the header comment.  acc[0] += r.r, acc[1] += r.Dr of the residual written here.  One warp;
-// `stage` = this warp's 2 x kFzStageDoubles staging buffer in shared memory.
-static __device__ __noinline__ void fz_update_phase(const FusedParams &fz, double *__restrict__ pvec, double *__restrict__ hvec,
-                                             int K, uint64_t pol, double *stage, double (&acc)[2]) {
+// U(K): see the header comment.  acc[0] += r.r, acc[1] += r.Dr of the residual written here.  Called by every
+// warp of the streaming kernel; MODE = FUSE_U_*.
+template <int MODE, bool DIAG>
+static __device__ __forceinline__ void fz_update_phase(const FusedParams &fz, int K, uint64_t pol, double (&acc)[2]) {
   const int ra = fz_rows_through<true>(fz, K - 1), rb = fz_rows_through<true>(fz, K);
   if (rb <= ra) return;
   const int lane = threadIdx.x & 31;
-  const int umode = fz.umode;
   double alpha = 0.0, beta = 0.0, apa = 0.0, aob = 0.0;
-  if (umode == FUSE_U_CG1 || umode == FUSE_U_CG3) { alpha = fz.st->alpha; beta = fz.st->beta; }
-  if (umode == FUSE_U_CG3) { aob = fz.st->alpha_old / fz.st->beta_old; apa = alpha + aob; }
-  double *__restrict__ rvec = fz.r, *__restrict__ xvec = fz.x;
+  if (MODE == FUSE_U_CG1 || MODE == FUSE_U_CG3) { alpha = fz.st->alpha; beta = fz.st->beta; }
+  if (MODE == FUSE_U_CG3) { aob = fz.st->alpha_old / fz.st->beta_old; apa = alpha + aob; }
+  double *__restrict__ rvec = fz.r, *__restrict__ xvec = fz.x, *__restrict__ pvec = fz.pvec, *__restrict__ hvec = fz.hvec;
   const double *__restrict__ diag = fz.diag;
-  const bool ld_r = umode != FUSE_U_ZERO, ld_hp = umode == FUSE_U_CG1 || umode == FUSE_U_CG3, ld_x = umode == FUSE_U_CG3;
+  constexpr bool ld_r = MODE != FUSE_U_ZERO, ld_hp = MODE == FUSE_U_CG1 || MODE == FUSE_U_CG3, ld_x = MODE == FUSE_U_CG3;
   const int xlo = fz.lo[0] ? fz.p : 0, xhi = fz.od0 - 1 - fz.hi[0];
   if (xhi < xlo) return;
   const int lz_a = ra / fz.nry, lz_b = (rb - 1) / fz.nry;
-  constexpr int VS = kFzBatch * 32;          // doubles per vector per stage
 #pragma unroll 1
   for (int lz = lz_a; lz <= lz_b; ++lz) {
     const int ja = (lz == lz_a) ? ra - lz * fz.nry : 0, jb = (lz == lz_b) ? (rb - 1) - lz * fz.nry : fz.nry - 1;
@@ -253,74 +245,56 @@ static __device__ __noinline__ void fz_update_phase(const FusedParams &fz, doubl
     if (nj <= 0 || nk <= 0) continue;
     FzCursor cur;
     cur.start(fz, klo, nk, jlo, nj, xlo, xhi, K + lz);
-    // software pipeline over stages of kFzBatch items: issue the copies of stage s+1, then consume stage s
-    int s = 0;
-    bool have = false;
 #pragma unroll 1
-    while (true) {
-      const bool more = cur.valid();
-      if (more) {
-        double *buf = stage + (have ? (s ^ 1) : s) * kFzStageDoubles + lane;
-        int *ibuf = reinterpret_cast<int *>(stage + (have ? (s ^ 1) : s) * kFzStageDoubles + kFzStageVecs * VS) + lane;
-#pragma unroll 1
-        for (int u = 0; u < kFzBatch; ++u) {
-          const int i = (cur.valid() && cur.x + lane <= xhi) ? cur.idx + lane : -1;
-          if (cur.valid()) cur.next();
-          ibuf[u * 32] = i;
-          if (i >= 0 && ld_r) {
-            double *slot = buf + u * 32;
-            fz_cp_async8(slot, rvec + i);
-            if (ld_hp) { fz_cp_async8(slot + VS, hvec + i); fz_cp_async8(slot + 2 * VS, pvec + i); }
-            if (ld_x) fz_cp_async8(slot + 3 * VS, xvec + i);
-            if (diag) fz_cp_async8(slot + 4 * VS, diag + i);
-          }
-        }
-        fz_cp_commit();
-      }
-      if (!have) {
-        if (!more) break;
-        have = true;
-        continue;                           // first stage issued: go and issue the second before consuming
-      }
-      if (more) fz_cp_wait<1>(); else fz_cp_wait<0>();
-      const double *buf = stage + s * kFzStageDoubles + lane;
-      const int *ibuf = reinterpret_cast<const int *>(stage + s * kFzStageDoubles + kFzStageVecs * VS) + lane;
-#pragma unroll 1
+    while (cur.valid()) {
+      int idx[kFzBatch];
+      double rv[kFzBatch], hv[kFzBatch], pv[kFzBatch], xv[kFzBatch], dv[kFzBatch];
+#pragma unroll
       for (int u = 0; u < kFzBatch; ++u) {
-        const int i = ibuf[u * 32];
+        idx[u] = (cur.valid() && cur.x + lane <= xhi) ? cur.idx + lane : -1;
+        if (cur.valid()) cur.next();
+      }
+#pragma unroll
+      for (int u = 0; u < kFzBatch; ++u) {
+        rv[u] = hv[u] = pv[u] = xv[u] = 0.0; dv[u] = 1.0;
+        if (ld_r && idx[u] >= 0) {
+          rv[u] = fz_ld_stream(rvec + idx[u], pol);
+          if (ld_hp) { hv[u] = fz_ld_stream(hvec + idx[u], pol); pv[u] = fz_ld_stream(pvec + idx[u], pol); }
+          if (ld_x) xv[u] = fz_ld_stream(xvec + idx[u], pol);
+          if (DIAG) dv[u] = fz_ld_stream(diag + idx[u], pol);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kFzBatch; ++u) {
+        const int i = idx[u];
         if (i < 0) continue;
         if (ld_r) {
-          const double *slot = buf + u * 32;
-          const double rv = slot[0], dv = diag ? slot[4 * VS] : 1.0;
-          double r_new = rv;
+          double r_new = rv[u];
           if (!ld_hp) {
-            __stcg(pvec + i, -dv * r_new);
+            __stcg(pvec + i, -dv[u] * r_new);
           } else {
-            const double hv = slot[VS], pv = slot[2 * VS];
-            r_new = rv + alpha * hv;
-            if (ld_x) fz_st_stream(xvec + i, slot[3 * VS] + (apa * pv + aob * dv * rv), pol);
+            r_new = rv[u] + alpha * hv[u];
+            if (ld_x) fz_st_stream(xvec + i, xv[u] + (apa * pv[u] + aob * dv[u] * rv[u]), pol);
             __stcg(rvec + i, r_new);
-            __stcg(pvec + i, beta * pv - dv * r_new);
+            __stcg(pvec + i, beta * pv[u] - dv[u] * r_new);
           }
           acc[0] += r_new * r_new;
-          if (diag) acc[1] += r_new * dv * r_new;
+          if (DIAG) acc[1] += r_new * dv[u] * r_new;
         }
         __stcg(hvec + i, 0.0);
       }
-      s ^= 1;
-      if (!more) break;
     }
   }
 }
 
-// D(K): see the header comment.  acc: 0 correction of p.h, 1 h.h, 2 r.h, 3 r.Dh, 4 h.Dh.  One warp.
-static __device__ __noinline__ void fz_finish_phase(const FusedParams &fz, const double *__restrict__ pvec,
-                                             double *__restrict__ hvec, int K, uint64_t pol, double (&acc)[5]) {
+// D(K): see the header comment.  acc: 0 correction of p.h, 1 h.h, 2 r.h, 3 r.Dh, 4 h.Dh.
+template <bool CG, bool DIAG>
+static __device__ __forceinline__ void fz_finish_phase(const FusedParams &fz, int K, uint64_t pol, double (&acc)[5]) {
   const int ra = fz_rows_through<false>(fz, K - 1), rb = fz_rows_through<false>(fz, K);
   if (rb <= ra) return;
   const int lane = threadIdx.x & 31;
-  const bool cg = fz.dmode == FUSE_D_CG;
-  const double *__restrict__ rvec = fz.r;
+  const double *__restrict__ rvec = fz.r, *__restrict__ pvec = fz.pvec;
+  double *__restrict__ hvec = fz.hvec;
   const double *__restrict__ diag = fz.diag;
   const int xlo = fz.lo[0] ? fz.p : 0, xhi = fz.od0 - 1 - fz.hi[0];
   if (xhi < xlo) return;
@@ -329,7 +303,6 @@ static __device__ __noinline__ void fz_finish_phase(const FusedParams &fz, const
   const int xd0 = fz.lo[0] ? -1 : 0, xd1 = fz.hi[0] ? -1 : fz.od0 - 1;
   const int jd0 = fz.lo[1] ? -1 : 0, jd1 = fz.hi[1] ? -1 : fz.od1 - 1;
   const int kd0 = fz.lo[2] ? -1 : 0, kd1 = fz.hi[2] ? -1 : fz.od2 - 1;
-  constexpr int DB = 4;                      // items per (unrolled) batch: loads of a batch are issued together
 #pragma unroll 1
   for (int lz = lz_a; lz <= lz_b; ++lz) {
     const int ja = (lz == lz_a) ? ra - lz * fz.nry : 0, jb = (lz == lz_b) ? (rb - 1) - lz * fz.nry : fz.nry - 1;
@@ -342,11 +315,11 @@ static __device__ __noinline__ void fz_finish_phase(const FusedParams &fz, const
     cur.start(fz, klo, nk, jlo, nj, xlo, xhi, K + lz);
 #pragma unroll 1
     while (cur.valid()) {
-      int idx[DB];
-      bool dir[DB];
-      double rv[DB], hv[DB], pv[DB], dv[DB];
+      int idx[kFzBatch];
+      bool dir[kFzBatch];
+      double rv[kFzBatch], hv[kFzBatch], pv[kFzBatch], dv[kFzBatch];
 #pragma unroll
-      for (int u = 0; u < DB; ++u) {
+      for (int u = 0; u < kFzBatch; ++u) {
         const int x = cur.x + lane;
         const bool ok = cur.valid() && x <= xhi;
         idx[u] = ok ? cur.idx + lane : -1;
@@ -354,19 +327,19 @@ static __device__ __noinline__ void fz_finish_phase(const FusedParams &fz, const
         if (cur.valid()) cur.next();
       }
 #pragma unroll
-      for (int u = 0; u < DB; ++u) {
+      for (int u = 0; u < kFzBatch; ++u) {
         rv[u] = hv[u] = pv[u] = 0.0; dv[u] = 1.0;
         if (idx[u] >= 0) {
-          if (cg) {
+          if (CG) {
             rv[u] = fz_ld_stream(rvec + idx[u], pol);
             hv[u] = fz_ld_stream(hvec + idx[u], pol);
-            if (diag) dv[u] = fz_ld_stream(diag + idx[u], pol);
+            if (DIAG) dv[u] = fz_ld_stream(diag + idx[u], pol);
           }
           if (dir[u]) pv[u] = __ldcg(pvec + idx[u]);
         }
       }
 #pragma unroll
-      for (int u = 0; u < DB; ++u) {
+      for (int u = 0; u < kFzBatch; ++u) {
         if (idx[u] < 0) continue;
         double vs = hv[u];
         if (dir[u]) {
@@ -375,72 +348,82 @@ static __device__ __noinline__ void fz_finish_phase(const FusedParams &fz, const
           vs = pv[u];
           __stcg(hvec + idx[u], vs);
         }
-        if (cg) {
+        if (CG) {
           acc[1] += vs * vs;
           acc[2] += rv[u] * vs;
-          if (diag) { const double dvs = dv[u] * vs; acc[3] += rv[u] * dvs; acc[4] += vs * dvs; }
+          if (DIAG) { const double dvs = dv[u] * vs; acc[3] += rv[u] * dvs; acc[4] += vs * dvs; }
         }
       }
     }
   }
 }
 
-// The streaming warp's whole life (one warp per CTA): U runs `ua` macro steps ahead of the cells, D `dl` behind.
-// Tick t: U(t), signal; then D(t - ua - dl) once every cell group has finished that step.
-static __device__ __noinline__ void fz_stream_role(const FusedParams &fz, double *pvec, double *hvec, uint64_t pol,
-                                            double *stage) {
+__device__ __forceinline__ void fz_finalize(const FusedParams &fz);
+
+// The streaming kernel: U runs `ua` macro steps ahead of the cells, D `dl` behind.
+// Tick t: U(t), signal; then D(t - ua - dl) once every cell CTA has finished that step.
+template <int UMODE, bool CG, bool DIAG>
+__global__ void __launch_bounds__(kFzStreamThreads, 4) bp5_stream_kernel(const __grid_constant__ FusedParams fz) {
+  if (fz.st != nullptr && fz.st->state != 0) return;         // CG already converged: no-op like every other kernel
   unsigned *u_ring = fz.sync, *c_ring = fz.sync + kFzRing, *err = fz.sync + kFzErr;
-  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint64_t pol = make_evict_first_policy_fz();
   double acc_u[2] = {0.0, 0.0}, acc_d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   const int n_steps = fz.n_steps, lag = fz.ua + fz.dl;
-  if (fz.debug & 16) return;                       // tuning: idle streaming warp (with bit 8)
 #pragma unroll 1
   for (int t = 0; t < n_steps + lag; ++t) {
     if (t < n_steps + fz.ua) {
-      { FZ_DBG_T0(); if (!(fz.debug & 1)) fz_update_phase(fz, pvec, hvec, t, pol, stage, acc_u); __syncwarp(); if (lane == 0) FZ_DBG_ADD(fz, 3); }
-      { FZ_DBG_T0(); if (lane == 0) { fz_signal(u_ring, t); FZ_DBG_ADD(fz, 5); } }
+      { FZ_DBG_T0(); if (!(fz.debug & 1)) fz_update_phase<UMODE, DIAG>(fz, t, pol, acc_u); __syncthreads(); if (tid == 0) FZ_DBG_ADD(fz, 3); }
+      { FZ_DBG_T0(); if (tid == 0) { fz_signal(u_ring, t); FZ_DBG_ADD(fz, 5); } }
     }
     const int kd = t - lag;
     if (kd >= 0 && !(fz.debug & 32)) {
-      { FZ_DBG_T0(); if (lane == 0) { fz_wait(c_ring, kd, err); FZ_DBG_ADD(fz, 2); } }
-      __syncwarp();
-      { FZ_DBG_T0(); if (!(fz.debug & 2)) fz_finish_phase(fz, pvec, hvec, kd, pol, acc_d); __syncwarp(); if (lane == 0) FZ_DBG_ADD(fz, 4); }
+      { FZ_DBG_T0(); if (tid == 0) { fz_wait(c_ring, kd, fz.n_cell_arrivals, err); FZ_DBG_ADD(fz, 2); } }
+      __syncthreads();
+      { FZ_DBG_T0(); if (!(fz.debug & 2)) fz_finish_phase<CG, DIAG>(fz, kd, pol, acc_d); if (tid == 0) FZ_DBG_ADD(fz, 4); }
     }
   }
-  // per-CTA partial sums of the two phases, lanes in butterfly order
-  double *out = fz.partials + (size_t)blockIdx.x * kFusedPartials;
+  // per-CTA partial sums of the two phases: lanes in butterfly order, then the warps in order
+  __shared__ double wsum[kFzStreamThreads / 32][8];
+  double v7[7] = {acc_u[0], acc_u[1], acc_d[0], acc_d[1], acc_d[2], acc_d[3], acc_d[4]};
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    double v = acc_u[j];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) out[kFzSlotU + j] = v;
-  }
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    double v = acc_d[j];
+  for (int j = 0; j < 7; ++j) {
+    double v = v7[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) out[kFzSlotD + j] = v;
+    if (lane == 0) wsum[tid >> 5][j] = v;
   }
+  __syncthreads();
+  if (tid < 7) {
+    double v = 0.0;
+    for (int w = 0; w < kFzStreamThreads / 32; ++w) v += wsum[w][tid];
+    fz.partials[(size_t)(fz.n_cell_ctas + blockIdx.x) * kFusedPartials + tid] = v;      // slots 0..6 = U | D order
+  }
+  fz_finalize(fz);
 }
 
-// End of the launch: the last CTA to get here adds the per-CTA sums in CTA order (deterministic for a given grid),
-// runs the scalar recurrences (or leaves the local sums for the caller's all-rank sum) and re-arms the counters.
+// End of the iteration: the last CTA of EITHER kernel to get here adds the per-CTA sums in CTA order
+// (deterministic for given grids), runs the scalar recurrences (or leaves the local sums for the caller's all-rank
+// sum) and re-arms the counters.  partials: rows [0, n_cell_ctas) hold the cell kernel's p.(A p) in slot 7, rows
+// [n_cell_ctas, n_cell_ctas + n_stream_ctas) the streaming kernel's seven sums in slots 0..6.
 __device__ __forceinline__ void fz_finalize(const FusedParams &fz) {
   __shared__ bool last;
   __shared__ double tot[kFusedPartials];
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    last = (atomicAdd(fz.sync + kFzTicket, 1u) == gridDim.x - 1);
+    last = (atomicAdd(fz.sync + kFzTicket, 1u) == (unsigned)(fz.n_cell_ctas + fz.n_stream_ctas) - 1);
     if (last) __threadfence();
   }
   __syncthreads();
   if (!last) return;
   if (threadIdx.x < kFusedPartials) {
     double s = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(fz.partials + b * kFusedPartials + threadIdx.x);
+    if (threadIdx.x == kFzSlotC)
+      for (int b = 0; b < fz.n_cell_ctas; ++b) s += __ldcg(fz.partials + (size_t)b * kFusedPartials + kFzSlotC);
+    else
+      for (int b = 0; b < fz.n_stream_ctas; ++b)
+        s += __ldcg(fz.partials + (size_t)(fz.n_cell_ctas + b) * kFusedPartials + threadIdx.x);
     tot[threadIdx.x] = s;
   }
   __syncthreads();

@@ -134,9 +134,6 @@ int bp5_operator_profile(bp5_operator_t op, int enable);
 int bp5_operator_profile_result(bp5_operator_t op, int64_t *launches, double *total_ms);
 /* name of the hand-written kernel variant chosen for this operator */
 const char *bp5_operator_kernel_name(bp5_operator_t op);
-/* name of the kernel bp5_cg_solve(BP5_CG_MERGED) spends its time in: the fused per-iteration kernel (update +
- * cell loop + dot products in one launch) where it applies, else the cell kernel above */
-const char *bp5_operator_cg_kernel_name(bp5_operator_t op);
 /* number of kernels this library has launched on the context since creation */
 int64_t bp5_context_launch_count(bp5_context_t ctx);
 
