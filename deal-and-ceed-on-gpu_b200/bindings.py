@@ -128,6 +128,11 @@ ABI = [
     ("bp5_peer_cg_solve", C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _dp, _dp,
                                     C.c_int]),
     ("bp5_peer_allreduce", C.c_int, [_vp, _dp, C.c_int]),
+    ("bp5_peer_world_size", C.c_int, [_vp]),
+    ("bp5_vector_update_ghost_values", C.c_int, [_vp, _vp]),
+    ("bp5_vector_compress_add", C.c_int, [_vp, _vp]),
+    ("bp5_peer_cg_solve_host", C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
+                                         C.POINTER(C.c_int), _dp]),
 ]
 
 

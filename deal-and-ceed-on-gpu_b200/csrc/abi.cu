@@ -688,6 +688,53 @@ int bp5_peer_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vec
   BP5_ABI_GUARD_END
 }
 
+int bp5_peer_world_size(bp5_operator_t op) { return op ? peer_world_size(op) : 1; }
+
+int bp5_vector_update_ghost_values(bp5_operator_t op, bp5_vector_t vec) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op, "null operator");
+  int rc;
+  if ((rc = check_vec(op, vec))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  if (peer_world_size(op) == 1 && op->n_ghost == 0) return BP5_OK;     // single block: nothing to exchange
+  return peer_update_ghost_values(op, vec);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_vector_compress_add(bp5_operator_t op, bp5_vector_t vec) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op, "null operator");
+  int rc;
+  if ((rc = check_vec(op, vec))) return rc;
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  if (peer_world_size(op) == 1 && op->n_ghost == 0) return BP5_OK;
+  return peer_compress_add(op, vec);
+  BP5_ABI_GUARD_END
+}
+
+int bp5_peer_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, int64_t n, int x0_is_zero,
+                           int control, double tol, int max_its, int *last_step, double *last_value) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && x_host && b_host, "null argument");
+  BP5_REQUIRE(n == op->n_owned, "host buffers hold this block's owned range: n == n_owned");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  bp5_context_t ctx = op->ctx;
+  int rc;
+  if (!op->xh) {
+    if ((rc = bp5_vector_create(ctx, op->n_owned, op->n_ghost, &op->xh))) return rc;
+    if ((rc = bp5_vector_create(ctx, op->n_owned, op->n_ghost, &op->bh))) return rc;
+  }
+  BP5_CUDA(cudaMemcpyAsync(op->bh->d, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->xh->d, 0, sizeof(double) * (op->n_owned + op->n_ghost), ctx->stream));
+  if (!x0_is_zero) BP5_CUDA(cudaMemcpyAsync(op->xh->d, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  rc = cg_solve_peer(op, op->xh, op->bh, nullptr, control, tol, max_its, last_step, last_value, nullptr, 0);
+  if (rc != BP5_OK && rc != BP5_ERR_NO_CONVERGENCE) return rc;
+  BP5_CUDA(cudaMemcpyAsync(x_host, op->xh->d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  return rc;
+  BP5_ABI_GUARD_END
+}
+
 int bp5_peer_allreduce(bp5_operator_t op, double *values, int n) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && values && n >= 1 && n <= 8, "bad argument");

@@ -179,6 +179,9 @@ int peer_wait_add(bp5_operator_t op, double *vec);
 int peer_allreduce(bp5_operator_t op, const double *local_dev, double *out_dev, int n_vals, bool honour_skip);
 int peer_allreduce_host(bp5_operator_t op, double *vals, int n);
 int peer_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src);
+int peer_world_size(bp5_operator_t op);
+int peer_update_ghost_values(bp5_operator_t op, bp5_vector_t vec);
+int peer_compress_add(bp5_operator_t op, bp5_vector_t vec);
 double *peer_scratch(bp5_operator_t op);
 int peer_check(bp5_operator_t op);
 int cg_solve_peer(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t diag, int control, double tol,

@@ -432,6 +432,7 @@ int peer_check(bp5_operator_t op) {
 // sum over all ranks of n host values (norms, parity checks): host -> device -> peers -> host
 int peer_allreduce_host(bp5_operator_t op, double *vals, int n) {
   BP5_REQUIRE(op->peer && op->peer_connected, "peer transport not connected");
+  BP5_REQUIRE(n >= 1 && n <= 8, "1..8 values");
   PeerState *ps = static_cast<PeerState *>(op->peer);
   cudaStream_t s = op->ctx->stream;
   BP5_CUDA(cudaMemcpyAsync(ps->scratch, vals, sizeof(double) * n, cudaMemcpyHostToDevice, s));
@@ -440,6 +441,41 @@ int peer_allreduce_host(bp5_operator_t op, double *vals, int n) {
   BP5_CUDA(cudaMemcpyAsync(vals, ps->scratch + 8, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
   BP5_CUDA(cudaStreamSynchronize(s));
   return peer_check(op);
+}
+
+int peer_world_size(bp5_operator_t op) {
+  if (!op->peer || !op->peer_connected) return 1;
+  return static_cast<PeerState *>(op->peer)->world;
+}
+
+// Stand-alone ghost operations on any vector of the operator's layout.  Each one is a complete exchange round
+// (forward, consume, reverse, add) so that the flag / epoch protocol of the CG loop -- where the flag of one
+// direction acknowledges the buffer of the other -- stays intact whatever sequence of calls the host makes.
+// update_ghost_values: the forward half carries the data (it lands in the neighbour's ghost segment of ITS d
+// vector, from where that rank copies it into its vector); the reverse half carries zeros.
+int peer_update_ghost_values(bp5_operator_t op, bp5_vector_t vec) {
+  BP5_REQUIRE(op->peer && op->peer_connected, "peer transport not connected");
+  cudaStream_t s = op->ctx->stream;
+  int rc;
+  if ((rc = peer_forward(op, vec->d))) return rc;
+  if (op->n_ghost > 0 && vec->d != op->d->d)
+    BP5_CUDA(cudaMemcpyAsync(vec->d + op->n_owned, op->d->d + op->n_owned, sizeof(double) * op->n_ghost,
+                             cudaMemcpyDeviceToDevice, s));
+  if (op->n_ghost > 0) BP5_CUDA(cudaMemsetAsync(op->h->d + op->n_owned, 0, sizeof(double) * op->n_ghost, s));
+  if ((rc = peer_reverse(op, op->h->d))) return rc;
+  return peer_wait_add(op, op->h->d);              // adds zeros onto the scratch vector's faces
+}
+
+// compress(add): the forward half carries nothing of interest, the reverse half the ghost contributions
+int peer_compress_add(bp5_operator_t op, bp5_vector_t vec) {
+  BP5_REQUIRE(op->peer && op->peer_connected, "peer transport not connected");
+  int rc;
+  if ((rc = peer_forward(op, op->d->d))) return rc;
+  if ((rc = peer_reverse(op, vec->d))) return rc;
+  if ((rc = peer_wait_add(op, vec->d))) return rc;
+  if (op->n_ghost > 0)
+    BP5_CUDA(cudaMemsetAsync(vec->d + op->n_owned, 0, sizeof(double) * op->n_ghost, op->ctx->stream));
+  return BP5_OK;
 }
 
 // PoissonOperator::vmult over the partition through the peer transport (bp5/step-64.cu:263-276 with the

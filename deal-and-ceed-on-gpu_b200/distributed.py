@@ -260,12 +260,30 @@ class DistributedPoisson:
         return lambda t, buf: B._check(B.lib().bp5_operator_halo_unpack_add(self.op.h, vec.h, buf.data_ptr()))
 
     def update_ghost_values(self, vec):
+        """LinearAlgebra::distributed::Vector::update_ghost_values [UPSTREAM] on any vector of the block's layout"""
+        if self.transport == "peer":
+            B._check(B.lib().bp5_vector_update_ghost_values(self.op.h, vec.h))
+            return
         with self.torch.cuda.stream(self.stream):
             self.halo.update_ghost_values(self.view(vec), self._pack(vec))
 
     def compress_add(self, vec):
+        """compress(VectorOperation::add) [UPSTREAM]; the ghost entries are zero afterwards"""
+        if self.transport == "peer":
+            B._check(B.lib().bp5_vector_compress_add(self.op.h, vec.h))
+            return
         with self.torch.cuda.stream(self.stream):
             self.halo.compress_add(self.view(vec), self._unpack(vec))
+
+    def cg_solve_host(self, x_host, b_host, control, x0_is_zero=True):
+        """merged CG with this block's HOST buffers (owned range): b in, x out -- peer transport, one native call"""
+        if self.transport != "peer":
+            raise B.Bp5Error(B.ERR_UNSUPPORTED, "cg_solve_host needs the peer transport")
+        its, val = B.C.c_int(0), B.C.c_double(0.0)
+        rc = B.lib().bp5_peer_cg_solve_host(self.op.h, x_host.ctypes.data, b_host.ctypes.data, x_host.size, int(x0_is_zero),
+                                            control.kind, control.tol, control.max_its, B.C.byref(its), B.C.byref(val))
+        control._last_step, control._last_value = its.value, val.value
+        B._check(rc)
 
     def allreduce_scalar(self, value, op=None):
         t = self.torch.tensor([value], dtype=self.torch.float64, device=self._plumbing_device())

@@ -285,6 +285,21 @@ int bp5_peer_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vec
                       int max_its, int *last_step, double *last_value, double *history, int history_len);
 /* in-place sum over all ranks of n <= 8 host values (l2_norm and friends, bp5/solver.h:382) */
 int bp5_peer_allreduce(bp5_operator_t op, double *values, int n);
+/* number of ranks this operator's peer transport is connected to (1: single block / not connected) */
+int bp5_peer_world_size(bp5_operator_t op);
+/* Ghost-value semantics of LinearAlgebra::distributed::Vector [UPSTREAM] for ANY vector of this operator's layout
+ * (the reference relies on them inside cell_loop, bp5/step-64.cu:241,272-275, and on vectors made by
+ * reinit(owned, relevant, comm), :349,363-366).  Collective: every rank calls, in the same order.
+ *   update_ghost_values: ghost entries <- the owners' values;
+ *   compress_add:        owners' entries += the ghost entries of the neighbours, ghost entries <- 0
+ *                        (compress(VectorOperation::add) followed by zero_out_ghosts, as cell_loop leaves dst). */
+int bp5_vector_update_ghost_values(bp5_operator_t op, bp5_vector_t vec);
+int bp5_vector_compress_add(bp5_operator_t op, bp5_vector_t vec);
+/* bp5_peer_cg_solve with HOST buffers of this block's owned range (n = n_owned): b in, x out (and x in unless
+ * x0_is_zero) -- the reference imports the right-hand side from the host and exports the solution
+ * (bp5/step-64.cu:415-417,553-555).  Collective. */
+int bp5_peer_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, int64_t n, int x0_is_zero,
+                           int control, double tol, int max_its, int *last_step, double *last_value);
 
 #ifdef __cplusplus
 }

@@ -87,20 +87,55 @@ inline void check(int rc) {
   if (rc == BP5_ERR_DIVIDE_BY_ZERO) throw ExcDivideByZero();
   throw ExcMessage("bp5_b200 error " + std::to_string(rc) + ": " + msg);
 }
-// one context per process: device = rank % n_devices (bp5/step-64.cu:704-707)
+// one context per process: device = rank % n_devices (bp5/step-64.cu:704-707).  Call set_device() before the
+// first library object is made (the reference calls cudaSetDevice at the top of main); default: device 0.
 class Context {
  public:
-  static bp5_context_t get(int device = -1) {
-    static Context c(device < 0 ? 0 : device);
+  static void set_device(int device) { requested_device() = device; }
+  static bp5_context_t get() {
+    static Context c(requested_device());
     return c.h;
   }
   static void synchronize() { check(bp5_context_synchronize(get())); }   // cudaDeviceSynchronize in the driver
 
  private:
+  static int &requested_device() { static int d = 0; return d; }
   explicit Context(int device) { check(bp5_context_create(device, &h)); }
   ~Context() { bp5_context_destroy(h); }
   bp5_context_t h = nullptr;
 };
+
+// What MPI_COMM_WORLD is to the reference (bp5/step-64.cu:349,363-366,720): one rank per GPU inside one NVLink
+// domain.  Only the set-up travels through it (a few hundred bytes of CUDA IPC handles per rank and barriers):
+// implement it over MPI_Allgather / MPI_Barrier in an MPI program, or over shared memory between forked
+// processes (examples/bp5_step64_multi.cc).  The data plane -- halo exchange, sums of the CG scalars -- is the
+// library's peer-memory transport (bp5_peer_*).
+class Communicator {
+ public:
+  virtual ~Communicator() = default;
+  virtual int rank() const = 0;
+  virtual int size() const = 0;
+  virtual void allgather(const void *send, void *recv_all, std::size_t bytes_per_rank) = 0;
+  virtual void barrier() = 0;
+};
+
+// 1x1x1, 2x1x1, 2x2x1, 2x2x2; otherwise the most cubic factorisation, x >= y >= z
+inline std::array<int, 3> process_grid(int world) {
+  std::array<int, 3> best{world, 1, 1};
+  int best_spread = world, best_px = world;
+  for (int pz = 1; pz <= world; ++pz) {
+    if (world % pz) continue;
+    for (int py = pz; py <= world / pz; ++py) {
+      if ((world / pz) % py) continue;
+      const int px = world / (pz * py);
+      if (px < py) continue;
+      if (px - pz < best_spread || (px - pz == best_spread && px < best_px)) {
+        best_spread = px - pz; best_px = px; best = {px, py, pz};
+      }
+    }
+  }
+  return best;
+}
 }  // namespace b200
 
 // ------------------------------------------------------------------ mesh description
@@ -135,6 +170,10 @@ template <int dim> class Triangulation {
   // smooth deformation of the mesh (BASELINE config 5; not in the reference)
   int deformation = 0;
   double deformation_eps = 0.0;
+  // parallel::distributed::Triangulation<dim>(MPI_COMM_WORLD) (bp5/step-64.cu:310): the mesh is split into a
+  // Cartesian grid of blocks, one per rank of the communicator (nullptr: one block)
+  b200::Communicator *communicator = nullptr;
+  explicit Triangulation(b200::Communicator *comm = nullptr) : communicator(comm) {}
 };
 namespace parallel {
 template <int dim> using Triangulation = dealii::Triangulation<dim>;
@@ -229,9 +268,20 @@ template <> class Vector<double, MemorySpace::CUDA> {
   // non-owning alias of a vector that lives in the library (the solver's temporaries)
   void view(bp5_vector_t handle) { release(); h = handle; owning = false; is_constant = false; }
   Vector &operator=(double s) { b200::check(bp5_vector_set(h, s)); constant = s; is_constant = true; return *this; }
-  double l2_norm() const { double v; b200::check(bp5_vector_norm_sqr_local(h, &v)); return std::sqrt(v); }
-  double operator*(const Vector &o) const { double v; b200::check(bp5_vector_dot_local(h, o.h, &v)); return v; }
-  bool all_zero() const { int z; b200::check(bp5_vector_all_zero_local(h, &z)); return z != 0; }
+  // reductions are over all blocks of the partition (MPI_Allreduce in deal.II [UPSTREAM]): local part on this
+  // GPU, then the peer transport's all-rank sum; identical result on every rank
+  double l2_norm() const { double v; b200::check(bp5_vector_norm_sqr_local(h, &v)); return std::sqrt(global_sum(v)); }
+  double operator*(const Vector &o) const { double v; b200::check(bp5_vector_dot_local(h, o.h, &v)); return global_sum(v); }
+  bool all_zero() const { int z; b200::check(bp5_vector_all_zero_local(h, &z)); return global_sum(z ? 0.0 : 1.0) == 0.0; }
+  // ghost-value semantics (collective over the partition; no-ops on a single block):
+  // update_ghost_values / compress(VectorOperation::add) [UPSTREAM], requested inside cell_loop at
+  // bp5/step-64.cu:241,272-275
+  void update_ghost_values() const { if (partitioned()) b200::check(bp5_vector_update_ghost_values(bp5_vector_owner(h), h)); }
+  void compress(int /*VectorOperation::add*/ = 0) {
+    if (partitioned()) b200::check(bp5_vector_compress_add(bp5_vector_owner(h), h));
+    is_constant = false;
+  }
+  bool partitioned() const { bp5_operator_t op = bp5_vector_owner(h); return op != nullptr && bp5_peer_world_size(op) > 1; }
   void add(double a, const Vector &v) { b200::check(bp5_vector_add(h, a, v.h)); is_constant = false; }
   void equ(double a, const Vector &v) { b200::check(bp5_vector_equ(h, a, v.h)); is_constant = false; }
   void sadd(double s, double a, const Vector &v) { b200::check(bp5_vector_sadd(h, s, a, v.h)); is_constant = false; }
@@ -240,7 +290,13 @@ template <> class Vector<double, MemorySpace::CUDA> {
   double *get_values() { is_constant = false; return bp5_vector_get_values(h); }
   const double *get_values() const { return bp5_vector_get_values(h); }
   size_type local_size() const { int64_t a = 0, g = 0; bp5_vector_local_size(h, &a, &g); return (size_type)a; }
-  size_type size() const { return local_size(); }
+  size_type size() const {                              // global size, like deal.II's Vector::size()
+    bp5_operator_t op = bp5_vector_owner(h);
+    if (!op) return local_size();
+    int64_t n_global = 0;
+    bp5_operator_sizes(op, nullptr, nullptr, &n_global, nullptr);
+    return (size_type)n_global;
+  }
   // import(ReadWriteVector, insert) / the reverse, bp5/step-64.cu:415-417,553-555
   void import_from_host(const std::vector<double> &v) {
     b200::check(bp5_vector_import_host(h, v.data(), (int64_t)v.size())); is_constant = false;
@@ -248,6 +304,11 @@ template <> class Vector<double, MemorySpace::CUDA> {
   void copy_to_host(std::vector<double> &v) const {
     v.resize(local_size());
     b200::check(bp5_vector_export_host(h, v.data(), (int64_t)v.size()));
+  }
+  double global_sum(double v) const {
+    if (!partitioned()) return v;
+    b200::check(bp5_peer_allreduce(bp5_vector_owner(h), &v, 1));
+    return v;
   }
   bp5_vector_t handle() const { return h; }
   void mark_modified() { is_constant = false; }
@@ -283,21 +344,40 @@ template <int dim, int fe_degree, int operator_kind> class MatrixFreeOperator {
     bp5_problem_t pr{};
     pr.degree = fe_degree; pr.quadrature = quadrature; pr.operator_kind = operator_kind;
     pr.geometry_mode = BP5_GEOM_STORED;
+    comm = t.communicator;
+    const int world = comm ? comm->size() : 1, rank = comm ? comm->rank() : 0;
+    const std::array<int, 3> grid = process_grid(world);
+    const int coord[3] = {rank % grid[0], (rank / grid[0]) % grid[1], rank / (grid[0] * grid[1])};
     for (int d = 0; d < 3; ++d) {
       pr.cells[d] = (int32_t)t.cells(d); pr.lower[d] = t.p1[d]; pr.upper[d] = t.p2[d];
-      pr.part_grid[d] = 1; pr.part_coord[d] = 0;
+      pr.part_grid[d] = grid[d]; pr.part_coord[d] = coord[d];
     }
     pr.deformation = t.deformation; pr.deformation_eps = t.deformation_eps;
     check(bp5_operator_create(Context::get(), &pr, &h));
+    if (world > 1) connect_peers(grid.data(), coord, world, rank);
   }
   MatrixFreeOperator(const MatrixFreeOperator &) = delete;
-  ~MatrixFreeOperator() { bp5_operator_destroy(h); }
+  ~MatrixFreeOperator() {
+    if (comm && comm->size() > 1) {        // nobody unmaps while a neighbour may still store into this block
+      bp5_context_synchronize(Context::get());
+      comm->barrier();
+    }
+    bp5_operator_destroy(h);
+  }
 
   void vmult(VectorType &dst, const VectorType &src) const {       // bp5/step-64.cu:263-276
-    check(bp5_operator_set_zero_out(h, do_zero_out));
-    check(bp5_operator_vmult(h, dst.handle(), src.handle()));
+    if (partitioned()) {
+      // update_ghost_values(src) / cell loop with interior-boundary overlap / compress(add)(dst) / Dirichlet
+      // copy, all by the peer transport's kernels.  (dst is overwritten: with do_zero_out == false the
+      // reference accumulates into whatever dst held, which is only ever zero or garbage)
+      check(bp5_peer_vmult(h, dst.handle(), src.handle()));
+    } else {
+      check(bp5_operator_set_zero_out(h, do_zero_out));
+      check(bp5_operator_vmult(h, dst.handle(), src.handle()));
+    }
     dst.mark_modified();
   }
+  bool partitioned() const { return comm != nullptr && comm->size() > 1; }
   void initialize_dof_vector(VectorType &vec) const {             // bp5/step-64.cu:210-215
     bp5_vector_t v = nullptr;
     check(bp5_operator_initialize_dof_vector(h, &v));
@@ -314,13 +394,40 @@ template <int dim, int fe_degree, int operator_kind> class MatrixFreeOperator {
   // (bp5/step-64.cu:604-615), on the device
   double l2_norm(const VectorType &u) const {
     double v = 0.0;
+    u.update_ghost_values();               // the cells of a block read its ghost DoFs
     check(bp5_operator_l2_norm_sqr(h, u.handle(), &v));
-    return std::sqrt(v);
+    return std::sqrt(u.global_sum(v));
   }
   bp5_operator_t handle() const { return h; }
 
  private:
+  // bp5_peer_export -> allgather of the handles -> bp5_peer_connect -> barrier (include/bp5_b200.h)
+  void connect_peers(const int *grid, const int *coord, int world, int rank) {
+    bp5_peer_info_t mine;
+    check(bp5_peer_export(h, rank, world, &mine));
+    std::vector<bp5_peer_info_t> all((std::size_t)world);
+    comm->allgather(&mine, all.data(), sizeof(bp5_peer_info_t));
+    int32_t upper[8], lower[8];
+    for (int m = 0; m < 8; ++m) {
+      upper[m] = lower[m] = -1;
+      if (m == 0) continue;
+      int cu[3], cl[3];
+      bool has_u = true, has_l = true;
+      for (int d = 0; d < 3; ++d) {
+        const int bit = (m >> d) & 1;
+        cu[d] = coord[d] + bit; cl[d] = coord[d] - bit;
+        if (cu[d] >= grid[d]) has_u = false;
+        if (cl[d] < 0) has_l = false;
+      }
+      if (has_u) upper[m] = cu[0] + grid[0] * (cu[1] + grid[1] * cu[2]);
+      if (has_l) lower[m] = cl[0] + grid[0] * (cl[1] + grid[1] * cl[2]);
+    }
+    check(bp5_peer_connect(h, all.data(), upper, lower));
+    check(bp5_context_synchronize(Context::get()));
+    comm->barrier();
+  }
   bp5_operator_t h = nullptr;
+  Communicator *comm = nullptr;
 
  public:
   bool do_zero_out;                                               // bp5/step-64.cu:223
@@ -332,7 +439,8 @@ namespace b200 {
 // does MatrixType expose the library operator (BP5::PoissonOperator, Step64::HelmholtzOperator)?
 template <typename M, typename = void> struct has_native_handle : std::false_type {};
 template <typename M>
-struct has_native_handle<M, std::void_t<decltype(std::declval<const M &>().handle()), decltype(std::declval<const M &>().do_zero_out)>>
+struct has_native_handle<M, std::void_t<decltype(std::declval<const M &>().handle()), decltype(std::declval<const M &>().do_zero_out),
+                                        decltype(std::declval<const M &>().partitioned())>>
     : std::is_same<decltype(std::declval<const M &>().handle()), bp5_operator_t> {};
 
 template <typename VectorType, int variant> class SolverCGBase {
@@ -348,9 +456,21 @@ template <typename VectorType, int variant> class SolverCGBase {
     bp5_vector_t dh = diag.is_constant_value(1.0) ? nullptr : diag.handle();
     if constexpr (has_native_handle<MatrixType>::value) {
       // library operator: the whole loop runs behind one ABI call with the tuned cell kernel
-      check(bp5_operator_set_zero_out(A.handle(), A.do_zero_out));
       int its = 0;
       double val = 0.0;
+      if (A.partitioned()) {
+        // one block per rank: the merged loop with its halo exchange and all-rank sums is one native call
+        // (bp5_peer_cg_solve); "pcg-standard" runs the generic loop below around the partitioned vmult
+        if constexpr (variant == BP5_CG_MERGED) {
+          const int rc = bp5_peer_cg_solve(A.handle(), x.handle(), b.handle(), dh, control.abi_kind(), control.tolerance(),
+                                           (int)control.max_steps(), &its, &val, nullptr, 0);
+          finish(rc, its, val, x);
+        } else {
+          solve_standard_generic(A, x, b, diag, dh != nullptr);
+        }
+        return;
+      }
+      check(bp5_operator_set_zero_out(A.handle(), A.do_zero_out));
       const int rc = bp5_cg_solve(A.handle(), x.handle(), b.handle(), dh, variant, control.abi_kind(),
                                   control.tolerance(), (int)control.max_steps(), &its, &val, nullptr, 0);
       finish(rc, its, val, x);

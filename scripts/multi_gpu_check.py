@@ -55,11 +55,37 @@ for transport, (p, cpg, quad, deform, geom) in [(t, c) for t in TRANSPORTS for c
     P.cg_solve(x, b, ctl, poll_every=3, history=True)
     xo, its, res, hist, ok = m.cg(bo, variant=1, control=1, tol=tol, max_its=500)
     xerr = np.sqrt(P.allreduce_scalar(np.linalg.norm(x.to_host() - xo[own]) ** 2)) / np.linalg.norm(xo)
-    good = rel <= 1e-12 and abs(ctl.last_step() - its) <= 1 and xerr <= 1e-7
+    # ghost-value semantics on arbitrary vectors (update_ghost_values / compress(add)), and the host-buffer solve
+    n_own, n_gh = P.op.n_owned, P.op.n_ghost
+    v = P.op.initialize_dof_vector()
+    full = np.full(n_own + n_gh, -1.0); full[:n_own] = gi[:n_own].astype(float)
+    v.import_host(full)
+    P.update_ghost_values(v)
+    ghost_ok = bool(np.array_equal(v.to_host(with_ghosts=True), gi.astype(float)))
+    full = np.zeros(n_own + n_gh); full[n_own:] = gi[n_own:].astype(float) + 1.0
+    v.import_host(full)
+    P.compress_add(v)
+    lists = [None] * world
+    dist.all_gather_object(lists, gi[n_own:].tolist())
+    counts = np.bincount(np.concatenate([np.asarray(l, dtype=np.int64) for l in lists]) if any(lists) else np.zeros(0, dtype=np.int64),
+                         minlength=m.n_dofs)
+    after = v.to_host(with_ghosts=True)
+    ghost_ok = ghost_ok and bool(np.array_equal(after[:n_own], counts[own] * (own.astype(float) + 1.0))) and not after[n_own:].any()
+    ghost_ok = bool(P.allreduce_scalar(0.0 if ghost_ok else 1.0) == 0.0)
+    v.close()
+    host_ok = True
+    if P.transport == "peer":
+        xh = np.empty(n_own); bhh = b.to_host()
+        ctl2 = dc.SolverControl(500, tol)
+        P.cg_solve_host(xh, bhh, ctl2)
+        herr = np.sqrt(P.allreduce_scalar(np.linalg.norm(xh - xo[own]) ** 2)) / np.linalg.norm(xo)
+        host_ok = abs(ctl2.last_step() - its) <= 1 and herr <= 1e-7
+    good = rel <= 1e-12 and abs(ctl.last_step() - its) <= 1 and xerr <= 1e-7 and ghost_ok and host_ok
     fails += 0 if good else 1
     if rank == 0:
         print(f"{'OK  ' if good else 'FAIL'} transport={transport} world={world} grid={P.part.grid} p={p} cells={cells} quad={quad} deform={deform} geom={geom}: "
-              f"vmult rel err {rel:.2e}, CG its {ctl.last_step()} (oracle {its}), x rel err {xerr:.2e}", flush=True)
+              f"vmult rel err {rel:.2e}, CG its {ctl.last_step()} (oracle {its}), x rel err {xerr:.2e}, "
+              f"ghost ops {'ok' if ghost_ok else 'WRONG'}, host solve {'ok' if host_ok else 'WRONG'}", flush=True)
     for v in (src, dst, b, x):
         v.close()
     P.close()

@@ -50,3 +50,31 @@ def test_step64_driver_reproduces_tutorial_iterations():
         assert abs(got - ref) <= 1
     norms = re.findall(r"solution norm: (\S+)", out.stdout)    # tutorial output: 0.0205439, 0.0205269
     assert [f"{float(v):.6g}" for v in norms] == ["0.0205439", "0.0205269", "0.0205439", "0.0205269"]
+
+
+def test_bp5_multi_rank_driver_reproduces_ladder_fixture():
+    """host code in C++ only on a PARTITIONED mesh (examples/bp5_step64_multi.cc): 2 forked ranks, partitioned
+    operator, owned + ghost vectors, peer-memory halo and all-rank sums behind the facade; same ladder fixture as the
+    single-block driver, and cell_loop bracketed by update_ghost_values / compress(add) must equal vmult.
+    On a 1-GPU box both ranks share cuda:0 (CUDA IPC works across processes on one device)."""
+    import torch
+    _build()
+    gold = json.load(open(os.path.join(GOLD, "bp5_ladder_p5.json")))
+    devices = max(1, min(2, torch.cuda.device_count()))
+    for quad in ("gauss", "gll"):
+        out = subprocess.run([os.path.join(ROOT, "build", "examples", "bp5_step64_multi"), "--ranks", "2", "--devices",
+                              str(devices), "--degree", "5", "--cycle-min", "7", "--cycle-max", "8", "--repetitions", "1",
+                              "--quadrature", quad], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-2000:]
+        blocks = out.stdout.split("Cycle ")[1:]
+        assert len(blocks) == 2
+        for blk, cyc in zip(blocks, (7, 8)):
+            g = gold[f"cycle{cyc}_{quad}"]
+            assert f"Number of degrees of freedom: {g['n_dofs']}" in blk
+            solved = re.findall(r"Solved in (\d+) iterations with time \S+ and DoFs/s \S+ norm (\S+)", blk)
+            assert len(solved) == 2            # standard, merged
+            for its, norm in solved:
+                assert abs(int(its) - g["its_merged"]) <= 1
+                assert float(norm) == pytest.approx(g["x_l2"], rel=1e-5)
+            ghost = re.findall(r"ghost semantics: .* = (\S+)", blk)
+            assert len(ghost) == 1 and float(ghost[0]) <= 1e-12
