@@ -1,4 +1,5 @@
 // extern "C" entry points declared in include/bp5_b200.h.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -146,6 +147,7 @@ int bp5_operator_create(bp5_context_t ctx, const bp5_problem_t *pr, bp5_operator
               (long long)(owned + goff));
     return BP5_ERR_UNSUPPORTED;
   }
+  if (const char *sv = getenv("BP5_SLAB")) op->slab_enabled = atoi(sv) != 0;
   int rc = apply_choose(op);
   if (rc == BP5_OK) rc = operator_setup_device(op);
   if (rc != BP5_OK) { bp5_operator_destroy(op); return rc; }
@@ -167,6 +169,8 @@ int bp5_operator_destroy(bp5_operator_t op) {
   cudaFree(op->coords);
   cudaFree(op->constrained);
   cudaFree(op->cg_scalars);
+  if (op->graph_exec) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(op->graph_exec));
+  slab_destroy(op);
   for (cudaEvent_t e : op->prof_events) cudaEventDestroy(e);
   bp5_vector_destroy(op->g);
   bp5_vector_destroy(op->d);
@@ -322,6 +326,13 @@ int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *per_vmult, double 
   if (per_vmult) *per_vmult = 16.0 * (double)op->n_owned + metric;
   if (per_cg_it) *per_cg_it = 72.0 * (double)op->n_owned + metric;
   return BP5_OK;
+}
+
+int bp5_operator_set_option(bp5_operator_t op, const char *name, int value) {
+  BP5_REQUIRE(op && name, "null argument");
+  if (std::strcmp(name, "slab_pipeline") == 0) { op->slab_enabled = value != 0; return BP5_OK; }
+  set_error("unknown option '%s'", name);
+  return BP5_ERR_INVALID;
 }
 
 int bp5_operator_profile(bp5_operator_t op, int enable) {

@@ -74,6 +74,9 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
   prm.src = src; prm.dst = dst;
   prm.tile_begin = which == 2 ? op->n_boundary_tiles : 0;
   prm.n_tiles = which == 1 ? op->n_boundary_tiles : op->n_tiles;      // end of the range
+  if (op->range_begin >= 0) { prm.tile_begin = op->range_begin; prm.n_tiles = op->range_end; }   // slab pipeline
+  if (op->range_query) { op->apply_grid_full = blocks_per_sm * op->ctx->sm_count; return BP5_OK; }
+  cudaStream_t stream = op->launch_stream ? op->launch_stream : op->ctx->stream;
   prm.sy = op->od[0]; prm.sz = op->od[0] * op->od[1];
   if (prm.n_tiles <= prm.tile_begin) { op->apply_grid = 0; return BP5_OK; }
   prm.skip = op->skip_flag;
@@ -90,11 +93,11 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
       for (int i = 0; i < 64; ++i) { cudaEvent_t e; BP5_CUDA(cudaEventCreate(&e)); op->prof_events.push_back(e); }
     }
     e0 = op->prof_events[op->prof_used++]; e1 = op->prof_events[op->prof_used++];
-    BP5_CUDA(cudaEventRecord(e0, op->ctx->stream));
+    BP5_CUDA(cudaEventRecord(e0, stream));
   }
-  kernel<<<(unsigned)grid, Cfg::NT, Cfg::SMEM_BYTES, op->ctx->stream>>>(prm);
+  kernel<<<(unsigned)grid, Cfg::NT, Cfg::SMEM_BYTES, stream>>>(prm);
   BP5_CHECK_LAUNCH();
-  if (e1) BP5_CUDA(cudaEventRecord(e1, op->ctx->stream));
+  if (e1) BP5_CUDA(cudaEventRecord(e1, stream));
   op->ctx->launches++;
   return BP5_OK;
 }

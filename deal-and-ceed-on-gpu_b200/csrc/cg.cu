@@ -20,7 +20,10 @@
 //    iterations only; as shipped (test at solver.h:425) it runs on every
 //    iteration >= 3 and returns a wrong x (SURVEY.md finding 4).  Residual
 //    history and iteration count are identical either way.
+#include <algorithm>
+
 #include "apply.cuh"
+#include "cg_state.cuh"
 #include "common.h"
 
 namespace bp5 {
@@ -29,16 +32,6 @@ constexpr int kCgBlocks = 592;
 constexpr int kCgThreads = 256;
 
 constexpr int kUpdatePartialCap = 4096;     // >= grid of the update kernel (sm_count * 16)
-
-struct CgState {
-  double alpha, beta, alpha_old, beta_old;
-  double res, tol, gh;
-  int it;          // iterations completed == SolverControl::last_step()
-  int state;       // 0 iterate, 1 success, 2 failure (max its / nan), 3 divide by zero
-  int max_its, control;
-  unsigned ticket;
-  int history_len;
-};
 
 // device scratch of one solve: [CgState | dots partials | cell-kernel p.v partials | Dirichlet correction
 // partials | update-kernel r.r partials | residual history]
@@ -91,14 +84,6 @@ __device__ __forceinline__ void block_sum_k(double (&v)[K], double *sh /*[K*32]*
   __syncthreads();
 }
 
-// SolverControl::check / IterationNumberControl::check [UPSTREAM]
-__device__ __forceinline__ int control_check(int control, int step, int max_its, double value, double tol) {
-  if (control == BP5_CONTROL_ITERATION_NUMBER && step >= max_its) return 1;
-  if (value <= tol) return 1;
-  if (step >= max_its || isnan(value)) return 2;
-  return 0;
-}
-
 // ---------------------------------------------------------------- merged CG
 // MODE 0: update_a0 (solver.h:48-72)  1: update_a<false> (:74-104)  3: update_a1 (:106-140)
 // Fused here: r.r (and r.Dr) of the residual this kernel WRITES -- two of the seven sums of update_b
@@ -136,29 +121,6 @@ __global__ void __launch_bounds__(256) cg_update_kernel(const CgState *__restric
   }
   block_sum_k<2>(s, sh);
   if (threadIdx.x == 0) { rr[2 * blockIdx.x] = s[0]; rr[2 * blockIdx.x + 1] = s[1]; }
-}
-
-// scalar recurrences of one iteration from the seven (globally summed) dot products
-// (solver.h:497-533); one thread
-__device__ __forceinline__ void cg_scalar_step(CgState *st, const double (&rr)[7], double *history) {
-  const int it = st->it + 1;
-  st->alpha_old = st->alpha;
-  st->beta_old = st->beta;
-  st->it = it;
-  if (rr[0] == 0.0) { st->state = 3; return; }                 // ExcDivideByZero, solver.h:501
-  const double alpha = rr[6] / rr[0];                         // solver.h:502
-  // solver.h:504-505; finite negatives are clamped at 0 (deviation): at exact convergence the
-  // three-term expression can round slightly negative and the unguarded sqrt would report NaN.
-  // A NaN expression (overflow, indefinite operator, inf in diag) must stay NaN so that the
-  // stopping test fails like the reference's (fmax(0, NaN) would turn it into "converged").
-  const double res_sq = rr[3] + 2 * alpha * rr[2] + alpha * alpha * rr[1];
-  const double res = (res_sq < 0.0) ? 0.0 : sqrt(res_sq);
-  st->alpha = alpha;
-  st->res = res;
-  if (history && it < st->history_len) history[it] = res;
-  const int conv = control_check(st->control, it, st->max_its, res, st->tol);
-  if (conv != 0) { st->state = conv; return; }
-  st->beta = alpha * (rr[4] + alpha * rr[5]) / rr[6];         // solver.h:533
 }
 
 // partitioned meshes: the sums come back from an allreduce over the blocks
@@ -386,6 +348,14 @@ static int run_iterations(bp5_operator_t op, CgState *st, int max_its, Enqueue e
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   int64_t launches_per_graph = 0;
+  // cached graph of a previous solve with the same vectors (slab pipeline only: graph_key[0] != nullptr)
+  const bool cacheable = op->graph_key[0] != nullptr;
+  bool from_cache = false;
+  if (cacheable && op->graph_exec && std::equal(op->graph_key, op->graph_key + 4, op->graph_key_cached)) {
+    gexec = static_cast<cudaGraphExec_t>(op->graph_exec);
+    launches_per_graph = op->graph_launches;
+    from_cache = true;
+  }
   int it = 0, nbatch = 0, rc = BP5_OK;
   bool done = false;
   while (!done && it < max_its && rc == BP5_OK) {
@@ -422,7 +392,18 @@ static int run_iterations(bp5_operator_t op, CgState *st, int max_its, Enqueue e
     ++nbatch;
   }
   if (rc == BP5_ERR_CUDA && get_error()[0] == 0) set_error("CUDA error in the CG loop: %s", cudaGetErrorString(cudaGetLastError()));
-  if (gexec) { cudaStreamSynchronize(s); cudaGraphExecDestroy(gexec); }
+  if (gexec && cacheable && rc == BP5_OK) {
+    if (!from_cache) {
+      if (op->graph_exec) { cudaStreamSynchronize(s); cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(op->graph_exec)); }
+      op->graph_exec = gexec;
+      op->graph_launches = launches_per_graph;
+      std::copy(op->graph_key, op->graph_key + 4, op->graph_key_cached);
+    }
+  } else if (gexec) {
+    cudaStreamSynchronize(s);
+    cudaGraphExecDestroy(gexec);
+    if (from_cache) op->graph_exec = nullptr;
+  }
   if (graph) cudaGraphDestroy(graph);
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
@@ -508,8 +489,19 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
   BP5_CUDA(cudaMemcpyAsync(st, &init, sizeof(CgState), cudaMemcpyHostToDevice, s));
 
   op->skip_flag = &st->state;
+  // Large single blocks: the iteration as a pipeline of slabs (slab.cu) -- update, cells, dot products a few slabs
+  // apart so that h, p, r change hands in L2.  Same kernels' arithmetic, same sums, different summation order.
+  const bool slabbed = variant == BP5_CG_MERGED && op->slab_enabled && slab_supported(op);
+  if (slabbed && op->apply_grid_full == 0) {
+    // size of the cell kernel's persistent grid (one-time attribute set-up and occupancy query)
+    op->range_begin = 0; op->range_end = 0; op->range_query = true;
+    rc = apply_cell_loop(op, h, d, true, cb.ph);
+    op->range_begin = op->range_end = -1; op->range_query = false;
+    if (rc) return rc;
+  }
   auto enqueue = [&](int cur) -> int {
     int rc = BP5_OK;
+    if (slabbed) return slab_enqueue_iteration(op, cur, st, hist_dev, g, d, h, x->d, diag);
     if (variant == BP5_CG_MERGED) {
       // 1) update region (solver.h:413-448), with the parity-correct x update
       //    (+ r.r, r.Dr of the new residual as per-block partials)
@@ -541,6 +533,10 @@ int cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t dia
     }
     return BP5_OK;
   };
+  // the slab pipeline's graph has thousands of nodes: keep the instantiated graph while the solve is repeated with
+  // the same vectors (the benchmark loop of the reference does exactly that, bp5/step-64.cu:481-517)
+  op->graph_key[0] = slabbed ? (const void *)x->d : nullptr;
+  op->graph_key[1] = (const void *)diag; op->graph_key[2] = (const void *)hist_dev; op->graph_key[3] = (const void *)st;
   rc = run_iterations(op, st, max_its, enqueue);
   op->skip_flag = nullptr;
   if (rc == BP5_OK && variant == BP5_CG_MERGED) {

@@ -138,6 +138,16 @@ struct bp5_operator_s {
   void *peer = nullptr;          // peer-memory transport state (peer.cu), or null
   bool peer_connected = false;
   const int *skip_flag = nullptr; // device word: when non-zero the cell loop is a no-op (CG converged)
+  // slab-pipelined CG iteration (slab.cu): overrides of the next cell-kernel launch, plan, cached graph
+  long long range_begin = -1, range_end = -1;   // tile range instead of `which`
+  bool range_query = false;                     // only size the persistent grid (apply_grid_full), no launch
+  cudaStream_t launch_stream = nullptr;         // instead of the context's stream
+  int apply_grid_full = 0;                      // CTAs of a full launch of the CG-mode cell kernel
+  bool slab_enabled = false;                    // bp5_operator_set_option("slab_pipeline", 1) or BP5_SLAB=1
+  void *slab = nullptr;                         // SlabPlan
+  void *graph_exec = nullptr;                   // cudaGraphExec_t of the last slab-pipelined batch
+  int64_t graph_launches = 0;
+  const void *graph_key[4] = {nullptr, nullptr, nullptr, nullptr}, *graph_key_cached[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace bp5 {
@@ -160,6 +170,11 @@ int apply_cell_loop_otf(bp5_operator_t op, double *dst, const double *src, int m
 int apply_copy_constrained_dot(bp5_operator_t op, double *dst, const double *src, double *partials);
 int apply_zero_skeleton(bp5_operator_t op, double *dst);
 int apply_copy_constrained(bp5_operator_t op, double *dst, const double *src);
+// slab.cu
+bool slab_supported(bp5_operator_t op);
+void slab_destroy(bp5_operator_t op);
+int slab_enqueue_iteration(bp5_operator_t op, int cur, void *state, double *hist_dev, double *g, double *d, double *h,
+                           double *x, const double *diag);
 // vector.cu
 int vec_fill(bp5_context_t ctx, double *d, int64_t n, double v);
 int vec_axpy(bp5_context_t ctx, double *y, double s, double a, const double *x, int64_t n, int mode);

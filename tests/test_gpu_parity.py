@@ -407,3 +407,34 @@ def test_nan_residual_is_reported_as_no_convergence(gpu_ctx, variant):
             solver(control).solve(op, x, b)
         assert control.last_step() < 50 and not np.isfinite(control.last_value())
     b.close(); x.close(); op.close()
+
+
+@pytest.mark.parametrize("p,cells,quad,rounds", [(4, (9, 7, 6), 1, 1), (6, (5, 4, 4), 0, 2), (2, (17, 9, 8), 1, 1)])
+def test_slab_pipelined_iteration_reproduces_the_separate_kernels(gpu_ctx, p, cells, quad, rounds, monkeypatch):
+    """opt-in "slab_pipeline": update, cells and dot products of an iteration a few slabs apart on four streams.
+    Same operator, same sums (other summation order): residual history equal to 1e-10, same iteration count, same
+    solution; with a Jacobi diagonal too."""
+    dc = _dc()
+    monkeypatch.setenv("BP5_SLAB_ROUNDS", str(rounds))
+    runs = {}
+    for slab in (0, 1):
+        op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=quad, deformation=1, eps=0.1))
+        op.set_option("slab_pipeline", slab)
+        b, x, diag = op.initialize_dof_vector(), op.initialize_dof_vector(), op.initialize_dof_vector()
+        op.assemble_rhs(b)
+        op.compute_diagonal(diag, invert=True)
+        op.do_zero_out = False
+        out = []
+        for pre in (None, diag):
+            ctl = dc.SolverControl(400, 1e-9 * b.l2_norm())
+            x.set(0.0)
+            dc.SolverCGFullMerge(ctl).solve(op, x, b, preconditioner=pre)
+            out.append((ctl.last_step(), ctl.history.copy(), x.to_host()))
+        runs[slab] = out
+        for v in (b, x, diag):
+            v.close()
+        op.close()
+    for (its0, h0, x0), (its1, h1, x1) in zip(runs[0], runs[1]):
+        assert its0 == its1
+        np.testing.assert_allclose(h1, h0, rtol=1e-10, atol=1e-14 * h0[0])
+        assert relerr(x1, x0) <= 1e-10
