@@ -290,6 +290,27 @@ def measure_helmholtz(dc, torch, ctx, stream):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
+def measure_user_functor(hbm_peak):
+    """What staying on the reference's device-functor API costs (examples/bp5_functors.cu bench mode): the user-written
+    LocalPoissonOperator on CUDAWrappers::MatrixFree / FEEvaluationGL (one CTA per cell, deal.II-layout arrays) against
+    the tuned kernel, p = 6 GLL, 42^3 cells = 16.2 M DoFs.  Reported under "variants"; never fatal."""
+    exe = os.path.join(ROOT, "build", "examples", "bp5_functors")
+    try:
+        if not os.path.exists(exe):
+            return {"error": "build/examples/bp5_functors not built"}
+        out = subprocess.run([exe, "bench", "6", "42"], capture_output=True, text=True, timeout=300)
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+        ach = d["algorithmic_bytes_per_vmult"] / (d["user_functor_vmult_ms"] * 1e-3) / 1e9
+        ach_lib = d["algorithmic_bytes_per_vmult"] / (d["library_vmult_ms"] * 1e-3) / 1e9
+        return {"workload": f"BP5 vmult through user-written device functors, p=6 GLL, {d['cells']}^3 cells = {d['dofs']} DoFs",
+                "vmult_ms": d["user_functor_vmult_ms"], "value": d["dofs"] / (d["user_functor_vmult_ms"] * 1e-3) / 1e9,
+                "unit": "GDoF/s", "roofline_achieved": ach, "roofline_frac": ach / hbm_peak,
+                "tuned_kernel_vmult_ms": d["library_vmult_ms"], "tuned_kernel_roofline_frac": ach_lib / hbm_peak,
+                "rel_diff_vs_tuned_kernel": d["rel_diff"]}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -405,6 +426,8 @@ def run_b200(args):
                            "cg_frac": cg_fracs(r)[0], "cg_frac_64B_model": cg_fracs(r)[1], "x_l2": r["xnorm"]}
     if helm is not None:
         variants["helmholtz_config2"] = helm
+    if not args.no_variants:
+        variants["user_functor"] = measure_user_functor(hbm_peak)
     out["variants"] = variants
     if not args.no_cpu_baseline:
         cells = args.cpu_cells or auto_cpu_cells(args.degree)

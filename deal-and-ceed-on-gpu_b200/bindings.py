@@ -111,6 +111,7 @@ ABI = [
     ("bp5_cg_solve_host", C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.POINTER(C.c_int), _dp]),
     ("bp5_operator_matrix_free_data", C.c_int, [_vp, _vp]),
+    ("bp5_operator_matrix_free_data_colored", C.c_int, [_vp, C.c_int, _vp]),
     ("bp5_operator_halo_info", C.c_int, [_vp] + [C.POINTER(C.c_int64)] * 4),
     ("bp5_operator_halo_pack", C.c_int, [_vp, _vp, _vp]),
     ("bp5_operator_halo_unpack_add", C.c_int, [_vp, _vp, _vp]),

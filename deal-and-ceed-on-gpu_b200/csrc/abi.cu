@@ -165,6 +165,10 @@ int bp5_operator_destroy(bp5_operator_t op) {
   cudaFree(op->l2g_irr);
   cudaFree(op->mf_l2g); cudaFree(op->mf_constraint_mask); cudaFree(op->mf_inv_jacobian);
   cudaFree(op->mf_jxw); cudaFree(op->mf_q_points);
+  for (int c = 0; c < 8; ++c) {
+    cudaFree(op->mfc_l2g[c]); cudaFree(op->mfc_constraint_mask[c]); cudaFree(op->mfc_inv_jacobian[c]);
+    cudaFree(op->mfc_jxw[c]); cudaFree(op->mfc_q_points[c]);
+  }
   cudaFree(op->metric);
   cudaFree(op->coords);
   cudaFree(op->constrained);
@@ -551,6 +555,38 @@ int bp5_operator_matrix_free_data(bp5_operator_t op, bp5_matrix_free_data_t *out
       out->shape_gradients[q * op->n + i] = op->tab.Dg[q * op->n + i];
       out->co_shape_gradients[q * op->n + i] = op->tab.Dt[q * op->n + i];
     }
+  return BP5_OK;
+  BP5_ABI_GUARD_END
+}
+
+static void fill_tables(bp5_operator_t op, bp5_matrix_free_data_t *out) {
+  out->padding_length = (unsigned int)op->mf_padding;
+  out->n_q_points_1d = op->n;
+  out->collocation = op->prob.quadrature == BP5_QUAD_GLL;
+  for (int q = 0; q < op->n; ++q)
+    for (int i = 0; i < op->n; ++i) {
+      out->shape_values[q * op->n + i] = op->tab.B[q * op->n + i];
+      out->shape_gradients[q * op->n + i] = op->tab.Dg[q * op->n + i];
+      out->co_shape_gradients[q * op->n + i] = op->tab.Dt[q * op->n + i];
+    }
+}
+
+int bp5_operator_matrix_free_data_colored(bp5_operator_t op, int color, bp5_matrix_free_data_t *out) {
+  BP5_ABI_GUARD_BEGIN
+  BP5_REQUIRE(op && out, "null argument");
+  BP5_REQUIRE(color >= 0 && color < 8, "colour must be 0..7");
+  BP5_REQUIRE(op->n_ghost == 0, "the generic functor path handles a single block");
+  BP5_CUDA(cudaSetDevice(op->ctx->device));
+  int rc;
+  if ((rc = operator_generic_data_colored(op))) return rc;
+  std::memset(out, 0, sizeof(*out));
+  out->q_points = op->mfc_q_points[color];
+  out->local_to_global = op->mfc_l2g[color];
+  out->inv_jacobian = op->mfc_inv_jacobian[color];
+  out->JxW = op->mfc_jxw[color];
+  out->constraint_mask = op->mfc_constraint_mask[color];
+  out->n_cells = (unsigned int)op->mfc_n_cells[color];
+  fill_tables(op, out);
   return BP5_OK;
   BP5_ABI_GUARD_END
 }

@@ -781,6 +781,9 @@ int cg_solve_peer(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_
     if ((rc = peer_reverse(op, h))) return rc;
     if ((rc = apply_cell_loop(op, h, d, true, cb.ph + grid_b, 2))) return rc;
     const int n_ph = grid_b + op->apply_grid;
+    // boundary + interior partials + the Dirichlet correction share cb.ph: the next buffer (r.r partials) must
+    // never be reached
+    BP5_REQUIRE(n_ph + n_corr <= kApplyPartialCap + kConstrainedPartials, "cell-kernel partial sums exceed their buffer");
     if ((rc = peer_wait_add(op, h))) return rc;
     if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + n_ph))) return rc;
     launch_dots<false>(has_diag, /*lean=*/true, s, st, d, g, h, diag, n, cb, sums, n_ph + n_corr, (int)grid);

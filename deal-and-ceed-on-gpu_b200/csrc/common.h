@@ -115,6 +115,11 @@ struct bp5_operator_s {
   unsigned int *mf_l2g = nullptr, *mf_constraint_mask = nullptr;
   double *mf_inv_jacobian = nullptr, *mf_jxw = nullptr, *mf_q_points = nullptr;
   int mf_padding = 0;
+  // the same arrays per parity colour of the cells (use_coloring): colour = px + 2 py + 4 pz
+  bool mf_colors_built = false;
+  unsigned int *mfc_l2g[8] = {nullptr}, *mfc_constraint_mask[8] = {nullptr};
+  double *mfc_inv_jacobian[8] = {nullptr}, *mfc_jxw[8] = {nullptr}, *mfc_q_points[8] = {nullptr};
+  int64_t mfc_n_cells[8] = {0};
   double *coords = nullptr;     // BP5_GEOM_ON_THE_FLY: nodal coordinates [3][n_owned + n_ghost] instead of the metric
   double *metric = nullptr;     // [tile][cpt][planes][n^3]; planes: 6 (Poisson) or 7 (Helmholtz: + a*JxW)
   int metric_planes = 6;
@@ -157,6 +162,7 @@ int operator_setup_device(bp5_operator_t op);
 int operator_assemble_rhs(bp5_operator_t op, double *b_dev);
 int operator_l2_norm_sqr(bp5_operator_t op, const double *u_dev, double *out);
 int operator_generic_data(bp5_operator_t op);
+int operator_generic_data_colored(bp5_operator_t op);
 int operator_diagonal(bp5_operator_t op, double *diag_dev, bool invert);
 int operator_export_coefficients(bp5_operator_t op, double *host_out);
 int operator_export_coords(bp5_operator_t op, double *host_out);

@@ -17,6 +17,8 @@
 //             mailboxes in rank order (bitwise identical everywhere) and runs the scalar recurrences.
 // Flags carry a monotonically increasing epoch; a flag doubles as the acknowledgement that frees the
 // buffer of the opposite direction (see the ordering argument in DESIGN.md section 6).
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -75,8 +77,10 @@ __device__ __forceinline__ int ld_acquire_sys(const int *p) {
 // Wait until *flag has reached `epoch`.  A neighbour that died (or a caller that broke the collective call
 // order) must not hang this GPU: after kPeerTimeoutNs the wait gives up, latches *err, and every later wait
 // returns at once; the host reports the failure when the solve ends (peer_check).
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
+// default 20 s, BP5_PEER_TIMEOUT_S overrides (read when the transport is connected)
+__device__ unsigned long long g_peer_timeout_ns = 20ull * 1000 * 1000 * 1000;
 __device__ __forceinline__ void spin_until(const int *flag, int epoch, unsigned *err) {
+  const unsigned long long kPeerTimeoutNs = g_peer_timeout_ns;
   if (*reinterpret_cast<volatile unsigned *>(err) != 0) return;
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -327,6 +331,10 @@ int peer_connect(bp5_operator_t op, const bp5_peer_info_t *all, const int *upper
       ps->rev_flag[m] = flag_ptr(static_cast<double *>(ps->mapped[lo]), L) + 8 + m;
     }
   }
+  if (const char *tv = getenv("BP5_PEER_TIMEOUT_S")) {
+    const unsigned long long ns = (unsigned long long)(std::max(1.0, atof(tv)) * 1e9);
+    BP5_CUDA(cudaMemcpyToSymbol(g_peer_timeout_ns, &ns, sizeof(ns)));
+  }
   op->peer_connected = true;
   return BP5_OK;
 }
@@ -423,7 +431,11 @@ int peer_check(bp5_operator_t op) {
   BP5_CUDA(cudaMemcpyAsync(&err, ps->ticket + 4, sizeof(unsigned), cudaMemcpyDeviceToHost, op->ctx->stream));
   BP5_CUDA(cudaStreamSynchronize(op->ctx->stream));
   if (err != 0) {
-    set_error("peer exchange timed out: a neighbouring rank did not reach the same collective call");
+    // reported once: re-arm the latch so that a later, correctly ordered collective call can succeed (the flags and
+    // epochs of the call that timed out are undefined, the caller should re-create the operator to be safe)
+    BP5_CUDA(cudaMemsetAsync(ps->ticket + 4, 0, sizeof(unsigned), op->ctx->stream));
+    set_error("peer exchange timed out: a neighbouring rank did not reach the same collective call within "
+              "BP5_PEER_TIMEOUT_S (default 20 s); ranks must enter collective calls together (barrier after connect)");
     return BP5_ERR_CUDA;
   }
   return BP5_OK;

@@ -396,13 +396,19 @@ int operator_export_global_indices(bp5_operator_t op, int64_t *host_out) { retur
 //   local_to_global[cell*pad + i]                       fe_evaluation_gl.h:118,144
 //   q_points[cell*pad + q] (3 doubles each)             step-64/step-64.cu:105-108
 // pad = next power of two >= n^3 (padding_length).
-__global__ void generic_data_kernel(BlockGeom g, int pad, unsigned int *__restrict__ l2g, double *__restrict__ inv_jac,
-                                    double *__restrict__ jxw, double *__restrict__ qpts) {
+// The cells written are those of the sub-lattice (off + stride * i) in each direction, numbered x fastest:
+// stride 1, off 0 = all cells in lexicographic order; stride 2 = one of the eight parity colours (cells of one
+// colour share no DoF, MatrixFree::AdditionalData::use_coloring, bp5/fe_evaluation_gl.h:176-177).
+struct CellLattice { int stride, off[3], dims[3]; };
+__global__ void generic_data_kernel(BlockGeom g, CellLattice lat, int pad, unsigned int *__restrict__ l2g,
+                                    double *__restrict__ inv_jac, double *__restrict__ jxw, double *__restrict__ qpts) {
   extern __shared__ double sm[];
   const int n = g.n, n2 = n * n, n3 = n2 * n;
   const long long cell = blockIdx.x;
   const long long n_cells = gridDim.x;
-  const int lcx = cell % g.lc[0], lcy = (cell / g.lc[0]) % g.lc[1], lcz = cell / ((long long)g.lc[0] * g.lc[1]);
+  const int lcx = lat.off[0] + lat.stride * (int)(cell % lat.dims[0]);
+  const int lcy = lat.off[1] + lat.stride * (int)((cell / lat.dims[0]) % lat.dims[1]);
+  const int lcz = lat.off[2] + lat.stride * (int)(cell / ((long long)lat.dims[0] * lat.dims[1]));
   const int t = threadIdx.x;
   const int i = t % n, j = (t / n) % n, k = t / n2;
   if (t < n3) l2g[cell * pad + t] = (unsigned int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
@@ -427,6 +433,56 @@ __global__ void generic_data_kernel(BlockGeom g, int pad, unsigned int *__restri
   for (int d = 0; d < 3; ++d) qpts[3 * at + d] = xr[d];
 }
 
+// arrays of one cell lattice in deal.II's layout; n_cells_out = 0 leaves everything null
+static int build_generic_arrays(bp5_operator_t op, const CellLattice &lat, unsigned int **l2g, double **inv_jac,
+                                double **jxw, double **qpts, unsigned int **cmask, int64_t *n_cells_out) {
+  bp5_context_t ctx = op->ctx;
+  const int n = op->n, n3 = n * n * n, pad = op->mf_padding;
+  const size_t cells = (size_t)lat.dims[0] * lat.dims[1] * lat.dims[2];
+  *n_cells_out = (int64_t)cells;
+  if (cells == 0) return BP5_OK;
+  BP5_CUDA(cudaMalloc(l2g, sizeof(unsigned int) * cells * pad));
+  BP5_CUDA(cudaMalloc(inv_jac, sizeof(double) * 9 * cells * pad));
+  BP5_CUDA(cudaMalloc(jxw, sizeof(double) * cells * pad));
+  BP5_CUDA(cudaMalloc(qpts, sizeof(double) * 3 * cells * pad));
+  BP5_CUDA(cudaMalloc(cmask, sizeof(unsigned int) * cells));
+  BP5_CUDA(cudaMemsetAsync(*l2g, 0, sizeof(unsigned int) * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(*inv_jac, 0, sizeof(double) * 9 * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(*jxw, 0, sizeof(double) * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(*qpts, 0, sizeof(double) * 3 * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(*cmask, 0, sizeof(unsigned int) * cells, ctx->stream));   // conforming mesh
+  const BlockGeom g = make_geom(op);
+  BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = ((n3 + 31) / 32) * 32;
+  generic_data_kernel<<<(unsigned)cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(g, lat, pad, *l2g, *inv_jac, *jxw,
+                                                                                        *qpts);
+  BP5_CHECK_LAUNCH();
+  ctx->launches++;
+  return BP5_OK;
+}
+
+// the same arrays once per parity colour (px, py, pz), colour = px + 2 py + 4 pz
+int operator_generic_data_colored(bp5_operator_t op) {
+  if (op->mf_colors_built) return BP5_OK;
+  int pad = 1;
+  while (pad < op->n * op->n * op->n) pad <<= 1;
+  op->mf_padding = pad;
+  for (int c = 0; c < 8; ++c) {
+    CellLattice lat;
+    lat.stride = 2;
+    for (int d = 0; d < 3; ++d) {
+      lat.off[d] = (c >> d) & 1;
+      lat.dims[d] = op->lc[d] > lat.off[d] ? (op->lc[d] - lat.off[d] + 1) / 2 : 0;
+    }
+    int rc = build_generic_arrays(op, lat, &op->mfc_l2g[c], &op->mfc_inv_jacobian[c], &op->mfc_jxw[c], &op->mfc_q_points[c],
+                                  &op->mfc_constraint_mask[c], &op->mfc_n_cells[c]);
+    if (rc) return rc;
+  }
+  BP5_CUDA(cudaStreamSynchronize(op->ctx->stream));
+  op->mf_colors_built = true;
+  return BP5_OK;
+}
+
 int operator_generic_data(bp5_operator_t op) {
   if (op->mf_l2g) return BP5_OK;
   bp5_context_t ctx = op->ctx;
@@ -448,8 +504,9 @@ int operator_generic_data(bp5_operator_t op) {
   const BlockGeom g = make_geom(op);
   BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
   const int threads = ((n3 + 31) / 32) * 32;
+  const CellLattice all{1, {0, 0, 0}, {op->lc[0], op->lc[1], op->lc[2]}};
   generic_data_kernel<<<(unsigned)op->n_cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
-      g, pad, op->mf_l2g, op->mf_inv_jacobian, op->mf_jxw, op->mf_q_points);
+      g, all, pad, op->mf_l2g, op->mf_inv_jacobian, op->mf_jxw, op->mf_q_points);
   BP5_CHECK_LAUNCH();
   ctx->launches++;
   BP5_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -320,6 +320,10 @@ class DistributedPoisson:
             control.history = hist[: its.value + 1] if history else None
             B._check(rc)
             return
+        # the stepwise path starts from g = -b (bp5_cg_step_begin): a non-zero initial guess would silently give a
+        # wrong answer (the reference forms g = A x - b, solver.h:375-381); the peer path rejects it the same way
+        if self.allreduce_scalar(0.0 if x.all_zero() else 1.0) != 0.0:
+            raise B.Bp5Error(B.ERR_INVALID, "DistributedPoisson.cg_solve needs x == 0 on entry")
         res0 = self.l2_norm(b)
         hist_len = control.max_its + 2 if history else 0
         state = 1 if res0 <= control.tol else (0 if control.max_its > 0 else (1 if control.kind == 0 else 2))

@@ -13,6 +13,7 @@
 //
 //   bp5_functors <degree 2..6> <gauss|gll> <cells_x> <cells_y> <cells_z> <deformation eps> [cell edge = 1]
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <iomanip>
 
@@ -109,7 +110,8 @@ template <int dim, int fe_degree> class LocalPoissonOperatorPlain {
 
 template <int dim, int fe_degree> class PoissonOperator {
  public:
-  PoissonOperator(const DoFHandler<dim> &dof_handler, const AffineConstraints<double> &constraints, bool collocation);
+  PoissonOperator(const DoFHandler<dim> &dof_handler, const AffineConstraints<double> &constraints, bool collocation,
+                  bool use_coloring = false);
   void vmult(VectorType &dst, const VectorType &src) const;
   void vmult_plain(VectorType &dst, const VectorType &src) const;
   void initialize_dof_vector(VectorType &vec) const { mf_data.initialize_dof_vector(vec); }
@@ -127,12 +129,16 @@ template <int dim, int fe_degree> class PoissonOperator {
 
 template <int dim, int fe_degree>
 PoissonOperator<dim, fe_degree>::PoissonOperator(const DoFHandler<dim> &dof_handler,
-                                                 const AffineConstraints<double> &constraints, bool collocation)
+                                                 const AffineConstraints<double> &constraints, bool collocation,
+                                                 bool use_coloring)
     : do_zero_out(true) {
   MappingQGeneric<dim> mapping(fe_degree);
   typename CUDAWrappers::MatrixFree<dim, double>::AdditionalData additional_data;
   additional_data.mapping_update_flags = update_values | update_gradients | update_JxW_values | update_quadrature_points;
   additional_data.overlap_communication_computation = true;
+  // colouring: only vmult_plain may be used then -- like the reference's, JacobianFunctor / LocalPoissonOperator
+  // index the coefficient by the colour-local cell number without the colour's row offset
+  additional_data.use_coloring = use_coloring;
   if (collocation) mf_data.reinit(mapping, dof_handler, constraints, QGaussLobatto<1>(fe_degree + 1), additional_data);
   else mf_data.reinit(mapping, dof_handler, constraints, QGauss<1>(fe_degree + 1), additional_data);
   n_owned_cells =
@@ -210,10 +216,12 @@ template <int dim, int fe_degree> class LocalHelmholtzOperator {
 
 template <int dim, int fe_degree> class HelmholtzOperator {
  public:
-  HelmholtzOperator(const DoFHandler<dim> &dof_handler, const AffineConstraints<double> &constraints) {
+  HelmholtzOperator(const DoFHandler<dim> &dof_handler, const AffineConstraints<double> &constraints,
+                    bool use_coloring = false) {
     MappingQGeneric<dim> mapping(fe_degree);
     typename CUDAWrappers::MatrixFree<dim, double>::AdditionalData additional_data;
     additional_data.mapping_update_flags = update_values | update_gradients | update_JxW_values | update_quadrature_points;
+    additional_data.use_coloring = use_coloring;      // local_q_point_id adds the colour's row offset
     const QGauss<1> quad(fe_degree + 1);
     mf_data.reinit(mapping, dof_handler, constraints, quad, additional_data);
     const unsigned int n_owned_cells =
@@ -243,8 +251,19 @@ static double rel_diff(const std::vector<double> &a, const std::vector<double> &
   return std::sqrt(num / (den > 0. ? den : 1.));
 }
 
+static void dump(const std::string &prefix, const char *name, const std::vector<double> &v) {
+  if (prefix.empty()) return;
+  FILE *f = std::fopen((prefix + name + ".f64").c_str(), "wb");
+  if (!f) throw ExcMessage("cannot write " + prefix + name);
+  std::fwrite(v.data(), sizeof(double), v.size(), f);
+  std::fclose(f);
+}
+static bool same_bits(const std::vector<double> &a, const std::vector<double> &b) {
+  return a.size() == b.size() && std::memcmp(a.data(), b.data(), sizeof(double) * a.size()) == 0;
+}
+
 template <int dim, int fe_degree>
-int run(bool collocation, const std::vector<unsigned int> &cells, double eps, double cell_edge) {
+int run(bool collocation, const std::vector<unsigned int> &cells, double eps, double cell_edge, const std::string &dump_prefix) {
   parallel::distributed::Triangulation<dim> triangulation;
   Point<dim> p2;
   for (int d = 0; d < dim; ++d) p2[d] = cells[d] * cell_edge;
@@ -286,8 +305,24 @@ int run(bool collocation, const std::vector<unsigned int> &cells, double eps, do
     std::vector<double> a, c;
     y_user.copy_to_host(a); y_lib.copy_to_host(c);
     report("bp5_vmult_user_vs_library", rel_diff(a, c), 1e-12);
+    dump(dump_prefix, "bp5_Ab", a);
     y_plain.copy_to_host(a);
     report("bp5_vmult_plain_vs_library", rel_diff(a, c), 1e-12);
+    {  // use_coloring: eight colour passes with plain += (fe_evaluation_gl.h:176-177): same operator, and
+       // bitwise reproducible from run to run (atomics add in whatever order the hardware schedules)
+      UserBP5::PoissonOperator<dim, fe_degree> col_op(dof_handler, constraints, collocation, /*use_coloring=*/true);
+      VectorType bc, y1, y2;
+      col_op.initialize_dof_vector(bc);
+      bc.equ(1., b);
+      y1.reinit(bc); y2.reinit(bc);
+      col_op.vmult_plain(y1, bc);
+      col_op.vmult_plain(y2, bc);
+      std::vector<double> a1, a2;
+      y1.copy_to_host(a1); y2.copy_to_host(a2);
+      report("bp5_vmult_colored_vs_library", rel_diff(a1, c), 1e-12);
+      std::cout << "bp5_colored_bitwise_reproducible " << (same_bits(a1, a2) ? 1 : 0) << std::endl;
+      if (!same_bits(a1, a2)) ++failures;
+    }
     std::cout << "bp5_norm_b " << b.l2_norm() << std::endl;
     std::cout << "bp5_norm_Ab " << y_user.l2_norm() << std::endl;
     std::cout << "bp5_norm_AAb " << z_user.l2_norm() << std::endl;
@@ -306,6 +341,7 @@ int run(bool collocation, const std::vector<unsigned int> &cells, double eps, do
     std::cout << "bp5_norm_x " << x_user.l2_norm() << std::endl;
     x_user.copy_to_host(a); x_lib.copy_to_host(c);
     report("bp5_x_user_vs_library", rel_diff(a, c), 1e-8);
+    dump(dump_prefix, "bp5_x", a);
     if (std::abs((int)c_user.last_step() - (int)c_lib.last_step()) > 1) { ++failures; std::cout << "iteration counts differ <-- FAIL\n"; }
     user_op.do_zero_out = true;
     x_user = 0.;
@@ -328,6 +364,21 @@ int run(bool collocation, const std::vector<unsigned int> &cells, double eps, do
     std::vector<double> a, c;
     y_user.copy_to_host(a); y_lib.copy_to_host(c);
     report("helmholtz_vmult_user_vs_library", rel_diff(a, c), 1e-12);
+    dump(dump_prefix, "helmholtz_Ab", a);
+    {  // the same operator with use_coloring (the coefficient is indexed through local_q_point_id: colour-safe)
+      UserStep64::HelmholtzOperator<dim, fe_degree> col_op(dof_handler, constraints, /*use_coloring=*/true);
+      VectorType bc, y1, y2;
+      col_op.initialize_dof_vector(bc);
+      bc.equ(1., b);
+      y1.reinit(bc); y2.reinit(bc);
+      col_op.vmult(y1, bc);
+      col_op.vmult(y2, bc);
+      std::vector<double> a1, a2;
+      y1.copy_to_host(a1); y2.copy_to_host(a2);
+      report("helmholtz_vmult_colored_vs_library", rel_diff(a1, c), 1e-12);
+      std::cout << "helmholtz_colored_bitwise_reproducible " << (same_bits(a1, a2) ? 1 : 0) << std::endl;
+      if (!same_bits(a1, a2)) ++failures;
+    }
     std::cout << "helmholtz_norm_Ab " << y_user.l2_norm() << std::endl;
     DiagonalMatrix<VectorType> preconditioner;
     preconditioner.get_vector().reinit(b);
@@ -345,8 +396,57 @@ int run(bool collocation, const std::vector<unsigned int> &cells, double eps, do
   return failures;
 }
 
+// `bp5_functors bench <degree> <cells per direction>`: what staying on the reference's functor API costs --
+// user-written LocalPoissonOperator (one CTA per cell, deal.II-layout arrays, atomics) against the library's
+// tuned kernel on the same mesh, GLL collocation, CUDA events on the library's stream.
+template <int dim, int fe_degree> int run_bench(unsigned int nc) {
+  parallel::distributed::Triangulation<dim> triangulation;
+  Point<dim> p2;
+  for (int d = 0; d < dim; ++d) p2[d] = nc;
+  GridGenerator::subdivided_hyper_rectangle(triangulation, std::vector<unsigned int>(dim, nc), Point<dim>(), p2);
+  FE_Q<dim> fe(fe_degree);
+  DoFHandler<dim> dof_handler(triangulation);
+  dof_handler.distribute_dofs(fe);
+  AffineConstraints<double> constraints;
+  UserBP5::PoissonOperator<dim, fe_degree> user_op(dof_handler, constraints, true);
+  BP5::PoissonOperator<dim, fe_degree> lib_op(dof_handler, constraints, BP5_QUAD_GLL);
+  VectorType bu, yu, bl, yl;
+  user_op.initialize_dof_vector(bu); yu.reinit(bu);
+  lib_op.initialize_dof_vector(bl); yl.reinit(bl);
+  lib_op.assemble_rhs(bl);
+  bu.equ(1., bl);
+  cudaStream_t stream = static_cast<cudaStream_t>(bp5_context_stream(b200::Context::get()));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int reps = 10;
+  float ms_user = 0.f, ms_lib = 0.f;
+  for (int w = 0; w < 2; ++w) { user_op.vmult(yu, bu); lib_op.vmult(yl, bl); }
+  cudaEventRecord(e0, stream);
+  for (int i = 0; i < reps; ++i) user_op.vmult(yu, bu);
+  cudaEventRecord(e1, stream); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_user, e0, e1);
+  cudaEventRecord(e0, stream);
+  for (int i = 0; i < reps; ++i) lib_op.vmult(yl, bl);
+  cudaEventRecord(e1, stream); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_lib, e0, e1);
+  double bytes_vmult = 0., bytes_cg = 0.;
+  b200::check(bp5_operator_algorithmic_bytes(lib_op.handle(), &bytes_vmult, &bytes_cg));
+  std::vector<double> a, c;
+  yu.copy_to_host(a); yl.copy_to_host(c);
+  std::cout << std::setprecision(8) << "{\"degree\": " << fe_degree << ", \"cells\": " << nc << ", \"dofs\": " << dof_handler.n_dofs()
+            << ", \"user_functor_vmult_ms\": " << ms_user / reps << ", \"library_vmult_ms\": " << ms_lib / reps
+            << ", \"algorithmic_bytes_per_vmult\": " << bytes_vmult << ", \"rel_diff\": " << rel_diff(a, c) << "}" << std::endl;
+  return rel_diff(a, c) <= 1e-12 ? 0 : 1;
+}
+
 int main(int argc, char *argv[]) {
   try {
+    if (argc > 3 && std::strcmp(argv[1], "bench") == 0) {
+      const unsigned int nc = std::atoi(argv[3]);
+      switch (std::atoi(argv[2])) {
+        case 4: return run_bench<3, 4>(nc);
+        case 6: return run_bench<3, 6>(nc);
+        default: throw ExcMessage("bench: degree 4 or 6");
+      }
+    }
     const int degree = argc > 1 ? std::atoi(argv[1]) : 4;
     const bool collocation = argc > 2 && std::strcmp(argv[2], "gll") == 0;
     std::vector<unsigned int> cells(3, 3);
@@ -354,13 +454,17 @@ int main(int argc, char *argv[]) {
       if (argc > 3 + d) cells[d] = std::atoi(argv[3 + d]);
     const double eps = argc > 6 ? std::atof(argv[6]) : 0.1;
     const double cell_edge = argc > 7 ? std::atof(argv[7]) : 1.0;
+    const std::string dump_prefix = argc > 8 ? argv[8] : "";     // write the vectors as raw doubles: <prefix><name>.f64
     switch (degree) {
-      case 2: return run<3, 2>(collocation, cells, eps, cell_edge);
-      case 3: return run<3, 3>(collocation, cells, eps, cell_edge);
-      case 4: return run<3, 4>(collocation, cells, eps, cell_edge);
-      case 5: return run<3, 5>(collocation, cells, eps, cell_edge);
-      case 6: return run<3, 6>(collocation, cells, eps, cell_edge);
-      default: throw ExcMessage("degree must be 2..6");
+      case 1: return run<3, 1>(collocation, cells, eps, cell_edge, dump_prefix);
+      case 2: return run<3, 2>(collocation, cells, eps, cell_edge, dump_prefix);
+      case 3: return run<3, 3>(collocation, cells, eps, cell_edge, dump_prefix);
+      case 4: return run<3, 4>(collocation, cells, eps, cell_edge, dump_prefix);
+      case 5: return run<3, 5>(collocation, cells, eps, cell_edge, dump_prefix);
+      case 6: return run<3, 6>(collocation, cells, eps, cell_edge, dump_prefix);
+      case 7: return run<3, 7>(collocation, cells, eps, cell_edge, dump_prefix);
+      case 8: return run<3, 8>(collocation, cells, eps, cell_edge, dump_prefix);
+      default: throw ExcMessage("degree must be 1..8");
     }
   } catch (std::exception &exc) {
     std::cerr << "Exception on processing: " << std::endl << exc.what() << std::endl << "Aborting!" << std::endl;

@@ -216,6 +216,11 @@ typedef struct bp5_matrix_free_data {
   double co_shape_gradients[81];
 } bp5_matrix_free_data_t;
 int bp5_operator_matrix_free_data(bp5_operator_t op, bp5_matrix_free_data_t *out);
+/* The same arrays for ONE of the eight parity colours of the cells (colour = px + 2 py + 4 pz, cells with
+ * cx % 2 == px, ... in x-fastest order): cells of a colour share no DoF, so a cell loop over one colour may add
+ * into dst with plain stores -- MatrixFree::AdditionalData::use_coloring / get_data(color) [UPSTREAM],
+ * bp5/fe_evaluation_gl.h:176-177.  n_cells is that colour's cell count (0: nothing allocated). */
+int bp5_operator_matrix_free_data_colored(bp5_operator_t op, int color, bp5_matrix_free_data_t *out);
 
 /* ---- partitioned meshes: halo exchange and stepwise CG -------------------- */
 /* Message shapes of update_ghost_values / compress(add) [UPSTREAM, inside cell_loop,

@@ -150,7 +150,10 @@ template <int dim, typename Number = double> class MatrixFree {
               const AdditionalData &additional_data = AdditionalData()) {
     if (mapping.degree != dof_handler.degree) throw ExcMessage("MappingQGeneric degree must equal fe_degree");
     if (quad.n_points_1d != dof_handler.degree + 1) throw ExcMessage("n_q_points_1d must be fe_degree + 1");
-    if (additional_data.use_coloring) throw ExcMessage("colouring is not implemented (atomics only)");
+    // the ghost exchange of a partitioned mesh happens behind the library operator (BP5::PoissonOperator on a
+    // communicator); this generic path drives one block, where the flag has nothing to overlap
+    (void)additional_data.overlap_communication_computation;
+    use_coloring = additional_data.use_coloring;
     bp5_operator_destroy(op); op = nullptr;
     const Triangulation<dim> &t = dof_handler.get_triangulation();
     bp5_problem_t pr{};
@@ -179,9 +182,30 @@ template <int dim, typename Number = double> class MatrixFree {
       data.shape_values[i] = md.shape_values[i];
       data.co_shape_gradients[i] = md.co_shape_gradients[i];
     }
+    n_colors = 1;
+    if (use_coloring) {
+      // eight parity colours; each one has its own arrays like deal.II's per-colour Data, row_start counts
+      // the cells of the colours before it (local_q_point_id adds it, step-64/step-64.cu:208)
+      n_colors = 8;
+      unsigned int row_start = 0;
+      for (int c = 0; c < 8; ++c) {
+        b200::check(bp5_operator_matrix_free_data_colored(op, c, &md));
+        color_data[c] = data;
+        color_data[c].q_points = reinterpret_cast<Point<dim, Number> *>(md.q_points);
+        color_data[c].local_to_global = md.local_to_global;
+        color_data[c].inv_jacobian = md.inv_jacobian;
+        color_data[c].JxW = md.JxW;
+        color_data[c].n_cells = md.n_cells;
+        color_data[c].constraint_mask = md.constraint_mask;
+        color_data[c].row_start = row_start;
+        color_data[c].use_coloring = true;
+        row_start += md.n_cells * md.padding_length;
+      }
+    }
   }
 
-  Data get_data(unsigned int /*color*/ = 0) const { return data; }
+  unsigned int n_colors_used() const { return (unsigned int)n_colors; }
+  Data get_data(unsigned int color = 0) const { return use_coloring ? color_data[color] : data; }
   bp5_operator_t handle() const { return op; }
   cudaStream_t stream() const { return static_cast<cudaStream_t>(bp5_context_stream(b200::Context::get())); }
 
@@ -202,6 +226,9 @@ template <int dim, typename Number = double> class MatrixFree {
  private:
   bp5_operator_t op = nullptr;
   Data data{};
+  Data color_data[8]{};
+  bool use_coloring = false;
+  int n_colors = 1;
   int n_q_points_1d = 0;
 };
 
@@ -254,9 +281,20 @@ void MatrixFree<dim, Number>::cell_loop(const Functor &func, const VectorType &s
   if ((int)Functor::n_dofs_1d != n_q_points_1d) throw ExcMessage("functor degree does not match MatrixFree::reinit");
   const dim3 block(Functor::n_dofs_1d, Functor::n_dofs_1d, Functor::n_dofs_1d);
   // no ghost exchange around the kernel: this path handles one block (one GPU)
-  internal::apply_kernel_shmem<dim, Number, Functor>
-      <<<data.n_cells, block, 0, stream()>>>(func, data, src.get_values(), dst.get_values());
-  b200::check_cuda(cudaGetLastError(), "apply_kernel_shmem launch");
+  if (use_coloring) {
+    // one launch per colour, in order: within a colour no two cells touch the same DoF (plain += in
+    // distribute_local_to_global), the colours add in a fixed order -> bitwise reproducible results
+    for (int c = 0; c < 8; ++c) {
+      if (color_data[c].n_cells == 0) continue;
+      internal::apply_kernel_shmem<dim, Number, Functor>
+          <<<color_data[c].n_cells, block, 0, stream()>>>(func, color_data[c], src.get_values(), dst.get_values());
+      b200::check_cuda(cudaGetLastError(), "apply_kernel_shmem launch");
+    }
+  } else {
+    internal::apply_kernel_shmem<dim, Number, Functor>
+        <<<data.n_cells, block, 0, stream()>>>(func, data, src.get_values(), dst.get_values());
+    b200::check_cuda(cudaGetLastError(), "apply_kernel_shmem launch");
+  }
   dst.mark_modified();
 }
 
@@ -265,8 +303,16 @@ template <typename Functor>
 void MatrixFree<dim, Number>::evaluate_coefficients(Functor func) const {
   if ((int)Functor::n_dofs_1d != n_q_points_1d) throw ExcMessage("functor degree does not match MatrixFree::reinit");
   const dim3 block(Functor::n_dofs_1d, Functor::n_dofs_1d, Functor::n_dofs_1d);
-  internal::evaluate_coeff<dim, Number, Functor><<<data.n_cells, block, 0, stream()>>>(func, data);
-  b200::check_cuda(cudaGetLastError(), "evaluate_coeff launch");
+  if (use_coloring) {
+    for (int c = 0; c < 8; ++c) {
+      if (color_data[c].n_cells == 0) continue;
+      internal::evaluate_coeff<dim, Number, Functor><<<color_data[c].n_cells, block, 0, stream()>>>(func, color_data[c]);
+      b200::check_cuda(cudaGetLastError(), "evaluate_coeff launch");
+    }
+  } else {
+    internal::evaluate_coeff<dim, Number, Functor><<<data.n_cells, block, 0, stream()>>>(func, data);
+    b200::check_cuda(cudaGetLastError(), "evaluate_coeff launch");
+  }
   b200::check_cuda(cudaStreamSynchronize(stream()), "evaluate_coefficients");
 }
 

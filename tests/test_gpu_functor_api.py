@@ -15,10 +15,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CELLS, EPS = (3, 2, 2), 0.1
 
 
-def _run(degree, quad):
+def _run(degree, quad, dump_dir=None):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")], stdout=subprocess.DEVNULL)
-    out = subprocess.run([os.path.join(ROOT, "build", "examples", "bp5_functors"), str(degree), quad,
-                          *[str(c) for c in CELLS], str(EPS)], capture_output=True, text=True, timeout=600)
+    cmd = [os.path.join(ROOT, "build", "examples", "bp5_functors"), str(degree), quad, *[str(c) for c in CELLS], str(EPS)]
+    if dump_dir is not None:
+        cmd += ["1.0", os.path.join(str(dump_dir), "v_")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert out.stdout.strip().endswith("OK"), out.stdout[-3000:]
     vals = {}
@@ -29,11 +31,19 @@ def _run(degree, quad):
     return vals
 
 
-@pytest.mark.parametrize("degree", [2, 3, 4, 6])
+def _rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("degree", range(1, 9))
 @pytest.mark.parametrize("quad", ["gauss", "gll"])
-def test_user_functors_match_library_and_oracle(degree, quad):
+def test_user_functors_match_library_and_oracle(degree, quad, tmp_path):
     import oracle as O
-    v = _run(degree, quad)
+    v = _run(degree, quad, tmp_path)
+    # use_coloring mode: eight colour passes with plain stores, bitwise reproducible
+    assert v["bp5_colored_bitwise_reproducible"] == 1
+    if quad == "gauss":
+        assert v["helmholtz_colored_bitwise_reproducible"] == 1
     q = O.GLL if quad == "gll" else O.GAUSS
     m = O.OracleMesh(degree, CELLS, quad=q, deform=1, eps=EPS)
     assert v["n_dofs"] == m.n_dofs
@@ -47,8 +57,12 @@ def test_user_functors_match_library_and_oracle(degree, quad):
     assert abs(v["bp5_merged_its_user"] - its) <= 1                               # same count +-1
     assert abs(v["bp5_standard_its_user"] - its) <= 1
     assert v["bp5_norm_x"] == pytest.approx(np.linalg.norm(x), rel=1e-7)
+    # the vectors themselves, not only their norms
+    assert _rel(np.fromfile(tmp_path / "v_bp5_Ab.f64"), Ab) <= 1e-12
+    assert _rel(np.fromfile(tmp_path / "v_bp5_x.f64"), x) <= 1e-7
     if quad == "gauss":
         Hb = m.vmult(b, kind=O.HELMHOLTZ)
+        assert _rel(np.fromfile(tmp_path / "v_helmholtz_Ab.f64"), Hb) <= 1e-12
         assert v["helmholtz_norm_Ab"] == pytest.approx(np.linalg.norm(Hb), rel=1e-12)
         xh, its_h, _, _, _ = m.cg(b, kind=O.HELMHOLTZ, variant=1, control=1, tol=1e-12 * np.linalg.norm(b),
                                   max_its=m.n_dofs)
