@@ -51,6 +51,41 @@ def parity_leg(args, dc, DistributedPoisson, local_rank, quad_id):
     return out
 
 
+def strong_leg(args, dc, DistributedPoisson, local_rank, quad_id, cells, steps, torch, dist, max_its):
+    """A short STRONG-scaling measurement on the same ranks: one cells^3 mesh split over all GPUs, merged CG,
+    device-timed like the headline (max over ranks).  Reported under "variants" of the N>1 line; the N=1 line of
+    the same mesh is the denominator (cells = --cells: the headline's own N=1 workload)."""
+    try:
+        P = DistributedPoisson(args.degree, (cells,) * 3, quadrature=quad_id, device=local_rank, transport=args.transport,
+                               global_cells=(cells,) * 3)
+        op = P.op
+        b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+        op.assemble_rhs(b)
+        control = dc.IterationNumberControl(max_its, 1e-6 * P.l2_norm(b))
+        op.do_zero_out = False
+        for _ in range(2):
+            x.set(0.0); P.cg_solve(x, b, control)
+        P.ctx.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(P.stream)
+        its = 0
+        for _ in range(steps):
+            x.set(0.0); P.cg_solve(x, b, control)
+            its += control.last_step()
+        e1.record(P.stream); e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out = {"workload": f"strong scaling: BP5 p={args.degree}, {cells}^3 cells = {P.n_global} DoFs in total over "
+                           f"{P.part.grid[0]}x{P.part.grid[1]}x{P.part.grid[2]} blocks",
+               "dofs_global": P.n_global, "dofs_per_gpu": P.n_global / dist.get_world_size(),
+               "value": P.n_global * its / float(t.item()) / 1e9, "unit": "GDoF*it/s",
+               "ms_per_iteration": float(t.item()) / max(1, its) * 1e3, "x_l2": P.l2_norm(x)}
+        b.close(); x.close(); P.close()
+        return out
+    except Exception as e:                        # a side measurement must not cost the headline line
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def run(args):
     import numpy as np
     import torch
@@ -168,6 +203,15 @@ def run(args):
     e2e_secs = float(t.item())
 
     bytes_vmult, bytes_cg = op.algorithmic_bytes()
+    launches_per_it = launches / max(1, its_total)
+    variants = {}
+    if not args.no_variants and not strong:
+        # the weak-scaling vectors go first: the strong-scaling legs need their own blocks
+        ctx.synchronize()
+        variants["strong_same_mesh_as_n1"] = strong_leg(args, dc, DistributedPoisson, local_rank, quad_ids[args.quadrature],
+                                                        args.cells, 2, torch, dist, single.MAX_ITS)
+        variants["strong_small_mesh"] = strong_leg(args, dc, DistributedPoisson, local_rank, quad_ids[args.quadrature],
+                                                   max(8, args.cells // 2), 3, torch, dist, single.MAX_ITS)
     if rank == 0:
         n_glob = P.n_global
         k_s = float(slow[0])
@@ -198,7 +242,8 @@ def run(args):
                     "h2d_bytes_per_step": n_loc * 8 * world, "d2h_bytes_per_step": n_loc * 8 * world,
                     "steps": e2e_steps,
                     "api": "per rank: pinned host b -> device, zero initial guess, DistributedPoisson.cg_solve, x -> host"},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "launches_per_iteration": launches_per_it,
+            "variants": variants,
             "roofline": {"bound": "hbm", "kernel": op.kernel_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": bytes_vmult,
                          "avg_launch_ms": k_s * 1e3, "launches_timed": k_launches, "applications_timed": prof_its,

@@ -28,6 +28,7 @@ static int launch_otf(bp5_operator_t op, double *dst, const double *src, double 
   prm.src = src; prm.dst = dst;
   prm.tile_begin = which == 2 ? op->n_boundary_tiles : 0;
   prm.n_tiles = which == 1 ? op->n_boundary_tiles : op->n_tiles;
+  if (op->range_begin >= 0) { prm.tile_begin = op->range_begin; prm.n_tiles = op->range_end; }   // explicit tile range
   prm.sy = op->od[0]; prm.sz = op->od[0] * op->od[1];
   prm.skip = op->skip_flag;
   prm.dot_partials = dot_partials;

@@ -775,11 +775,25 @@ int cg_solve_peer(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_
     else launch_update<3>(has_diag, grid, s, st, d, g, h, x->d, diag, cb.rr, n);
     ctx->launches++;
     if (op->n_ghost) BP5_CUDA(cudaMemsetAsync(h + n, 0, sizeof(double) * op->n_ghost, s));
-    if ((rc = peer_forward(op, d))) return rc;
-    if ((rc = apply_cell_loop(op, h, d, true, cb.ph, 1))) return rc;
-    const int grid_b = op->apply_grid;
+    // Both halves of the halo exchange hide behind cells that need no ghost data (MatrixFree's
+    // overlap_communication_computation, bp5/step-64.cu:241): the upper faces of d leave for the neighbours, the
+    // first half of the interior tiles runs, then the boundary tiles (they wait for the ghosts), the ghost
+    // contributions leave, the second half of the interior runs, then the contributions that arrived are added.
+    if ((rc = peer_forward(op, d, /*wait=*/false))) return rc;
+    const long long n_int = op->n_tiles - op->n_boundary_tiles, half = op->n_boundary_tiles + n_int / 2;
+    op->range_begin = op->n_boundary_tiles; op->range_end = half;
+    rc = apply_cell_loop(op, h, d, true, cb.ph);
+    op->range_begin = op->range_end = -1;
+    if (rc) return rc;
+    const int grid_a = op->apply_grid;
+    if ((rc = peer_wait_forward(op))) return rc;
+    if ((rc = apply_cell_loop(op, h, d, true, cb.ph + grid_a, 1))) return rc;
+    const int grid_b = grid_a + op->apply_grid;
     if ((rc = peer_reverse(op, h))) return rc;
-    if ((rc = apply_cell_loop(op, h, d, true, cb.ph + grid_b, 2))) return rc;
+    op->range_begin = half; op->range_end = op->n_tiles;
+    rc = apply_cell_loop(op, h, d, true, cb.ph + grid_b);
+    op->range_begin = op->range_end = -1;
+    if (rc) return rc;
     const int n_ph = grid_b + op->apply_grid;
     // boundary + interior partials + the Dirichlet correction share cb.ph: the next buffer (r.r partials) must
     // never be reached
@@ -788,9 +802,8 @@ int cg_solve_peer(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_
     if (n_corr && (rc = apply_copy_constrained_dot(op, h, d, cb.ph + n_ph))) return rc;
     launch_dots<false>(has_diag, /*lean=*/true, s, st, d, g, h, diag, n, cb, sums, n_ph + n_corr, (int)grid);
     ctx->launches++;
-    if ((rc = peer_allreduce(op, sums, sums + 8, 7, true))) return rc;
-    cg_scalars_kernel<<<1, 32, 0, s>>>(st, sums + 8, cb.hist);
-    ctx->launches++;
+    // all-rank sum of the seven scalars; the same one-block kernel then runs the scalar recurrences
+    if ((rc = peer_allreduce(op, sums, sums + 8, 7, true, st, cb.hist))) return rc;
     return BP5_OK;
   };
   rc = run_iterations(op, st, max_its, enqueue);

@@ -194,10 +194,12 @@ int halo_unpack_add(bp5_operator_t op, double *vec, const double *recvbuf);
 int peer_export(bp5_operator_t op, int rank, int world, bp5_peer_info_t *out);
 int peer_connect(bp5_operator_t op, const bp5_peer_info_t *all, const int *upper_rank, const int *lower_rank);
 void peer_destroy(bp5_operator_t op);
-int peer_forward(bp5_operator_t op, const double *vec);
+int peer_forward(bp5_operator_t op, const double *vec, bool wait = true);   // wait: also wait for the lower neighbours' data
+int peer_wait_forward(bp5_operator_t op);
 int peer_reverse(bp5_operator_t op, const double *vec);
 int peer_wait_add(bp5_operator_t op, double *vec);
-int peer_allreduce(bp5_operator_t op, const double *local_dev, double *out_dev, int n_vals, bool honour_skip);
+int peer_allreduce(bp5_operator_t op, const double *local_dev, double *out_dev, int n_vals, bool honour_skip,
+                   void *cg_state = nullptr, double *history = nullptr);
 int peer_allreduce_host(bp5_operator_t op, double *vals, int n);
 int peer_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src);
 int peer_world_size(bp5_operator_t op);

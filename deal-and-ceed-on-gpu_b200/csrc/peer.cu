@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "cg_state.cuh"
 #include "common.h"
 
 namespace bp5 {
@@ -201,11 +202,14 @@ struct PeerSumPtrs {
 
 // One block.  Stores `n_vals` (<= 8) local sums into slot [parity][rank] of every rank's mailbox, raises the
 // flags, waits for everybody's, and leaves the rank-ordered total in out[0..n_vals).
+// cg != nullptr: the seven sums of a merged-CG iteration -- thread 0 goes on with the scalar recurrences
+// (solver.h:497-533) right here instead of in a kernel of its own.
 __global__ void peer_allreduce_kernel(PeerSumPtrs pp, const double *__restrict__ local, double *__restrict__ out,
                                       int n_vals, int rank, int world, unsigned *epoch_word, unsigned *err,
-                                      const int *skip) {
+                                      const int *skip, CgState *cg, double *history) {
   if (skip != nullptr && *skip != 0) return;
   __shared__ int epoch_sh;
+  __shared__ double total_sh[8];
   if (threadIdx.x == 0) epoch_sh = (int)(++*epoch_word);
   __syncthreads();
   const int epoch = epoch_sh;
@@ -228,6 +232,16 @@ __global__ void peer_allreduce_kernel(PeerSumPtrs pp, const double *__restrict__
     const double *mb = pp.mailbox[rank] + (long long)parity * kPeerMaxWorld * 8;
     for (int r = 0; r < world; ++r) s += __ldcg(mb + r * 8 + t);     // rank order: identical on every rank
     out[t] = s;
+    total_sh[t] = s;
+  }
+  if (cg != nullptr) {
+    __syncthreads();
+    if (t == 0) {
+      double q[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) q[j] = total_sh[j];
+      cg_scalar_step(cg, q, history);
+    }
   }
 }
 
@@ -357,7 +371,18 @@ void peer_destroy(bp5_operator_t op) {
 }
 
 // update_ghost_values(d), sender half + receiver wait
-int peer_forward(bp5_operator_t op, const double *vec_owned_of_d) {
+int peer_wait_forward(bp5_operator_t op) {
+  PeerState *ps = static_cast<PeerState *>(op->peer);
+  if (op->n_ghost == 0) return BP5_OK;
+  const PeerSendGeom g = make_geom(op, ps);
+  peer_wait_forward_kernel<<<1, 32, 0, op->ctx->stream>>>(g, flag_ptr(ps->buf, ps->lay), ps->ticket + 2, ps->ticket + 4,
+                                                         op->skip_flag);
+  BP5_CHECK_LAUNCH();
+  op->ctx->launches++;
+  return BP5_OK;
+}
+
+int peer_forward(bp5_operator_t op, const double *vec_owned_of_d, bool wait) {
   PeerState *ps = static_cast<PeerState *>(op->peer);
   const PeerSendGeom g = make_geom(op, ps);
   cudaStream_t s = op->ctx->stream;
@@ -366,12 +391,7 @@ int peer_forward(bp5_operator_t op, const double *vec_owned_of_d) {
                                                            op->skip_flag);
   BP5_CHECK_LAUNCH();
   op->ctx->launches++;
-  if (op->n_ghost > 0) {
-    peer_wait_forward_kernel<<<1, 32, 0, s>>>(g, flag_ptr(ps->buf, ps->lay), ps->ticket + 2, ps->ticket + 4, op->skip_flag);
-    BP5_CHECK_LAUNCH();
-    op->ctx->launches++;
-  }
-  return BP5_OK;
+  return wait ? peer_wait_forward(op) : BP5_OK;
 }
 
 // compress(add)(h), sender half
@@ -400,7 +420,8 @@ int peer_wait_add(bp5_operator_t op, double *vec) {
 }
 
 // sum of n_vals doubles over all ranks, device to device
-int peer_allreduce(bp5_operator_t op, const double *local_dev, double *out_dev, int n_vals, bool honour_skip) {
+int peer_allreduce(bp5_operator_t op, const double *local_dev, double *out_dev, int n_vals, bool honour_skip,
+                   void *cg_state, double *history) {
   PeerState *ps = static_cast<PeerState *>(op->peer);
   BP5_REQUIRE(n_vals >= 1 && n_vals <= 8, "1..8 values");
   PeerSumPtrs pp{};
@@ -413,7 +434,8 @@ int peer_allreduce(bp5_operator_t op, const double *local_dev, double *out_dev, 
   const int threads = ((ps->world * 8 + 31) / 32) * 32;
   peer_allreduce_kernel<<<1, threads, 0, op->ctx->stream>>>(pp, local_dev, out_dev, n_vals, ps->rank, ps->world,
                                                            ps->ticket + 3, ps->ticket + 4,
-                                                           honour_skip ? op->skip_flag : nullptr);
+                                                           honour_skip ? op->skip_flag : nullptr,
+                                                           static_cast<CgState *>(cg_state), history);
   BP5_CHECK_LAUNCH();
   op->ctx->launches++;
   return BP5_OK;
@@ -449,7 +471,7 @@ int peer_allreduce_host(bp5_operator_t op, double *vals, int n) {
   cudaStream_t s = op->ctx->stream;
   BP5_CUDA(cudaMemcpyAsync(ps->scratch, vals, sizeof(double) * n, cudaMemcpyHostToDevice, s));
   int rc;
-  if ((rc = peer_allreduce(op, ps->scratch, ps->scratch + 8, n, false))) return rc;
+  if ((rc = peer_allreduce(op, ps->scratch, ps->scratch + 8, n, false, nullptr, nullptr))) return rc;
   BP5_CUDA(cudaMemcpyAsync(vals, ps->scratch + 8, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
   BP5_CUDA(cudaStreamSynchronize(s));
   return peer_check(op);
