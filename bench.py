@@ -290,6 +290,29 @@ def measure_helmholtz(dc, torch, ctx, stream):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
+def measure_affine_otf(dc, torch, ctx, stream, args, hbm_peak):
+    """Geometry on the fly on the headline's (undeformed) mesh: no metric stream at all, the kernel forms
+    G = w_q diag(hy hz / hx, ...) from three constants (bp5_problem_t.geometry_mode = BP5_GEOM_ON_THE_FLY, affine fast
+    path).  The headline stays on the stored metric tensor (north star, general meshes); this variant shows what
+    recomputation buys where it is cheap.  Reported under "variants"; never fatal."""
+    try:
+        op = dc.PoissonOperator(ctx, dc.make_problem(args.degree, (args.cells,) * 3, quadrature=dc.QUAD_GLL,
+                                                     geometry_mode=dc.GEOM_ON_THE_FLY))
+        r = measure_solver(dc, torch, ctx, stream, op, max(1, min(args.steps, 2)), 1)
+        bytes_vmult, bytes_cg = op.algorithmic_bytes()
+        k_s = r["kernel_ms"] * 1e-3 / max(1, r["kernel_launches"])
+        out = {"workload": f"BP5 p={args.degree} GLL, {args.cells}^3 cells, geometry on the fly (affine fast path), merged CG",
+               "kernel": op.kernel_name, "value": r["n"] * r["its_total"] / r["secs"] / 1e9, "unit": UNIT,
+               "ms_per_step": r["secs"] / max(1, min(args.steps, 2)) * 1e3, "cell_kernel_ms": k_s * 1e3,
+               "cell_kernel_gdofs": r["n"] / k_s / 1e9, "algorithmic_bytes_per_launch": bytes_vmult,
+               "cell_kernel_frac_of_hbm": bytes_vmult / k_s / 1e9 / hbm_peak,
+               "note": "16 B/DoF: this kernel is bound by the shared-memory pipe and fp64 issue, not by HBM", "x_l2": r["xnorm"]}
+        op.close()
+        return out
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def measure_user_functor(hbm_peak):
     """What staying on the reference's device-functor API costs (examples/bp5_functors.cu bench mode): the user-written
     LocalPoissonOperator on CUDAWrappers::MatrixFree / FEEvaluationGL (one CTA per cell, deal.II-layout arrays) against
@@ -353,9 +376,11 @@ def run_b200(args):
             r["e2e"] = measure_e2e(dc, torch, ctx, stream, op, max(1, min(args.steps, 3)), args.warmup)
         results[qname] = r
         op.close()
-    helm = None
+    helm = affine = None
     if not args.no_variants:
         helm = measure_helmholtz(dc, torch, ctx, stream)
+        if not args.deformation:
+            affine = measure_affine_otf(dc, torch, ctx, stream, args, hbm_peak)
     ctx.close()
 
     def summarize(r):
@@ -426,6 +451,8 @@ def run_b200(args):
                            "cg_frac": cg_fracs(r)[0], "cg_frac_64B_model": cg_fracs(r)[1], "x_l2": r["xnorm"]}
     if helm is not None:
         variants["helmholtz_config2"] = helm
+    if affine is not None:
+        variants["geometry_on_the_fly_affine"] = affine
     if not args.no_variants:
         variants["user_functor"] = measure_user_functor(hbm_peak)
     out["variants"] = variants

@@ -92,8 +92,9 @@ int bp5_operator_create(bp5_context_t ctx, const bp5_problem_t *pr, bp5_operator
   BP5_REQUIRE(pr->operator_kind == BP5_OP_POISSON || pr->operator_kind == BP5_OP_HELMHOLTZ, "unknown operator");
   BP5_REQUIRE(pr->geometry_mode == BP5_GEOM_STORED || pr->geometry_mode == BP5_GEOM_ON_THE_FLY, "unknown geometry mode");
   if (pr->geometry_mode == BP5_GEOM_ON_THE_FLY &&
-      (pr->quadrature != BP5_QUAD_GLL || pr->operator_kind != BP5_OP_POISSON)) {
-    set_error("on-the-fly geometry is implemented for the Poisson operator with Gauss-Lobatto collocation");
+      (pr->operator_kind != BP5_OP_POISSON || (pr->quadrature != BP5_QUAD_GLL && pr->deformation != 0))) {
+    set_error("on-the-fly geometry is implemented for the Poisson operator: Gauss-Lobatto collocation on any mesh, "
+              "both quadratures on undeformed (affine) meshes");
     return BP5_ERR_UNSUPPORTED;
   }
   BP5_REQUIRE(pr->deformation == 0 || pr->deformation == 1, "unknown deformation");
@@ -324,7 +325,8 @@ int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *per_vmult, double 
   // CG: read {x,r,p,h,diag} + write {x,r,p,h} = 72, plus the metric.
   const double n3 = (double)op->n * op->n * op->n;
   // stored metric: 8 bytes per plane per quadrature point; on the fly: three coordinates per local DoF
-  const double metric = op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY
+  const double metric = op->metric_path == 3 ? 0.0        // affine mesh, geometry on the fly: three constants
+                        : op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY
                             ? 24.0 * (double)(op->n_owned + op->n_ghost)
                             : 8.0 * op->metric_planes * n3 * (double)op->n_cells;
   if (per_vmult) *per_vmult = 16.0 * (double)op->n_owned + metric;

@@ -31,16 +31,21 @@ int apply_choose(bp5_operator_t op) {
   op->tile_doubles = ((int64_t)cpt * op->metric_planes * n3 + 1) & ~(int64_t)1;
   // how the metric reaches the quadrature phase (ApplyCfg::MLOAD); BP5_MLOAD overrides for tuning runs
   op->metric_path = 0;
+  // geometry on the fly on an undeformed (axis-parallel) mesh: one constant Jacobian, no coordinate gathers
+  const bool otf_affine = op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY && op->prob.deformation == 0 &&
+                          op->prob.operator_kind == BP5_OP_POISSON;
+  if (otf_affine) { op->metric_path = 3; cpt = cells_per_tile_for(op->p); op->cells_per_tile = cpt; operator_plan_tiles(op); }
 #ifdef BP5_ENABLE_MLOAD
   if (const char *mv = getenv("BP5_MLOAD")) op->metric_path = atoi(mv);
 #endif
-  BP5_REQUIRE(op->metric_path >= 0 && op->metric_path <= 2, "BP5_MLOAD must be 0, 1 or 2");
-  static const char *const kPath[3] = {"metric=tma-smem", "metric=ldg-regs", "metric=ldg-regs-ahead"};
+  BP5_REQUIRE(op->metric_path >= 0 && op->metric_path <= 3, "BP5_MLOAD must be 0, 1 or 2");
+  static const char *const kPath[4] = {"metric=tma-smem", "metric=ldg-regs", "metric=ldg-regs-ahead",
+                                       "geometry=on-the-fly(affine: constant Jacobian)"};
   char name[160];
   snprintf(name, sizeof(name), "bp5_apply_kernel<p=%d,%s,%s,cells_per_tile=%d,%s>", op->p,
            op->prob.quadrature == BP5_QUAD_GLL ? "gll-collocation" : "gauss",
            op->prob.operator_kind == BP5_OP_HELMHOLTZ ? "helmholtz" : "poisson", cpt, kPath[op->metric_path]);
-  if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY)
+  if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY && !otf_affine)
     snprintf(name, sizeof(name), "bp5_apply_otf_kernel<p=%d,gll-collocation,poisson,cells_per_tile=%d,geometry=on-the-fly>", op->p, cpt);
   op->kernel_name = name;
   return BP5_OK;
@@ -81,6 +86,12 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
   if (prm.n_tiles <= prm.tile_begin) { op->apply_grid = 0; return BP5_OK; }
   prm.skip = op->skip_flag;
   prm.dot_partials = dot_partials;
+  {
+    double hc[3];
+    for (int d = 0; d < 3; ++d) hc[d] = (op->prob.upper[d] - op->prob.lower[d]) / op->prob.cells[d];
+    prm.aff[0] = hc[1] * hc[2] / hc[0]; prm.aff[1] = hc[0] * hc[2] / hc[1]; prm.aff[2] = hc[0] * hc[1] / hc[2];
+    for (int q = 0; q < N; ++q) prm.wq[q] = op->tab.wq[q];
+  }
   fill_kernel_tables<N>(prm.tab, op->tab.B, op->tab.Dt);
   long long grid = (long long)blocks_per_sm * op->ctx->sm_count;
   if (grid > prm.n_tiles - prm.tile_begin) grid = prm.n_tiles - prm.tile_begin;
@@ -116,8 +127,20 @@ static int launch_pm(bp5_operator_t op, double *dst, const double *src, int mode
 #undef BP5_LAUNCH_MODE
 }
 
+// geometry on the fly, affine mesh (MLOAD = 3): Poisson only
+template <int P>
+static int launch_affine(bp5_operator_t op, double *dst, const double *src, int mode, double *dp, int which) {
+  const bool gll = op->prob.quadrature == BP5_QUAD_GLL;
+#define BP5_LAUNCH_AFF(M) (gll ? launch<P, 1, 0, M, 3>(op, dst, src, dp, which) : launch<P, 0, 0, M, 3>(op, dst, src, dp, which))
+  if (mode == 2) return BP5_LAUNCH_AFF(2);
+  if (mode == 1) return BP5_LAUNCH_AFF(1);
+  return BP5_LAUNCH_AFF(0);
+#undef BP5_LAUNCH_AFF
+}
+
 template <int P>
 static int launch_p(bp5_operator_t op, double *dst, const double *src, int mode, double *dp, int which) {
+  if (op->metric_path == 3) return launch_affine<P>(op, dst, src, mode, dp, which);
 #ifdef BP5_ENABLE_MLOAD   // tuning builds: metric straight to registers (measured slower, profiles/r1_v3_notes.md)
   if (op->metric_path == 1) return launch_pm<P, 1>(op, dst, src, mode, dp, which);
   if (op->metric_path == 2) return launch_pm<P, 2>(op, dst, src, mode, dp, which);
@@ -133,7 +156,8 @@ int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool over
                     int which) {
   BP5_REQUIRE(dot_partials == nullptr || overwrite_interior, "the fused dot product needs the overwrite kernel");
   const int mode = dot_partials ? 2 : (overwrite_interior ? 1 : 0);
-  if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY) return apply_cell_loop_otf(op, dst, src, mode, dot_partials, which);
+  if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY && op->metric_path != 3)
+    return apply_cell_loop_otf(op, dst, src, mode, dot_partials, which);
   switch (op->p) {
     case 1: return launch_p<1>(op, dst, src, mode, dot_partials, which);
     case 2: return launch_p<2>(op, dst, src, mode, dot_partials, which);

@@ -108,6 +108,11 @@ struct ApplyParams {
   const int *skip;        // optional device flag: non-zero => nothing to do (CG already converged)
   double *dot_partials;   // OVERWRITE == 2: [gridDim.x] per-CTA parts of src . (A src), summed by the CG dots kernel
   KernelTables<N> tab;
+  // MLOAD == 3 (geometry on the fly, affine mesh): G = w_q diag(aff) with aff = (hy hz / hx, hx hz / hy, hx hy / hz)
+  // and the 1D quadrature weights wq.  (Behind `tab`: moving the tables in the parameter bank changes ptxas's
+  // register allocation of the other kernels, p = 7 lost its third CTA per SM.)
+  double aff[3];
+  double wq[N];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -269,7 +274,10 @@ __device__ __forceinline__ void contract_in_regs(double (&w)[N], const double *_
 // MLOAD: how the metric reaches the quadrature phase.
 //   0: one TMA bulk copy per tile into shared memory (mbarrier), read back with LDS;
 //   1: plain streaming loads into registers, issued at the start of the tile;
-//   2: the same, issued one tile ahead (right after the previous quadrature phase).
+//   2: the same, issued one tile ahead (right after the previous quadrature phase);
+//   3: no metric at all -- geometry on the fly on an AFFINE (axis-parallel) mesh: the Jacobian is one constant
+//      diagonal, G = w_q diag(hy hz / hx, hx hz / hy, hx hy / hz) is formed from kernel parameters.
+//      16 bytes per DoF of HBM traffic instead of 16 + 48 r: shared-memory-pipe / fp64 bound.
 // tuning builds may force a minimum number of resident CTAs per SM (-D'BP5_MIN_BLOCKS(P)=...');
 // by default ptxas's own heuristic is kept: an explicit minimum of 1 makes it spend ~50 more registers
 #ifdef BP5_MIN_BLOCKS
@@ -287,7 +295,13 @@ struct ApplyCfg {
   static constexpr uint32_t METRIC_BYTES = METRIC_DOUBLES * 8;
   static constexpr int WORK_DOUBLES = CPT * (2 * L::A_CS + L::B_CS);   // S0, S1 (layout A) and S2 (layout B)
   static constexpr int STAGE_DOUBLES = MLOAD == 0 ? METRIC_DOUBLES : 0;   // shared-memory staging of the metric
-  static constexpr size_t SMEM_BYTES = (size_t)STAGE_DOUBLES * 8 + (size_t)WORK_DOUBLES * 8 + 16;
+  // the mbarrier (8 bytes) goes into the padding word at the end of the first cell's S0 array when the layout
+  // leaves one free, else behind the work arrays: at p = 7 those 16 bytes decide between 2 and 3 CTAs per SM
+  // (3 x (76800 + 1024 reserved) = 233472 bytes = all of an SM's shared memory)
+  static constexpr int A_LAST = (N - 1) * (L::A_S2 + L::A_S1 + 1);           // last used index of a layout-A array
+  static constexpr bool BAR_IN_PAD = L::A_CS - 1 > A_LAST;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGE_DOUBLES * 8 + (size_t)WORK_DOUBLES * 8 + (BAR_IN_PAD ? 0 : 16);
+  static_assert(MLOAD != 3 || PLANES == 6, "the affine fast path is for the Poisson operator");
   static_assert(METRIC_BYTES % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
 };
 
@@ -311,7 +325,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   double *S0 = Gs + Cfg::STAGE_DOUBLES;                              // layout A (home + x-line + y-line readers)
   double *S1 = S0 + CPT * L::A_CS;                                   // layout A (home + x-line)
   double *S2 = S1 + CPT * L::A_CS;                                   // layout B (home + y-line)
-  uint64_t *bar = reinterpret_cast<uint64_t *>(S2 + CPT * L::B_CS);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(Cfg::BAR_IN_PAD ? S0 + L::A_CS - 1 : S2 + CPT * L::B_CS);
 
   if (prm.skip != nullptr && *prm.skip != 0) return;
   const int tid = threadIdx.x;
@@ -354,9 +368,10 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
       }
     }
     __syncthreads();
-  } else {
+  } else if constexpr (MLOAD != 3) {
     policy = make_evict_first_policy();
   }
+  [[maybe_unused]] const double wab = MLOAD == 3 ? prm.wq[a] * prm.wq[b] : 0.0;
   // this thread's column of the metric within a tile: [c][plane][k][b][a]
   const int gcol = c * PLANES * N3 + b * N + a;
   [[maybe_unused]] double greg[N][PLANES];
@@ -475,7 +490,10 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         const int q = (k * N + b) * N + a, wA = hA + k * A2, wB = hB + k * B2;
         const double ur = s1[wA], us = s2[wB], ut = t[k];
         double g0, g1, g2, g3, g4, g5;
-        if constexpr (MLOAD == 0) {
+        if constexpr (MLOAD == 3) {
+          const double w = wab * prm.wq[k];
+          g0 = prm.aff[0] * w; g1 = prm.aff[1] * w; g2 = prm.aff[2] * w; g3 = g4 = g5 = 0.0;
+        } else if constexpr (MLOAD == 0) {
           g0 = gm[q]; g1 = gm[N3 + q]; g2 = gm[2 * N3 + q]; g3 = gm[3 * N3 + q]; g4 = gm[4 * N3 + q]; g5 = gm[5 * N3 + q];
         } else {
           g0 = greg[k][0]; g1 = greg[k][1]; g2 = greg[k][2]; g3 = greg[k][3]; g4 = greg[k][4]; g5 = greg[k][5];

@@ -140,7 +140,7 @@ class PoissonProblem {
     solution_dev.update_ghost_values();
     by_hand = 0.;
     b200::check(bp5_operator_cell_loop(system_matrix_dev->handle(), by_hand.handle(), solution_dev.handle()));
-    by_hand.compress(0);
+    by_hand.compress(VectorOperation::add);
     b200::check(bp5_operator_copy_constrained_values(system_matrix_dev->handle(), by_hand.handle(), solution_dev.handle()));
     by_hand.mark_modified();
     by_hand.add(-1., by_vmult);

@@ -38,6 +38,7 @@
 namespace dealii {
 
 namespace types { using global_dof_index = unsigned int; }
+namespace VectorOperation { enum values { unknown, insert, add }; }
 namespace MemorySpace { struct Host {}; struct CUDA {}; }
 
 struct ExcMessage : std::runtime_error { using std::runtime_error::runtime_error; };
@@ -277,7 +278,8 @@ template <> class Vector<double, MemorySpace::CUDA> {
   // update_ghost_values / compress(VectorOperation::add) [UPSTREAM], requested inside cell_loop at
   // bp5/step-64.cu:241,272-275
   void update_ghost_values() const { if (partitioned()) b200::check(bp5_vector_update_ghost_values(bp5_vector_owner(h), h)); }
-  void compress(int /*VectorOperation::add*/ = 0) {
+  void compress(VectorOperation::values operation = VectorOperation::add) {
+    if (operation != VectorOperation::add) throw ExcMessage("compress: only VectorOperation::add has an exchange here");
     if (partitioned()) b200::check(bp5_vector_compress_add(bp5_vector_owner(h), h));
     is_constant = false;
   }

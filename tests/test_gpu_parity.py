@@ -333,9 +333,45 @@ def test_on_the_fly_geometry_matches_stored_metric_and_oracle(gpu_ctx, p):
         assert relerr(outs[dc.GEOM_ON_THE_FLY], outs[dc.GEOM_STORED]) <= 1e-13
 
 
+@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("quad", [0, 1])
+def test_on_the_fly_geometry_affine_fast_path(gpu_ctx, p, quad):
+    """geometry on the fly on an undeformed mesh: the Jacobian is one constant diagonal, the kernel forms
+    G = w_q diag(hy hz / hx, ...) from three parameters and streams no geometry at all (16 bytes per DoF).  Both
+    quadratures, anisotropic cells, ragged tile counts: == stored metric to 1e-13, == oracle, CG iteration parity."""
+    dc = _dc()
+    import oracle as O
+    cells, upper = (3, 2, 3), (1.5, 2.0, 0.75)
+    m = O.OracleMesh(p, cells, quad=quad, upper=upper)
+    u = np.random.default_rng(20 + p).standard_normal(m.n_dofs)
+    ref = m.vmult(u)
+    outs = {}
+    for mode in (dc.GEOM_STORED, dc.GEOM_ON_THE_FLY):
+        op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=quad, upper=upper, geometry_mode=mode))
+        outs[mode] = _vmult(gpu_ctx, op, u)
+        assert relerr(outs[mode], ref) <= TOL
+        if mode == dc.GEOM_ON_THE_FLY:
+            assert "affine" in op.kernel_name
+            assert op.algorithmic_bytes()[0] == 16.0 * op.n_owned
+            b = op.initialize_dof_vector(); x = op.initialize_dof_vector()
+            op.assemble_rhs(b)
+            bh = b.to_host()
+            tol = 1e-8 * np.linalg.norm(bh)
+            ctl = dc.SolverControl(1000, tol)
+            op.do_zero_out = False
+            dc.SolverCGFullMerge(ctl).solve(op, x, b)
+            xo, its, _, _, _ = m.cg(bh, variant=1, control=1, tol=tol, max_its=1000)
+            assert abs(ctl.last_step() - its) <= 1
+            assert relerr(x.to_host(), xo) <= 1e-7
+            b.close(); x.close()
+        op.close()
+    assert relerr(outs[dc.GEOM_ON_THE_FLY], outs[dc.GEOM_STORED]) <= 1e-13
+
+
 def test_on_the_fly_geometry_rejects_unsupported_combinations(gpu_ctx):
     dc = _dc()
-    for kw in (dict(quadrature=dc.QUAD_GAUSS), dict(quadrature=dc.QUAD_GLL, operator_kind=dc.OP_HELMHOLTZ)):
+    for kw in (dict(quadrature=dc.QUAD_GAUSS, deformation=1, eps=0.1),
+               dict(quadrature=dc.QUAD_GLL, operator_kind=dc.OP_HELMHOLTZ)):
         with pytest.raises(dc.Bp5Error) as e:
             dc.PoissonOperator(gpu_ctx, dc.make_problem(3, (2, 2, 2), geometry_mode=dc.GEOM_ON_THE_FLY, **kw))
         assert e.value.code == dc.ERR_UNSUPPORTED
