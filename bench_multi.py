@@ -187,14 +187,20 @@ def run(args):
     t0 = time.perf_counter()
     e2e_its = 0
     e2e_steps = max(1, min(args.steps, 5))
+    use_host_entry = P.transport == "peer"
+    xnp, bnp = xh.numpy(), bh.numpy()
     for _ in range(e2e_steps):
-        with torch.cuda.stream(P.stream):
-            bview[:n_loc].copy_(bh, non_blocking=True)
-        x.set(0.0)                      # zero initial guess made on the device (bp5/step-64.cu:491): nothing to upload
-        P.cg_solve(x, b, control)
-        with torch.cuda.stream(P.stream):
-            xh.copy_(xview[:n_loc], non_blocking=True)
-        ctx.synchronize()
+        if use_host_entry:
+            # the C-ABI host-buffer entry point: pinned b -> device, zero initial guess on the device, solve, x -> host
+            P.cg_solve_host(xnp, bnp, control, x0_is_zero=True)
+        else:
+            with torch.cuda.stream(P.stream):
+                bview[:n_loc].copy_(bh, non_blocking=True)
+            x.set(0.0)                  # zero initial guess made on the device (bp5/step-64.cu:491): nothing to upload
+            P.cg_solve(x, b, control)
+            with torch.cuda.stream(P.stream):
+                xh.copy_(xview[:n_loc], non_blocking=True)
+            ctx.synchronize()
         e2e_its += control.last_step()
     dist.barrier()
     e2e_local = time.perf_counter() - t0
@@ -241,7 +247,9 @@ def run(args):
             "e2e": {"value": n_glob * e2e_its / e2e_secs / 1e9, "unit": single.UNIT,
                     "h2d_bytes_per_step": n_loc * 8 * world, "d2h_bytes_per_step": n_loc * 8 * world,
                     "steps": e2e_steps,
-                    "api": "per rank: pinned host b -> device, zero initial guess, DistributedPoisson.cg_solve, x -> host"},
+                    "api": ("per rank: bp5_peer_cg_solve_host (pinned host b -> device, zero initial guess, solve, x -> pinned host)"
+                            if use_host_entry else
+                            "per rank: pinned host b -> device, zero initial guess, DistributedPoisson.cg_solve, x -> host")},
             "gpu_launches": launches, "launches_per_iteration": launches_per_it,
             "variants": variants,
             "roofline": {"bound": "hbm", "kernel": op.kernel_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",

@@ -79,3 +79,36 @@ def test_facade_headers_compile_without_cuda(tmp_path):
     src.write_text('#include "dealii_b200/dealii_b200.h"\nint main() { dealii::Triangulation<3> t; '
                    'dealii::GridGenerator::hyper_cube(t); t.refine_global(2); return t.n_global_active_cells() == 64 ? 0 : 1; }\n')
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+def test_cpp_drivers_fail_loudly_without_a_gpu():
+    """the C++ drivers on the facade (single block and forked ranks) exit 1 with the library's message on a box
+    without a GPU -- no CPU fallback, and no rank left hanging in a barrier"""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")], stdout=subprocess.DEVNULL)
+    for cmd in (["bp5_step64", "--cycle-min", "7", "--cycle-max", "7"],
+                ["bp5_step64_multi", "--ranks", "2", "--cycle-min", "7", "--cycle-max", "7"]):
+        out = subprocess.run([os.path.join(ROOT, "build", "examples", cmd[0])] + cmd[1:], capture_output=True, text=True,
+                             timeout=60)
+        assert out.returncode == 1, (cmd, out.returncode)
+        assert "no CPU fallback" in out.stderr, out.stderr[-500:]
+
+
+def test_facade_process_grid_matches_the_python_layer(tmp_path):
+    """the block grid a C++ host gets from dealii::b200::process_grid is the one distributed.process_grid gives the
+    Python layer (2x1x1, 2x2x1, 2x2x2, ...): both sides of a mixed deployment must agree on who is whose neighbour"""
+    import subprocess
+    from dealceed_b200.distributed import process_grid
+    src = tmp_path / "grid_probe.cc"
+    src.write_text('#include <cstdio>\n#include "dealii_b200/dealii_b200.h"\nint main() { for (int w = 1; w <= 24; ++w) { '
+                   'auto g = dealii::b200::process_grid(w); std::printf("%d %d %d\\n", g[0], g[1], g[2]); } return 0; }\n')
+    exe = tmp_path / "grid_probe"
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", os.path.join(ROOT, "deal-and-ceed-on-gpu_b200"), "-lbp5b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "deal-and-ceed-on-gpu_b200")])
+    lines = subprocess.check_output([str(exe)], text=True).split("\n")
+    for w in range(1, 25):
+        assert tuple(int(v) for v in lines[w - 1].split()) == tuple(process_grid(w)), w
