@@ -22,8 +22,12 @@ int apply_choose(bp5_operator_t op) {
   int cpt = cells_per_tile_for(op->p);
   BP5_REQUIRE(cpt > 0, "degree must be 1..8");
   if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY) {
-    if (op->p == 6) cpt = OtfTileCells<6>::value;
-    if (op->p == 7) cpt = OtfTileCells<7>::value;
+    switch (op->p) {
+      case 1: cpt = OtfTileCells<1>::value; break; case 2: cpt = OtfTileCells<2>::value; break;
+      case 3: cpt = OtfTileCells<3>::value; break; case 4: cpt = OtfTileCells<4>::value; break;
+      case 5: cpt = OtfTileCells<5>::value; break; case 6: cpt = OtfTileCells<6>::value; break;
+      case 7: cpt = OtfTileCells<7>::value; break; case 8: cpt = OtfTileCells<8>::value; break;
+    }
   }
   const int n3 = op->n * op->n * op->n;
   op->cells_per_tile = cpt;

@@ -112,9 +112,10 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
     __syncthreads();
     // (2) x-line (j=a, k=b) and y-line (i=a, k=b): derivative along the line, one field after the other
     //     (rolled: the four fields share the code and the matrix operands)
+    // the four fields (u, x, y, z) share the code; unrolled over the fields (four independent chains, ~60 more
+    // registers) where it measured faster: p = 5 +11 %, p = 7 +11 %, p = 4 / 6 slower (profiles/r2_notes.md)
     if (active) {
-#pragma unroll 1
-      for (int f = 0; f < 4; ++f) {
+      auto lines_of_field = [&](int f) {
         double *s0 = F + f * FS + cA, *s1 = F + f * FS + OS1 + cA, *s2 = F + f * FS + OS2 + cB;
         double v[N];
 #pragma unroll
@@ -123,6 +124,13 @@ __global__ void __launch_bounds__(ApplyOtfCfg<P, CPT>::NT)
 #pragma unroll
         for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
         contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, v);
+      };
+      if constexpr (P == 5 || P == 7) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) lines_of_field(f);
+      } else {
+#pragma unroll 1
+        for (int f = 0; f < 4; ++f) lines_of_field(f);
       }
     }
     __syncthreads();

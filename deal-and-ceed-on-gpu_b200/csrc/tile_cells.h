@@ -39,7 +39,24 @@ template <> struct TileCells<7> { static constexpr int value = BP5_CPT_P7; };
 template <> struct TileCells<8> { static constexpr int value = BP5_CPT_P8; };
 
 // the on-the-fly-geometry kernel keeps 12-15 work arrays per cell in shared memory: fewer cells per tile
+// (round 2, deformed mesh, 27 M DoFs, vmult GDoF/s: p=4 5/3/2 cells 22.7/22.3/23.5; p=5 3/2/1 cells 14.2/18.2/16.0;
+//  p=6 3/2/1 cells 13.0/18.2/20.9)
+// (-DBP5_OTF_CPT_Pn=... overrides one entry for tuning builds)
 template <int P> struct OtfTileCells { static constexpr int value = TileCells<P>::value; };
-template <> struct OtfTileCells<6> { static constexpr int value = 2; };
-template <> struct OtfTileCells<7> { static constexpr int value = 2; };
+#ifndef BP5_OTF_CPT_P4
+#define BP5_OTF_CPT_P4 2
+#endif
+#ifndef BP5_OTF_CPT_P5
+#define BP5_OTF_CPT_P5 2
+#endif
+#ifndef BP5_OTF_CPT_P6
+#define BP5_OTF_CPT_P6 1
+#endif
+#ifndef BP5_OTF_CPT_P7
+#define BP5_OTF_CPT_P7 1
+#endif
+template <> struct OtfTileCells<4> { static constexpr int value = BP5_OTF_CPT_P4; };
+template <> struct OtfTileCells<5> { static constexpr int value = BP5_OTF_CPT_P5; };
+template <> struct OtfTileCells<6> { static constexpr int value = BP5_OTF_CPT_P6; };
+template <> struct OtfTileCells<7> { static constexpr int value = BP5_OTF_CPT_P7; };
 }  // namespace bp5
