@@ -23,6 +23,7 @@ LIB_PATH = os.environ.get("BP5_LIB", os.path.join(_HERE, "libbp5b200.so"))   # B
 QUAD_GAUSS, QUAD_GLL = 0, 1
 OP_POISSON, OP_HELMHOLTZ = 0, 1
 GEOM_STORED, GEOM_ON_THE_FLY = 0, 1
+CELL_ORDER_DEFAULT, CELL_ORDER_COLORED = 0, 1
 CONTROL_ITERATION_NUMBER, CONTROL_SOLVER = 0, 1
 CG_STANDARD, CG_MERGED = 0, 1
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_CONVERGENCE, ERR_DIVIDE_BY_ZERO, ERR_UNSUPPORTED = range(6)
@@ -33,7 +34,7 @@ class Problem(C.Structure):
         ("degree", C.c_int32), ("quadrature", C.c_int32), ("operator_kind", C.c_int32), ("geometry_mode", C.c_int32),
         ("cells", C.c_int32 * 3), ("lower", C.c_double * 3), ("upper", C.c_double * 3),
         ("deformation", C.c_int32), ("deformation_eps", C.c_double),
-        ("part_grid", C.c_int32 * 3), ("part_coord", C.c_int32 * 3), ("reserved", C.c_int32 * 8),
+        ("part_grid", C.c_int32 * 3), ("part_coord", C.c_int32 * 3), ("cell_order", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -257,7 +258,8 @@ class Vector:
 
 
 def make_problem(degree, cells, quadrature=QUAD_GAUSS, operator_kind=OP_POISSON, lower=(0., 0., 0.), upper=None,
-                 deformation=0, eps=0.0, part_grid=(1, 1, 1), part_coord=(0, 0, 0), geometry_mode=GEOM_STORED):
+                 deformation=0, eps=0.0, part_grid=(1, 1, 1), part_coord=(0, 0, 0), geometry_mode=GEOM_STORED,
+                 cell_order=CELL_ORDER_DEFAULT):
     p = Problem()
     p.degree, p.quadrature, p.operator_kind, p.geometry_mode = degree, quadrature, operator_kind, geometry_mode
     if upper is None:
@@ -266,6 +268,7 @@ def make_problem(degree, cells, quadrature=QUAD_GAUSS, operator_kind=OP_POISSON,
         p.cells[d] = int(cells[d]); p.lower[d] = float(lower[d]); p.upper[d] = float(upper[d])
         p.part_grid[d] = int(part_grid[d]); p.part_coord[d] = int(part_coord[d])
     p.deformation, p.deformation_eps = int(deformation), float(eps)
+    p.cell_order = int(cell_order)
     return p
 
 

@@ -98,6 +98,13 @@ int bp5_operator_create(bp5_context_t ctx, const bp5_problem_t *pr, bp5_operator
     return BP5_ERR_UNSUPPORTED;
   }
   BP5_REQUIRE(pr->deformation == 0 || pr->deformation == 1, "unknown deformation");
+  BP5_REQUIRE(pr->cell_order == BP5_CELL_ORDER_DEFAULT || pr->cell_order == BP5_CELL_ORDER_COLORED, "unknown cell order");
+  for (int i = 0; i < 7; ++i) BP5_REQUIRE(pr->reserved[i] == 0, "reserved fields of bp5_problem_t must be zero");
+  if (pr->cell_order == BP5_CELL_ORDER_COLORED &&
+      (pr->geometry_mode != BP5_GEOM_STORED || pr->part_grid[0] * pr->part_grid[1] * pr->part_grid[2] != 1)) {
+    set_error("the coloured cell order is implemented for one block with stored geometry");
+    return BP5_ERR_UNSUPPORTED;
+  }
   for (int d = 0; d < 3; ++d) {
     BP5_REQUIRE(pr->cells[d] >= 1, "cells must be >= 1");
     BP5_REQUIRE(pr->upper[d] > pr->lower[d], "upper must exceed lower");

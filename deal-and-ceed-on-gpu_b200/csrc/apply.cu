@@ -100,6 +100,7 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
   long long grid = (long long)blocks_per_sm * op->ctx->sm_count;
   if (grid > prm.n_tiles - prm.tile_begin) grid = prm.n_tiles - prm.tile_begin;
   if (grid < 1) grid = 1;
+  if (op->grid_cap > 0 && grid > op->grid_cap) grid = op->grid_cap;
   BP5_REQUIRE(grid <= kApplyPartialCap, "apply grid exceeds the partial-sum buffer");
   op->apply_grid = (int)grid;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -125,6 +126,11 @@ static int launch_pm(bp5_operator_t op, double *dst, const double *src, int mode
 #define BP5_LAUNCH_MODE(M)                                                                                       \
   (gll ? (helm ? launch<P, 1, 1, M, MLOAD>(op, dst, src, dp, which) : launch<P, 1, 0, M, MLOAD>(op, dst, src, dp, which))      \
        : (helm ? launch<P, 0, 1, M, MLOAD>(op, dst, src, dp, which) : launch<P, 0, 0, M, MLOAD>(op, dst, src, dp, which)))
+  if constexpr (MLOAD == 0) {   // one colour of the coloured cell order: plain adds (apply.cuh, OWMODE >= 3)
+    if (mode == 5) return BP5_LAUNCH_MODE(5);
+    if (mode == 4) return BP5_LAUNCH_MODE(4);
+    if (mode == 3) return BP5_LAUNCH_MODE(3);
+  }
   if (mode == 2) return BP5_LAUNCH_MODE(2);
   if (mode == 1) return BP5_LAUNCH_MODE(1);
   return BP5_LAUNCH_MODE(0);
@@ -156,10 +162,7 @@ static int launch_p(bp5_operator_t op, double *dst, const double *src, int mode,
 // zero on entry, cell-interior DoFs are overwritten; otherwise dst += A src.
 // dot_partials != nullptr (needs overwrite_interior): the kernel also leaves op->apply_grid per-CTA parts of
 // src . (A src) there (see bp5_apply_kernel, OVERWRITE == 2).
-int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior, double *dot_partials,
-                    int which) {
-  BP5_REQUIRE(dot_partials == nullptr || overwrite_interior, "the fused dot product needs the overwrite kernel");
-  const int mode = dot_partials ? 2 : (overwrite_interior ? 1 : 0);
+static int apply_dispatch(bp5_operator_t op, double *dst, const double *src, int mode, double *dot_partials, int which) {
   if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY && op->metric_path != 3)
     return apply_cell_loop_otf(op, dst, src, mode, dot_partials, which);
   switch (op->p) {
@@ -174,6 +177,28 @@ int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool over
   }
   set_error("unsupported degree %d", op->p);
   return BP5_ERR_UNSUPPORTED;
+}
+
+int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior, double *dot_partials,
+                    int which) {
+  BP5_REQUIRE(dot_partials == nullptr || overwrite_interior, "the fused dot product needs the overwrite kernel");
+  const int mode = dot_partials ? 2 : (overwrite_interior ? 1 : 0);
+  if (op->prob.cell_order != BP5_CELL_ORDER_COLORED || op->range_query) return apply_dispatch(op, dst, src, mode, dot_partials, which);
+  // coloured cell order: one launch per colour over that colour's tiles, in a fixed order on one stream; the
+  // per-CTA partial sums of the fused dot product are laid out colour after colour.
+  BP5_REQUIRE(op->range_begin < 0 && which == 0, "the coloured cell order runs whole cell loops only");
+  int total = 0, rc = BP5_OK;
+  op->grid_cap = kApplyPartialCap / 8;
+  for (int c = 0; c < 8 && rc == BP5_OK; ++c) {
+    op->range_begin = op->color_tile_begin[c];
+    op->range_end = op->color_tile_begin[c + 1];
+    rc = apply_dispatch(op, dst, src, mode + 3, dot_partials ? dot_partials + total : nullptr, 0);
+    total += op->apply_grid;
+  }
+  op->range_begin = -1; op->range_end = -1;
+  op->grid_cap = 0;
+  op->apply_grid = total;
+  return rc;
 }
 
 // "dst = 0" (bp5/step-64.cu:270-271) only has to reach the skeleton -- DoFs shared by several cells and the

@@ -313,8 +313,12 @@ struct ApplyCfg {
 // (bp5/solver.h:231,303) without reading either vector again;
 // 1 = cell-interior DoFs are stored, not added (dst's skeleton must be
 // zero on entry, its interior may hold anything); 0 = dst += A src everywhere.
-template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0>
+// OVERWRITE + 3 (3, 4, 5): the same with plain read-modify-writes in place of the atomics, for the launches over
+// the tiles of ONE colour of the coloured cell order (cells of a colour share no DoF): bitwise reproducible.
+template <int P, int QUAD, int HELM, int CPT, int OWMODE, int MLOAD = 0>
 __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
+  constexpr int OVERWRITE = OWMODE % 3;
+  constexpr bool PLAIN_ADD = OWMODE >= 3;
   using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = Cfg::N, N2 = Cfg::N2, N3 = Cfg::N3, PLANES = 6 + HELM;
   constexpr int RC = BP5_ROW_CHUNK(N, QUAD, OVERWRITE);     // rows per rolled iteration of a line contraction
@@ -550,6 +554,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
           if constexpr (HELM) s += mv[k];
           double *dp = dst + idx[k];
           if (col_interior && k > 0 && k < P) *dp = s;     // multiplicity 1: plain store
+          else if constexpr (PLAIN_ADD) *dp += s;          // one colour per launch: no other cell touches this DoF
           else atomicAdd(dp, s);                           // skeleton: red.global.add.f64
         }
       }
@@ -599,6 +604,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int k = 0; k < N; ++k) {
           double *dp = dst + idx[k];
           if (col_interior && k > 0 && k < P) *dp = o[k];
+          else if constexpr (PLAIN_ADD) *dp += o[k];
           else atomicAdd(dp, o[k]);
         }
       }
@@ -623,10 +629,10 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   }
 }
 
-template <int P, int QUAD, int HELM, int CPT, int OVERWRITE, int MLOAD = 0>
+template <int P, int QUAD, int HELM, int CPT, int OWMODE, int MLOAD = 0>
 __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
     bp5_apply_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
-  bp5_apply_body<P, QUAD, HELM, CPT, OVERWRITE, MLOAD>(prm);
+  bp5_apply_body<P, QUAD, HELM, CPT, OWMODE, MLOAD>(prm);
 }
 
 }  // namespace bp5

@@ -105,6 +105,7 @@ struct bp5_operator_s {
   int64_t n_tiles = 0;
   int64_t n_boundary_cells = 0;  // cells touching a lower ghost layer; they occupy tiles [0, n_boundary_tiles)
   int64_t n_boundary_tiles = 0;
+  int64_t color_tile_begin[9] = {0};  // cell_order = BP5_CELL_ORDER_COLORED: tiles [begin[c], begin[c+1]) hold colour c
   int64_t tile_doubles = 0;     // metric doubles per tile (padded to a multiple of 2)
   // device data
   int *cell_base = nullptr;     // [n_tiles*cpt] per-cell dof descriptor: >= 0 affine base (idx = base + i + j*od0 +
@@ -145,6 +146,7 @@ struct bp5_operator_s {
   const int *skip_flag = nullptr; // device word: when non-zero the cell loop is a no-op (CG converged)
   // slab-pipelined CG iteration (slab.cu): overrides of the next cell-kernel launch, plan, cached graph
   long long range_begin = -1, range_end = -1;   // tile range instead of `which`
+  int grid_cap = 0;                             // upper bound of the cell kernel's grid (colour passes), 0 = none
   bool range_query = false;                     // only size the persistent grid (apply_grid_full), no launch
   cudaStream_t launch_stream = nullptr;         // instead of the context's stream
   int apply_grid_full = 0;                      // CTAs of a full launch of the CG-mode cell kernel

@@ -235,15 +235,47 @@ static bool cell_is_boundary(const bp5_operator_t op, int cx, int cy, int cz) {
   return (cx == 0 && op->has_lo[0]) || (cy == 0 && op->has_lo[1]) || (cz == 0 && op->has_lo[2]);
 }
 
+// Colour of a cell in the deterministic mode (cell_order = BP5_CELL_ORDER_COLORED): the parity of its three
+// indices.  Cells of one colour share no DoF (neighbours differ by one in at least one index), so a pass over one
+// colour can add into dst with plain read-modify-writes; the eight passes run one after the other.  This is
+// MatrixFree::AdditionalData::use_coloring (bp5/step-64.cu:243 sets it to false and takes the atomics).
+static int cell_color(int cx, int cy, int cz) { return (cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2); }
+
 void operator_plan_tiles(bp5_operator_t op) {
+  const int cpt = op->cells_per_tile;
+  if (op->prob.cell_order == BP5_CELL_ORDER_COLORED) {
+    // colour-major order, every colour padded to whole tiles (single block: no boundary cells)
+    op->n_boundary_cells = 0;
+    op->n_boundary_tiles = 0;
+    op->color_tile_begin[0] = 0;
+    for (int c = 0; c < 8; ++c) {
+      int64_t cnt = 1;
+      for (int d = 0; d < 3; ++d) cnt *= ((c >> d) & 1) ? op->lc[d] / 2 : (op->lc[d] + 1) / 2;
+      op->color_tile_begin[c + 1] = op->color_tile_begin[c] + (cnt + cpt - 1) / cpt;
+    }
+    op->n_tiles = op->color_tile_begin[8];
+    return;
+  }
   // boundary cells: all cells minus those whose three indices are >= has_lo
   int64_t inner = 1;
   for (int d = 0; d < 3; ++d) inner *= op->lc[d] - op->has_lo[d];
   const int64_t n_b = op->n_cells - inner;
-  const int cpt = op->cells_per_tile;
   op->n_boundary_cells = n_b;
   op->n_boundary_tiles = (n_b + cpt - 1) / cpt;
   op->n_tiles = op->n_boundary_tiles + (inner + cpt - 1) / cpt;
+}
+
+// Slot (position in the processing order) of every local cell, cells numbered lexicographically.
+static void cell_slots(const bp5_operator_t op, std::vector<long long> &slot_of) {
+  slot_of.resize((size_t)op->n_cells);
+  const bool colored = op->prob.cell_order == BP5_CELL_ORDER_COLORED;
+  int64_t next_c[8];
+  for (int c = 0; c < 8; ++c) next_c[c] = colored ? op->color_tile_begin[c] * op->cells_per_tile : 0;
+  int64_t cell = 0, next_b = 0, next_i = op->n_boundary_tiles * op->cells_per_tile;
+  for (int cz = 0; cz < op->lc[2]; ++cz)
+    for (int cy = 0; cy < op->lc[1]; ++cy)
+      for (int cx = 0; cx < op->lc[0]; ++cx, ++cell)
+        slot_of[cell] = colored ? next_c[cell_color(cx, cy, cz)]++ : cell_is_boundary(op, cx, cy, cz) ? next_b++ : next_i++;
 }
 
 int operator_setup_device(bp5_operator_t op) {
@@ -254,18 +286,17 @@ int operator_setup_device(bp5_operator_t op) {
   // per-cell dof descriptors: affine base for regular cells, slot of an explicit
   // table for cells that touch a lower ghost layer, INT_MIN for tile padding
   std::vector<int> base((size_t)padded_cells, INT_MIN);
-  std::vector<long long> slot_of((size_t)op->n_cells);
+  std::vector<long long> slot_of;
+  cell_slots(op, slot_of);
   int64_t n_irr = 0;
   {
     const int p = op->p;
-    int64_t cell = 0, next_b = 0, next_i = op->n_boundary_tiles * op->cells_per_tile;
+    int64_t cell = 0;
     for (int cz = 0; cz < op->lc[2]; ++cz)
       for (int cy = 0; cy < op->lc[1]; ++cy)
         for (int cx = 0; cx < op->lc[0]; ++cx, ++cell) {
-          const bool irregular = cell_is_boundary(op, cx, cy, cz);
-          const int64_t slot = irregular ? next_b++ : next_i++;
-          slot_of[cell] = slot;
-          if (irregular)
+          const int64_t slot = slot_of[cell];
+          if (cell_is_boundary(op, cx, cy, cz))
             base[slot] = -(int)(n_irr++) - 1;
           else
             base[slot] = (int)((cx * p - op->has_lo[0]) +
@@ -356,10 +387,10 @@ int operator_export_coefficients(bp5_operator_t op, double *host_out) {
   const int P = op->metric_planes;
   std::vector<double> tmp((size_t)op->n_tiles * op->tile_doubles);
   BP5_CUDA(cudaMemcpy(tmp.data(), op->metric, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
-  int64_t next_b = 0, next_i = op->n_boundary_tiles * op->cells_per_tile;
+  std::vector<long long> slot_of;
+  cell_slots(op, slot_of);
   for (int64_t c = 0; c < op->n_cells; ++c) {
-    const int cx = (int)(c % op->lc[0]), cy = (int)((c / op->lc[0]) % op->lc[1]), cz = (int)(c / ((int64_t)op->lc[0] * op->lc[1]));
-    const int64_t sl = cell_is_boundary(op, cx, cy, cz) ? next_b++ : next_i++;   // processing-order slot, see operator_plan_tiles
+    const int64_t sl = slot_of[c];   // processing-order slot, see operator_plan_tiles
     const size_t base = (size_t)(sl / op->cells_per_tile) * op->tile_doubles + (size_t)(sl % op->cells_per_tile) * P * n3;
     for (int pl = 0; pl < 6; ++pl)
       std::copy_n(&tmp[base + (size_t)pl * n3], n3, &host_out[((size_t)pl * op->n_cells + c) * n3]);

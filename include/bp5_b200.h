@@ -48,6 +48,8 @@ enum bp5_status {
 enum { BP5_QUAD_GAUSS = 0, BP5_QUAD_GLL = 1 };     /* bp5/step-64.cu:243-247 (COLLOCATION) */
 enum { BP5_OP_POISSON = 0, BP5_OP_HELMHOLTZ = 1 }; /* bp5/step-64.cu:147 ; step-64/step-64.cu:201 */
 enum { BP5_GEOM_STORED = 0, BP5_GEOM_ON_THE_FLY = 1 };
+enum { BP5_CELL_ORDER_DEFAULT = 0,  /* one pass, skeleton DoFs accumulated with atomics (use_coloring = false, bp5/step-64.cu:243) */
+       BP5_CELL_ORDER_COLORED = 1 }; /* eight parity colours, one pass each, plain adds: bitwise reproducible (use_coloring = true) */
 enum { BP5_CONTROL_ITERATION_NUMBER = 0, /* IterationNumberControl, bp5/step-64.cu:443 */
        BP5_CONTROL_SOLVER = 1 };         /* SolverControl, step-64/step-64.cu:513 */
 enum { BP5_CG_STANDARD = 0,              /* dealii::SolverCG ("pcg-standard"), bp5/step-64.cu:446 */
@@ -70,7 +72,8 @@ typedef struct bp5_problem {
   double deformation_eps;
   int32_t part_grid[3];    /* process grid (1,1,1 for one GPU) */
   int32_t part_coord[3];   /* this block's coordinates in the grid */
-  int32_t reserved[8];     /* must be zero */
+  int32_t cell_order;      /* BP5_CELL_ORDER_* (single block, stored geometry) */
+  int32_t reserved[7];     /* must be zero */
 } bp5_problem_t;
 
 /* ---- context ---------------------------------------------------------- */

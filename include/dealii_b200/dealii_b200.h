@@ -340,12 +340,16 @@ template <int dim, int fe_degree, int operator_kind> class MatrixFreeOperator {
   static_assert(dim == 3, "the hot path is three-dimensional");
  public:
   using VectorType = LinearAlgebra::distributed::Vector<double, MemorySpace::CUDA>;
-  MatrixFreeOperator(const DoFHandler<dim> &dof_handler, const AffineConstraints<double> &, int quadrature)
+  // use_coloring: MatrixFree::AdditionalData::use_coloring (bp5/step-64.cu:243 passes false): eight colour passes
+  // with plain adds in place of the atomics, bitwise reproducible results (one block, stored geometry)
+  MatrixFreeOperator(const DoFHandler<dim> &dof_handler, const AffineConstraints<double> &, int quadrature,
+                     bool use_coloring = false)
       : do_zero_out(true) {
     const Triangulation<dim> &t = dof_handler.get_triangulation();
     bp5_problem_t pr{};
     pr.degree = fe_degree; pr.quadrature = quadrature; pr.operator_kind = operator_kind;
     pr.geometry_mode = BP5_GEOM_STORED;
+    pr.cell_order = use_coloring ? BP5_CELL_ORDER_COLORED : BP5_CELL_ORDER_DEFAULT;
     comm = t.communicator;
     const int world = comm ? comm->size() : 1, rank = comm ? comm->rank() : 0;
     const std::array<int, 3> grid = process_grid(world);
@@ -617,8 +621,9 @@ template <int dim, int fe_degree>
 class PoissonOperator : public dealii::b200::MatrixFreeOperator<dim, fe_degree, BP5_OP_POISSON> {
  public:
   PoissonOperator(const dealii::DoFHandler<dim> &dof_handler, const dealii::AffineConstraints<double> &constraints,
-                  int quadrature = BP5_QUAD_GAUSS)
-      : dealii::b200::MatrixFreeOperator<dim, fe_degree, BP5_OP_POISSON>(dof_handler, constraints, quadrature) {}
+                  int quadrature = BP5_QUAD_GAUSS, bool use_coloring = false)
+      : dealii::b200::MatrixFreeOperator<dim, fe_degree, BP5_OP_POISSON>(dof_handler, constraints, quadrature,
+                                                                         use_coloring) {}
 };
 }  // namespace BP5
 

@@ -19,7 +19,8 @@ for p in degrees:
         if geom and quad != 1:
             continue
         op = dc.PoissonOperator(ctx, dc.make_problem(p, (nc, nc, nc), quadrature=quad, geometry_mode=geom,
-                                                     deformation=1 if eps else 0, eps=eps))
+                                                     deformation=1 if eps else 0, eps=eps,
+                                                     cell_order=int(os.environ.get('PROBE_COLORED', '0'))))
         n = op.n_owned
         src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
         src.import_host(np.random.default_rng(0).standard_normal(n))

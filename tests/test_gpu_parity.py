@@ -478,3 +478,48 @@ def test_slab_pipelined_iteration_reproduces_the_separate_kernels(gpu_ctx, p, ce
         np.testing.assert_allclose(h1[:20], h0[:20], rtol=1e-10)
         assert np.all(np.abs(np.log(h1[:k] / h0[:k])) <= np.log(1.5))
         assert relerr(x1, x0) <= 1e-7
+
+
+@pytest.mark.parametrize("p,cells", [(1, (9, 8, 7)), (2, (5, 4, 3)), (4, (5, 5, 3)), (5, (4, 3, 3)), (6, (5, 3, 2)),
+                                     (7, (3, 3, 2)), (8, (3, 2, 1)), (3, (1, 1, 1))])
+@pytest.mark.parametrize("quad", [0, 1])
+def test_colored_cell_order_is_bitwise_reproducible(gpu_ctx, p, cells, quad):
+    """cell_order = COLORED (MatrixFree's use_coloring = true; bp5/step-64.cu:243 sets false): eight colour passes of
+    the tuned kernel with plain adds.  Same operator as the atomic path and the oracle (1e-12), and -- what the
+    atomics cannot give -- the same bits on every run, for vmult and for the whole merged-CG history.
+    Cell counts are odd/ragged so that colours have different sizes and partly filled tiles."""
+    dc = _dc()
+    import oracle as O
+    for kind in (0, 1):
+        m = O.OracleMesh(p, cells, quad=quad, deform=1, eps=0.1)
+        u = np.random.default_rng(11 * p + kind).standard_normal(m.n_dofs)
+        ref = m.vmult(u, kind=kind)
+        op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=quad, operator_kind=kind, deformation=1,
+                                                         eps=0.1, cell_order=dc.CELL_ORDER_COLORED))
+        assert np.abs(op.coefficients() - m.metric()).max() <= 1e-12 * np.abs(m.metric()).max()
+        outs = [_vmult(gpu_ctx, op, u) for _ in range(3)]
+        assert relerr(outs[0], ref) <= TOL
+        assert all(np.array_equal(outs[0], o) for o in outs[1:])
+        b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+        op.assemble_rhs(b)
+        op.do_zero_out = False
+        runs = []
+        for _ in range(2):
+            ctl = dc.SolverControl(300, 1e-8 * b.l2_norm())
+            x.set(0.0)
+            dc.SolverCGFullMerge(ctl).solve(op, x, b)
+            runs.append((ctl.last_step(), np.asarray(ctl.history).copy(), x.to_host()))
+        assert runs[0][0] == runs[1][0]
+        assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+        xo, its, _, _, _ = m.cg(m.rhs(), kind=kind, variant=1, control=1, tol=1e-8 * np.linalg.norm(m.rhs()), max_its=300)
+        assert abs(runs[0][0] - its) <= 1
+        assert relerr(runs[0][2], xo) <= 1e-6
+        b.close(); x.close(); op.close()
+
+
+def test_colored_cell_order_rejects_partitions_and_on_the_fly_geometry(gpu_ctx):
+    dc = _dc()
+    for kw in (dict(part_grid=(2, 1, 1)), dict(geometry_mode=dc.GEOM_ON_THE_FLY, quadrature=1)):
+        with pytest.raises(dc.Bp5Error) as e:
+            dc.PoissonOperator(gpu_ctx, dc.make_problem(3, (4, 4, 4), cell_order=dc.CELL_ORDER_COLORED, **kw))
+        assert "coloured cell order" in str(e.value)
