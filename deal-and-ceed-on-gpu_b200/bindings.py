@@ -34,7 +34,8 @@ class Problem(C.Structure):
         ("degree", C.c_int32), ("quadrature", C.c_int32), ("operator_kind", C.c_int32), ("geometry_mode", C.c_int32),
         ("cells", C.c_int32 * 3), ("lower", C.c_double * 3), ("upper", C.c_double * 3),
         ("deformation", C.c_int32), ("deformation_eps", C.c_double),
-        ("part_grid", C.c_int32 * 3), ("part_coord", C.c_int32 * 3), ("cell_order", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("part_grid", C.c_int32 * 3), ("part_coord", C.c_int32 * 3), ("cell_order", C.c_int32), ("refine_lo", C.c_int32 * 3), ("refine_hi", C.c_int32 * 3),
+        ("reserved", C.c_int32 * 1),
     ]
 
 

@@ -99,7 +99,20 @@ int bp5_operator_create(bp5_context_t ctx, const bp5_problem_t *pr, bp5_operator
   }
   BP5_REQUIRE(pr->deformation == 0 || pr->deformation == 1, "unknown deformation");
   BP5_REQUIRE(pr->cell_order == BP5_CELL_ORDER_DEFAULT || pr->cell_order == BP5_CELL_ORDER_COLORED, "unknown cell order");
-  for (int i = 0; i < 7; ++i) BP5_REQUIRE(pr->reserved[i] == 0, "reserved fields of bp5_problem_t must be zero");
+  BP5_REQUIRE(pr->reserved[0] == 0, "reserved fields of bp5_problem_t must be zero");
+  bool refined = false, refine_set = false;
+  for (int d = 0; d < 3; ++d) refine_set |= pr->refine_lo[d] != 0 || pr->refine_hi[d] != 0;
+  if (refine_set) {
+    for (int d = 0; d < 3; ++d)
+      BP5_REQUIRE(pr->refine_lo[d] >= 0 && pr->refine_lo[d] < pr->refine_hi[d] && pr->refine_hi[d] <= pr->cells[d],
+                  "refine box must satisfy 0 <= refine_lo < refine_hi <= cells in every direction");
+    refined = true;
+    if (pr->geometry_mode != BP5_GEOM_STORED || pr->cell_order != BP5_CELL_ORDER_DEFAULT ||
+        pr->part_grid[0] * pr->part_grid[1] * pr->part_grid[2] != 1) {
+      set_error("locally refined meshes are implemented for one block with stored geometry and the default cell order");
+      return BP5_ERR_UNSUPPORTED;
+    }
+  }
   if (pr->cell_order == BP5_CELL_ORDER_COLORED &&
       (pr->geometry_mode != BP5_GEOM_STORED || pr->part_grid[0] * pr->part_grid[1] * pr->part_grid[2] != 1)) {
     set_error("the coloured cell order is implemented for one block with stored geometry");
@@ -156,8 +169,15 @@ int bp5_operator_create(bp5_context_t ctx, const bp5_problem_t *pr, bp5_operator
     return BP5_ERR_UNSUPPORTED;
   }
   if (const char *sv = getenv("BP5_SLAB")) op->slab_enabled = atoi(sv) != 0;
-  int rc = apply_choose(op);
-  if (rc == BP5_OK) rc = operator_setup_device(op);
+  int rc;
+  if (refined) {
+    // hanging nodes: numbering and the generic functor path's arrays only (the tuned kernel handles conforming meshes)
+    op->kernel_name = "generic functor path (locally refined mesh, hanging-node constraints in the evaluator)";
+    rc = operator_setup_hanging(op);
+  } else {
+    rc = apply_choose(op);
+    if (rc == BP5_OK) rc = operator_setup_device(op);
+  }
   if (rc != BP5_OK) { bp5_operator_destroy(op); return rc; }
   *out = op;
   return BP5_OK;
@@ -215,6 +235,17 @@ int bp5_operator_set_zero_out(bp5_operator_t op, int z) {
   return BP5_OK;
 }
 
+// entry points of the tuned kernel: conforming meshes only
+#define BP5_CONFORMING_ONLY(op)                                                                                        \
+  do {                                                                                                                 \
+    if ((op)->hanging) {                                                                                               \
+      set_error("%s: this operator describes a locally refined mesh, which runs through the generic functor path "   \
+                "(bp5_operator_matrix_free_data + user functors); the tuned kernel handles conforming meshes",         \
+                __func__);                                                                                             \
+      return BP5_ERR_UNSUPPORTED;                                                                                      \
+    }                                                                                                                  \
+  } while (0)
+
 static int check_vec(bp5_operator_t op, bp5_vector_t v) {
   BP5_REQUIRE(v != nullptr, "null vector");
   BP5_REQUIRE(v->n_owned == op->n_owned && v->n_ghost == op->n_ghost, "vector layout does not match the operator");
@@ -224,6 +255,7 @@ static int check_vec(bp5_operator_t op, bp5_vector_t v) {
 int bp5_operator_cell_loop(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op, "null operator");
+  BP5_CONFORMING_ONLY(op);
   int rc;
   if ((rc = check_vec(op, dst)) || (rc = check_vec(op, src))) return rc;
   BP5_REQUIRE(dst != src, "dst and src must differ");
@@ -243,6 +275,7 @@ int bp5_operator_copy_constrained_values(bp5_operator_t op, bp5_vector_t dst, bp
 int bp5_operator_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op, "null operator");
+  BP5_CONFORMING_ONLY(op);
   int rc;
   if ((rc = check_vec(op, dst)) || (rc = check_vec(op, src))) return rc;
   BP5_REQUIRE(dst != src, "dst and src must differ");
@@ -262,6 +295,7 @@ int bp5_operator_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
 int bp5_operator_vmult_ptr(bp5_operator_t op, double *dst, const double *src, int zero_dst) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && dst && src && dst != src, "bad argument");
+  BP5_CONFORMING_ONLY(op);
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   int rc;
   if (zero_dst && (rc = apply_zero_skeleton(op, dst))) return rc;
@@ -273,6 +307,7 @@ int bp5_operator_vmult_ptr(bp5_operator_t op, double *dst, const double *src, in
 int bp5_operator_assemble_rhs(bp5_operator_t op, bp5_vector_t b) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op, "null operator");
+  BP5_CONFORMING_ONLY(op);
   int rc;
   if ((rc = check_vec(op, b))) return rc;
   BP5_CUDA(cudaSetDevice(op->ctx->device));
@@ -283,6 +318,7 @@ int bp5_operator_assemble_rhs(bp5_operator_t op, bp5_vector_t b) {
 int bp5_operator_export_coefficients(bp5_operator_t op, double *host_out) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && host_out, "null argument");
+  BP5_CONFORMING_ONLY(op);
   if (!op->metric) { set_error("this operator computes its geometry on the fly: no stored coefficient"); return BP5_ERR_UNSUPPORTED; }
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   BP5_CUDA(cudaStreamSynchronize(op->ctx->stream));
@@ -293,6 +329,7 @@ int bp5_operator_export_coefficients(bp5_operator_t op, double *host_out) {
 int bp5_operator_export_dof_coordinates(bp5_operator_t op, double *host_out) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && host_out, "null argument");
+  if (op->hanging) { std::copy(op->hanging_coords.begin(), op->hanging_coords.end(), host_out); return BP5_OK; }
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   return operator_export_coords(op, host_out);
   BP5_ABI_GUARD_END
@@ -301,6 +338,7 @@ int bp5_operator_export_dof_coordinates(bp5_operator_t op, double *host_out) {
 int bp5_operator_export_global_indices(bp5_operator_t op, int64_t *host_out) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && host_out, "null argument");
+  if (op->hanging) { for (int64_t i = 0; i < op->n_owned; ++i) host_out[i] = i; return BP5_OK; }
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   return operator_export_global_indices(op, host_out);
   BP5_ABI_GUARD_END
@@ -309,6 +347,7 @@ int bp5_operator_export_global_indices(bp5_operator_t op, int64_t *host_out) {
 int bp5_operator_l2_norm_sqr(bp5_operator_t op, bp5_vector_t u, double *out) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && out, "null argument");
+  BP5_CONFORMING_ONLY(op);
   int rc;
   if ((rc = check_vec(op, u))) return rc;
   BP5_CUDA(cudaSetDevice(op->ctx->device));
@@ -319,6 +358,7 @@ int bp5_operator_l2_norm_sqr(bp5_operator_t op, bp5_vector_t u, double *out) {
 int bp5_operator_compute_diagonal(bp5_operator_t op, bp5_vector_t diag, int invert) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op, "null operator");
+  BP5_CONFORMING_ONLY(op);
   int rc;
   if ((rc = check_vec(op, diag))) return rc;
   BP5_CUDA(cudaSetDevice(op->ctx->device));
@@ -328,6 +368,7 @@ int bp5_operator_compute_diagonal(bp5_operator_t op, bp5_vector_t diag, int inve
 
 int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *per_vmult, double *per_cg_it) {
   BP5_REQUIRE(op, "null operator");
+  BP5_CONFORMING_ONLY(op);
   // per DoF 8 (read src) + 8 (write dst) + 8*planes per q-point;
   // CG: read {x,r,p,h,diag} + write {x,r,p,h} = 72, plus the metric.
   const double n3 = (double)op->n * op->n * op->n;
@@ -511,6 +552,7 @@ int bp5_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t
                  double tol, int max_its, int *last_step, double *last_value, double *history, int history_len) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && x && b, "null argument");
+  BP5_CONFORMING_ONLY(op);
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   return cg_solve(op, x, b, diag, variant, control, tol, max_its, last_step, last_value, history, history_len);
   BP5_ABI_GUARD_END
@@ -520,6 +562,7 @@ int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, i
                       int control, double tol, int max_its, int *last_step, double *last_value) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && x_host && b_host, "null argument");
+  BP5_CONFORMING_ONLY(op);
   BP5_REQUIRE(n == op->n_owned && op->n_ghost == 0, "host solve needs a single block and n == n_dofs");
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   bp5_context_t ctx = op->ctx;
@@ -547,8 +590,10 @@ int bp5_operator_matrix_free_data(bp5_operator_t op, bp5_matrix_free_data_t *out
   BP5_REQUIRE(op->n_ghost == 0, "the generic functor path handles a single block");
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   int rc;
-  if ((rc = operator_generic_data(op))) return rc;
+  if (!op->hanging && (rc = operator_generic_data(op))) return rc;
   std::memset(out, 0, sizeof(*out));
+  for (int sI = 0; sI < 2; ++sI)
+    for (int i = 0; i < op->n * op->n; ++i) out->hanging_interpolation[sI][i] = op->hanging_interp[sI][i];
   out->q_points = op->mf_q_points;
   out->local_to_global = op->mf_l2g;
   out->inv_jacobian = op->mf_inv_jacobian;
@@ -584,6 +629,7 @@ int bp5_operator_matrix_free_data_colored(bp5_operator_t op, int color, bp5_matr
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && out, "null argument");
   BP5_REQUIRE(color >= 0 && color < 8, "colour must be 0..7");
+  BP5_CONFORMING_ONLY(op);
   BP5_REQUIRE(op->n_ghost == 0, "the generic functor path handles a single block");
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   int rc;
@@ -662,6 +708,7 @@ int bp5_cg_step_update(bp5_operator_t op, int iteration) {
 int bp5_cg_step_apply_local(bp5_operator_t op) {
   BP5_ABI_GUARD_BEGIN
   BP5_STEP_GUARD();
+  BP5_CONFORMING_ONLY(op);
   // h (zeroed by the update step) = local cells' part of A d; the caller exchanges halos around this
   return cg_step_apply_local(op);
   BP5_ABI_GUARD_END
@@ -708,6 +755,7 @@ int bp5_cg_step_finish(bp5_operator_t op, double *history) {
 int bp5_peer_export(bp5_operator_t op, int rank, int world, bp5_peer_info_t *info) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && info, "null argument");
+  BP5_CONFORMING_ONLY(op);
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   return peer_export(op, rank, world, info);
   BP5_ABI_GUARD_END

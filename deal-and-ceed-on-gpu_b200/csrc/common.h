@@ -125,6 +125,10 @@ struct bp5_operator_s {
   double *metric = nullptr;     // [tile][cpt][planes][n^3]; planes: 6 (Poisson) or 7 (Helmholtz: + a*JxW)
   int metric_planes = 6;
   int *constrained = nullptr;   // local owned indices of Dirichlet dofs
+  // locally refined mesh (refine_lo/refine_hi of the problem): generic functor path only, see operator_setup_hanging
+  bool hanging = false;
+  double hanging_interp[2][bp5::kMaxN * bp5::kMaxN] = {};   // [s][a * n + b] = l_b((s + xi_a) / 2): parent-to-child, 1D
+  std::vector<double> hanging_coords;             // [n_owned][3] mapped support point of every DoF
   int64_t n_constrained = 0;
   bool do_zero_out = true;
   std::string kernel_name;
@@ -159,6 +163,7 @@ struct bp5_operator_s {
 
 namespace bp5 {
 // setup.cu
+int operator_setup_hanging(bp5_operator_t op);      // locally refined mesh: numbering + generic-path arrays
 void operator_plan_tiles(bp5_operator_t op);       // fills n_boundary_cells, n_boundary_tiles, n_tiles
 int operator_setup_device(bp5_operator_t op);
 int operator_assemble_rhs(bp5_operator_t op, double *b_dev);

@@ -430,21 +430,16 @@ int operator_export_global_indices(bp5_operator_t op, int64_t *host_out) { retur
 // The cells written are those of the sub-lattice (off + stride * i) in each direction, numbered x fastest:
 // stride 1, off 0 = all cells in lexicographic order; stride 2 = one of the eight parity colours (cells of one
 // colour share no DoF, MatrixFree::AdditionalData::use_coloring, bp5/fe_evaluation_gl.h:176-177).
-struct CellLattice { int stride, off[3], dims[3]; };
-__global__ void generic_data_kernel(BlockGeom g, CellLattice lat, int pad, unsigned int *__restrict__ l2g,
-                                    double *__restrict__ inv_jac, double *__restrict__ jxw, double *__restrict__ qpts) {
-  extern __shared__ double sm[];
+// inverse Jacobian, JxW and quadrature point of this thread's point of lattice cell (cx, cy, cz) of `g`, written at
+// `cell` of the deal.II-layout arrays (whole CTA: cell_jacobian synchronises)
+__device__ void write_generic_geometry(const BlockGeom &g, double *sm, int cx, int cy, int cz, long long cell,
+                                       long long n_cells, int pad, double *__restrict__ inv_jac,
+                                       double *__restrict__ jxw, double *__restrict__ qpts) {
   const int n = g.n, n2 = n * n, n3 = n2 * n;
-  const long long cell = blockIdx.x;
-  const long long n_cells = gridDim.x;
-  const int lcx = lat.off[0] + lat.stride * (int)(cell % lat.dims[0]);
-  const int lcy = lat.off[1] + lat.stride * (int)((cell / lat.dims[0]) % lat.dims[1]);
-  const int lcz = lat.off[2] + lat.stride * (int)(cell / ((long long)lat.dims[0] * lat.dims[1]));
   const int t = threadIdx.x;
   const int i = t % n, j = (t / n) % n, k = t / n2;
-  if (t < n3) l2g[cell * pad + t] = (unsigned int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
   double J[3][3], xr[3];
-  cell_jacobian(g, c_tab.B, c_tab.Dg, sm, g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz, J, xr);
+  cell_jacobian(g, c_tab.B, c_tab.Dg, sm, cx, cy, cz, J, xr);
   if (t >= n3) return;
   const double det = det3(J), id = 1.0 / det;
   double I[3][3];
@@ -462,6 +457,22 @@ __global__ void generic_data_kernel(BlockGeom g, CellLattice lat, int pad, unsig
     for (int e = 0; e < 3; ++e) inv_jac[(d * 3 + e) * plane + at] = I[d][e];
   jxw[at] = det * c_tab.wq[i] * c_tab.wq[j] * c_tab.wq[k];
   for (int d = 0; d < 3; ++d) qpts[3 * at + d] = xr[d];
+}
+
+struct CellLattice { int stride, off[3], dims[3]; };
+__global__ void generic_data_kernel(BlockGeom g, CellLattice lat, int pad, unsigned int *__restrict__ l2g,
+                                    double *__restrict__ inv_jac, double *__restrict__ jxw, double *__restrict__ qpts) {
+  extern __shared__ double sm[];
+  const int n = g.n, n2 = n * n, n3 = n2 * n;
+  const long long cell = blockIdx.x;
+  const long long n_cells = gridDim.x;
+  const int lcx = lat.off[0] + lat.stride * (int)(cell % lat.dims[0]);
+  const int lcy = lat.off[1] + lat.stride * (int)((cell / lat.dims[0]) % lat.dims[1]);
+  const int lcz = lat.off[2] + lat.stride * (int)(cell / ((long long)lat.dims[0] * lat.dims[1]));
+  const int t = threadIdx.x;
+  const int i = t % n, j = (t / n) % n, k = t / n2;
+  if (t < n3) l2g[cell * pad + t] = (unsigned int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
+  write_generic_geometry(g, sm, g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz, cell, n_cells, pad, inv_jac, jxw, qpts);
 }
 
 // arrays of one cell lattice in deal.II's layout; n_cells_out = 0 leaves everything null
@@ -541,6 +552,201 @@ int operator_generic_data(bp5_operator_t op) {
   BP5_CHECK_LAUNCH();
   ctx->launches++;
   BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BP5_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Locally refined meshes with hanging nodes, for the generic functor path -- the `constraint_mask` /
+// resolve_hanging_nodes slot of the reference's evaluator (bp5/fe_evaluation_gl.h:88,150,167), which none of its
+// meshes exercises.  The coarse cells with indices in [refine_lo, refine_hi) are replaced by their eight children
+// (one level: 2:1 balanced by construction).  A child face that lies on a face of an unrefined neighbour carries no
+// DoFs of its own: its nodes take the values of the neighbour's face polynomial.
+//   numbering   coarse-lattice nodes that belong to an unrefined cell, x fastest; then the nodes of the fine lattice
+//               over the refined box that are not hanging, x fastest (oracle/hanging_oracle.py numbers the same way)
+//   cells       unrefined coarse cells, x fastest; then the children, parents x fastest, child = sx + 2 sy + 4 sz
+//   l2g         a local node ON a constrained face holds the PARENT's node with the same local index (which lies on
+//               the unrefined neighbour's face); the evaluator turns those values into the child's by 1D
+//               interpolations along the face's lines (read) or their transposes (distribute)
+//   mask        bit d (0..2): the child's face normal to d on the parent's boundary is constrained;
+//               bit 3 + d: the child's position s_d in the parent (selects the face: low if 0, high if 1, and the
+//               1D interpolation matrix along d).  Unrefined cells: 0.
+__global__ void hanging_geometry_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells, int pad,
+                                        double *__restrict__ inv_jac, double *__restrict__ jxw,
+                                        double *__restrict__ qpts) {
+  extern __shared__ double sm[];
+  const int4 c = cells[blockIdx.x];
+  write_generic_geometry(c.w ? g1 : g0, sm, c.x, c.y, c.z, blockIdx.x, gridDim.x, pad, inv_jac, jxw, qpts);
+}
+
+static void host_map_point(const bp5_problem_t &pr, const double *x, double *y) {
+  if (pr.deformation == 0) { y[0] = x[0]; y[1] = x[1]; y[2] = x[2]; return; }
+  double s = 1.0;
+  for (int d = 0; d < 3; ++d) s *= sin(M_PI * (x[d] - pr.lower[d]) / (pr.upper[d] - pr.lower[d]));
+  for (int d = 0; d < 3; ++d) y[d] = x[d] + pr.deformation_eps * (pr.upper[d] - pr.lower[d]) * s;
+}
+
+int operator_setup_hanging(bp5_operator_t op) {
+  bp5_context_t ctx = op->ctx;
+  const bp5_problem_t &pr = op->prob;
+  const int p = op->p, n = op->n, n3 = n * n * n;
+  const int *c = pr.cells, *r0 = pr.refine_lo, *r1 = pr.refine_hi;
+  auto in_box = [&](int i, int j, int k) {
+    return i >= r0[0] && i < r1[0] && j >= r0[1] && j < r1[1] && k >= r0[2] && k < r1[2];
+  };
+  // ---- numbering
+  const int64_t nc[3] = {(int64_t)c[0] * p + 1, (int64_t)c[1] * p + 1, (int64_t)c[2] * p + 1};
+  const int64_t nf[3] = {2ll * (r1[0] - r0[0]) * p + 1, 2ll * (r1[1] - r0[1]) * p + 1, 2ll * (r1[2] - r0[2]) * p + 1};
+  const int64_t f0[3] = {2ll * r0[0] * p, 2ll * r0[1] * p, 2ll * r0[2] * p};
+  BP5_REQUIRE(nc[0] * nc[1] * nc[2] + nf[0] * nf[1] * nf[2] < (int64_t)2147483647, "mesh too large for 32-bit indices");
+  std::vector<int> coarse_id((size_t)(nc[0] * nc[1] * nc[2]), -1), fine_id((size_t)(nf[0] * nf[1] * nf[2]), -1);
+  std::vector<int> cons;
+  std::vector<double> &X = op->hanging_coords;
+  X.clear();
+  const double h0[3] = {(pr.upper[0] - pr.lower[0]) / c[0], (pr.upper[1] - pr.lower[1]) / c[1],
+                        (pr.upper[2] - pr.lower[2]) / c[2]};
+  // node k of a lattice with `cells` cells of size h: the cell that holds it and its local index
+  auto lattice_point = [&](const int64_t k[3], const int cells_d[3], double scale, double *y) {
+    double x[3];
+    for (int d = 0; d < 3; ++d) {
+      const int i = (int)std::min<int64_t>(k[d] / p, cells_d[d] - 1);
+      x[d] = pr.lower[d] + h0[d] * scale * (i + op->tab.xi[k[d] - (int64_t)i * p]);
+    }
+    host_map_point(pr, x, y);
+  };
+  int N = 0;
+  for (int64_t kz = 0; kz < nc[2]; ++kz)
+    for (int64_t ky = 0; ky < nc[1]; ++ky)
+      for (int64_t kx = 0; kx < nc[0]; ++kx) {
+        const int64_t k[3] = {kx, ky, kz};
+        int lo[3], hi[3];
+        for (int d = 0; d < 3; ++d) {
+          hi[d] = (int)std::min<int64_t>(k[d] / p, c[d] - 1);
+          lo[d] = (k[d] % p == 0 && k[d] > 0) ? (int)(k[d] / p) - 1 : hi[d];
+        }
+        bool used = false;
+        for (int iz = lo[2]; iz <= hi[2]; ++iz)
+          for (int iy = lo[1]; iy <= hi[1]; ++iy)
+            for (int ix = lo[0]; ix <= hi[0]; ++ix) used |= !in_box(ix, iy, iz);
+        if (!used) continue;
+        coarse_id[(size_t)(kx + nc[0] * (ky + nc[1] * kz))] = N;
+        if (kx == 0 || kx == nc[0] - 1 || ky == 0 || ky == nc[1] - 1 || kz == 0 || kz == nc[2] - 1) cons.push_back(N);
+        double y[3];
+        lattice_point(k, c, 1.0, y);
+        X.insert(X.end(), y, y + 3);
+        ++N;
+      }
+  const int c2[3] = {2 * c[0], 2 * c[1], 2 * c[2]};
+  for (int64_t fz = 0; fz < nf[2]; ++fz)
+    for (int64_t fy = 0; fy < nf[1]; ++fy)
+      for (int64_t fx = 0; fx < nf[0]; ++fx) {
+        const int64_t f[3] = {fx, fy, fz};
+        bool hanging = false, boundary = false;
+        int64_t k[3];
+        for (int d = 0; d < 3; ++d) {
+          hanging |= (f[d] == 0 && r0[d] > 0) || (f[d] == nf[d] - 1 && r1[d] < c[d]);
+          k[d] = f0[d] + f[d];
+          boundary |= k[d] == 0 || k[d] == 2ll * c[d] * p;
+        }
+        if (hanging) continue;
+        fine_id[(size_t)(fx + nf[0] * (fy + nf[1] * fz))] = N;
+        if (boundary) cons.push_back(N);
+        double y[3];
+        lattice_point(k, c2, 0.5, y);
+        X.insert(X.end(), y, y + 3);
+        ++N;
+      }
+  // ---- cells
+  const int64_t n_box = (int64_t)(r1[0] - r0[0]) * (r1[1] - r0[1]) * (r1[2] - r0[2]);
+  const int64_t n_cells = (int64_t)c[0] * c[1] * c[2] - n_box + 8 * n_box;
+  int pad = 1;
+  while (pad < n3) pad <<= 1;
+  op->mf_padding = pad;
+  std::vector<unsigned int> l2g((size_t)n_cells * pad, 0u), mask((size_t)n_cells, 0u);
+  std::vector<int4> desc((size_t)n_cells);
+  int64_t cell = 0;
+  for (int cz = 0; cz < c[2]; ++cz)
+    for (int cy = 0; cy < c[1]; ++cy)
+      for (int cx = 0; cx < c[0]; ++cx) {
+        if (in_box(cx, cy, cz)) continue;
+        for (int t = 0; t < n3; ++t) {
+          const int64_t kx = (int64_t)cx * p + t % n, ky = (int64_t)cy * p + (t / n) % n, kz = (int64_t)cz * p + t / (n * n);
+          l2g[(size_t)cell * pad + t] = (unsigned int)coarse_id[(size_t)(kx + nc[0] * (ky + nc[1] * kz))];
+        }
+        desc[(size_t)cell] = make_int4(cx, cy, cz, 0);
+        ++cell;
+      }
+  for (int pz = r0[2]; pz < r1[2]; ++pz)
+    for (int py = r0[1]; py < r1[1]; ++py)
+      for (int px = r0[0]; px < r1[0]; ++px)
+        for (int s = 0; s < 8; ++s) {
+          const int par[3] = {px, py, pz}, sd[3] = {s & 1, (s >> 1) & 1, (s >> 2) & 1};
+          unsigned int m = 0;
+          int face[3];   // local index of the constrained face's plane, -1: not constrained
+          for (int d = 0; d < 3; ++d) {
+            const bool con = sd[d] == 0 ? (par[d] == r0[d] && r0[d] > 0) : (par[d] == r1[d] - 1 && r1[d] < c[d]);
+            face[d] = con ? (sd[d] ? p : 0) : -1;
+            if (con) m |= 1u << d;
+            m |= (unsigned int)sd[d] << (3 + d);
+          }
+          if ((m & 7u) == 0) m = 0;          // nothing to resolve: plain cell
+          mask[(size_t)cell] = m;
+          for (int t = 0; t < n3; ++t) {
+            const int a[3] = {t % n, (t / n) % n, t / (n * n)};
+            const bool on_face = a[0] == face[0] || a[1] == face[1] || a[2] == face[2];
+            int id;
+            if (on_face) {
+              const int64_t kx = (int64_t)px * p + a[0], ky = (int64_t)py * p + a[1], kz = (int64_t)pz * p + a[2];
+              id = coarse_id[(size_t)(kx + nc[0] * (ky + nc[1] * kz))];
+            } else {
+              const int64_t fx = (2ll * px + sd[0]) * p + a[0] - f0[0], fy = (2ll * py + sd[1]) * p + a[1] - f0[1],
+                            fz = (2ll * pz + sd[2]) * p + a[2] - f0[2];
+              id = fine_id[(size_t)(fx + nf[0] * (fy + nf[1] * fz))];
+            }
+            BP5_REQUIRE(id >= 0, "internal error: cell node without a DoF on the locally refined mesh");
+            l2g[(size_t)cell * pad + t] = (unsigned int)id;
+          }
+          desc[(size_t)cell] = make_int4(2 * px + sd[0], 2 * py + sd[1], 2 * pz + sd[2], 1);
+          ++cell;
+        }
+  BP5_REQUIRE(cell == n_cells, "internal error: cell count of the locally refined mesh");
+  // ---- sizes, Dirichlet set, 1D parent-to-child interpolation
+  op->n_owned = N; op->n_ghost = 0; op->n_global = N; op->n_cells = n_cells;
+  std::sort(cons.begin(), cons.end());
+  op->n_constrained = (int64_t)cons.size();
+  BP5_CUDA(cudaMalloc(&op->constrained, sizeof(int) * std::max<size_t>(cons.size(), 1)));
+  BP5_CUDA(cudaMemcpyAsync(op->constrained, cons.data(), sizeof(int) * cons.size(), cudaMemcpyHostToDevice, ctx->stream));
+  for (int s = 0; s < 2; ++s)
+    for (int a = 0; a < n; ++a) {
+      double val[kMaxN], der[kMaxN];
+      lagrange_eval(n, op->tab.xi, 0.5 * (s + op->tab.xi[a]), val, der);
+      for (int b = 0; b < n; ++b) op->hanging_interp[s][a * n + b] = val[b];
+    }
+  // ---- arrays in deal.II's layout
+  const size_t cells = (size_t)n_cells;
+  int4 *desc_dev = nullptr;
+  BP5_CUDA(cudaMalloc(&desc_dev, sizeof(int4) * cells));
+  BP5_CUDA(cudaMemcpyAsync(desc_dev, desc.data(), sizeof(int4) * cells, cudaMemcpyHostToDevice, ctx->stream));
+  BP5_CUDA(cudaMalloc(&op->mf_l2g, sizeof(unsigned int) * cells * pad));
+  BP5_CUDA(cudaMalloc(&op->mf_constraint_mask, sizeof(unsigned int) * cells));
+  BP5_CUDA(cudaMalloc(&op->mf_inv_jacobian, sizeof(double) * 9 * cells * pad));
+  BP5_CUDA(cudaMalloc(&op->mf_jxw, sizeof(double) * cells * pad));
+  BP5_CUDA(cudaMalloc(&op->mf_q_points, sizeof(double) * 3 * cells * pad));
+  BP5_CUDA(cudaMemcpyAsync(op->mf_l2g, l2g.data(), sizeof(unsigned int) * cells * pad, cudaMemcpyHostToDevice, ctx->stream));
+  BP5_CUDA(cudaMemcpyAsync(op->mf_constraint_mask, mask.data(), sizeof(unsigned int) * cells, cudaMemcpyHostToDevice, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->mf_inv_jacobian, 0, sizeof(double) * 9 * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->mf_jxw, 0, sizeof(double) * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->mf_q_points, 0, sizeof(double) * 3 * cells * pad, ctx->stream));
+  BlockGeom g0 = make_geom(op), g1 = g0;
+  for (int d = 0; d < 3; ++d) { g0.c0[d] = g1.c0[d] = 0; g1.h[d] = 0.5 * g0.h[d]; }
+  BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = ((n3 + 31) / 32) * 32;
+  hanging_geometry_kernel<<<(unsigned)cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
+      g0, g1, desc_dev, pad, op->mf_inv_jacobian, op->mf_jxw, op->mf_q_points);
+  BP5_CHECK_LAUNCH();
+  ctx->launches++;
+  BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  BP5_CUDA(cudaFree(desc_dev));
+  op->hanging = true;
   return BP5_OK;
 }
 

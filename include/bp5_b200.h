@@ -73,7 +73,12 @@ typedef struct bp5_problem {
   int32_t part_grid[3];    /* process grid (1,1,1 for one GPU) */
   int32_t part_coord[3];   /* this block's coordinates in the grid */
   int32_t cell_order;      /* BP5_CELL_ORDER_* (single block, stored geometry) */
-  int32_t reserved[7];     /* must be zero */
+  int32_t refine_lo[3];    /* locally refined mesh: the coarse cells with indices in [refine_lo, refine_hi) are replaced */
+  int32_t refine_hi[3];    /* by their eight children (hanging nodes on the box's faces); all zero: conforming mesh.    */
+                           /* Such an operator serves the generic functor path only (bp5_operator_matrix_free_data,     */
+                           /* vectors, copy_constrained_values, stepwise CG); the tuned kernel's entry points return    */
+                           /* BP5_ERR_UNSUPPORTED.  Single block, stored geometry.                                      */
+  int32_t reserved[1];     /* must be zero */
 } bp5_problem_t;
 
 /* ---- context ---------------------------------------------------------- */
@@ -199,7 +204,7 @@ int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, i
  * (bp5/step-64.cu:69-75,128-138; bp5/fe_evaluation_gl.h:107-124), in deal.II's layout:
  *   inv_jacobian[(d*3+e)*n_cells*padding_length + cell*padding_length + q] = d xi_d / d x_e
  *   JxW[cell*padding_length + q],  local_to_global[cell*padding_length + i],
- *   q_points[(cell*padding_length + q)*3 + c],  constraint_mask[cell] == 0 (conforming mesh),
+ *   q_points[(cell*padding_length + q)*3 + c],  constraint_mask[cell] (0 on conforming meshes; see below),
  * plus the 1D shape tables [q*n + i] that MatrixFree::reinit puts into constant memory
  * [UPSTREAM]: values, gradients, and gradients of the basis through the quadrature points.
  * Device arrays stay owned by the operator.  Single block (no ghosts).
@@ -217,6 +222,11 @@ typedef struct bp5_matrix_free_data {
   double shape_values[81];
   double shape_gradients[81];
   double co_shape_gradients[81];
+  /* locally refined meshes: [s][a*n + b] = value of the parent's 1D basis function b at node a of child s (s = 0, 1).
+   * constraint_mask[cell]: bit d (0..2) = the cell's face normal to d that lies on its parent's boundary is
+   * constrained (its nodes hold the unrefined neighbour's face DoFs and are interpolated by the evaluator);
+   * bit 3+d = the cell's position s_d in its parent (low face if 0, high face if 1).  0 on conforming cells. */
+  double hanging_interpolation[2][81];
 } bp5_matrix_free_data_t;
 int bp5_operator_matrix_free_data(bp5_operator_t op, bp5_matrix_free_data_t *out);
 /* The same arrays for ONE of the eight parity colours of the cells (colour = px + 2 py + 4 pz, cells with

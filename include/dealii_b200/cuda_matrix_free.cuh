@@ -138,6 +138,8 @@ template <int dim, typename Number = double> class MatrixFree {
     bool collocation;
     Number shape_values[81];
     Number co_shape_gradients[81];
+    // locally refined meshes: 1D parent-to-child interpolation [s][a*n + b] (bp5_matrix_free_data_t)
+    Number hanging_interpolation[2][81];
   };
 
   MatrixFree() = default;
@@ -164,6 +166,9 @@ template <int dim, typename Number = double> class MatrixFree {
       pr.part_grid[d] = 1; pr.part_coord[d] = 0;
     }
     pr.deformation = t.deformation; pr.deformation_eps = t.deformation_eps;
+    for (int d = 0; d < 3; ++d) { pr.refine_lo[d] = t.refine_lo[d]; pr.refine_hi[d] = t.refine_hi[d]; }
+    if (t.locally_refined() && additional_data.use_coloring)
+      throw ExcMessage("use_coloring is implemented for conforming meshes");
     b200::check(bp5_operator_create(b200::Context::get(), &pr, &op));
     bp5_matrix_free_data_t md;
     b200::check(bp5_operator_matrix_free_data(op, &md));
@@ -181,6 +186,8 @@ template <int dim, typename Number = double> class MatrixFree {
     for (int i = 0; i < 81; ++i) {
       data.shape_values[i] = md.shape_values[i];
       data.co_shape_gradients[i] = md.co_shape_gradients[i];
+      data.hanging_interpolation[0][i] = md.hanging_interpolation[0][i];
+      data.hanging_interpolation[1][i] = md.hanging_interpolation[1][i];
     }
     n_colors = 1;
     if (use_coloring) {
@@ -205,6 +212,11 @@ template <int dim, typename Number = double> class MatrixFree {
   }
 
   unsigned int n_colors_used() const { return (unsigned int)n_colors; }
+  unsigned long long n_dofs() const {
+    int64_t n = 0;
+    b200::check(bp5_operator_sizes(op, &n, nullptr, nullptr, nullptr));
+    return (unsigned long long)n;
+  }
   Data get_data(unsigned int color = 0) const { return use_coloring ? color_data[color] : data; }
   bp5_operator_t handle() const { return op; }
   cudaStream_t stream() const { return static_cast<cudaStream_t>(bp5_context_stream(b200::Context::get())); }
@@ -342,14 +354,17 @@ class FEEvaluationGL {
     idx = ix + n_q_points_1d * (iy + n_q_points_1d * iz);
   }
 
-  // values[idx] = src[local_to_global[idx]] (fe_evaluation_gl.h:133-152); conforming meshes only
+  // values[idx] = src[local_to_global[idx]], then the hanging-node constraints of this cell
+  // (fe_evaluation_gl.h:133-152: read, __syncthreads, resolve_hanging_nodes<false>(constraint_mask, values))
   __device__ void read_dof_values(const Number *src) {
     values[idx] = __ldg(&src[local_to_global[idx]]);
     __syncthreads();
+    if (constraint_mask != 0) resolve_hanging_nodes<false>();
   }
 
-  // dst[local_to_global[idx]] += values[idx] (fe_evaluation_gl.h:161-181)
-  __device__ void distribute_local_to_global(Number *dst) const {
+  // transposed constraints, then dst[local_to_global[idx]] += values[idx] (fe_evaluation_gl.h:161-181)
+  __device__ void distribute_local_to_global(Number *dst) {
+    if (constraint_mask != 0) resolve_hanging_nodes<true>();
     const types::global_dof_index j = local_to_global[idx];
     if (use_coloring) dst[j] += values[idx];
     else atomicAdd(&dst[j], values[idx]);     // red.global.add.f64
@@ -445,6 +460,36 @@ class FEEvaluationGL {
   }
 
  private:
+  // Hanging-node constraints of a child cell of a locally refined mesh (the slot of deal.II's
+  // internal::resolve_hanging_nodes [UPSTREAM], called at fe_evaluation_gl.h:150,167).  The nodes on a constrained
+  // face were loaded from the unrefined neighbour's face DoFs (same local index in the parent); the child's values
+  // are the parent's face polynomial at the child's nodes: a 1D interpolation along each of the face's two tangential
+  // directions.  Direction by direction, every line that lies in a constrained face is interpolated once -- a line on
+  // the edge between two constrained faces too.  transpose: the adjoint, for the scatter.
+  // constraint_mask: bit d = face normal to d constrained, bit 3+d = child position s_d (face at node 0 or p; matrix).
+  template <bool transpose> __device__ void resolve_hanging_nodes() {
+    const unsigned int pos[3] = {ix, iy, iz};
+    bool on_face[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      on_face[d] = ((constraint_mask >> d) & 1u) != 0 && pos[d] == (((constraint_mask >> (3 + d)) & 1u) ? fe_degree : 0);
+    resolve_direction<0, transpose>(on_face[1] || on_face[2]);
+    resolve_direction<1, transpose>(on_face[0] || on_face[2]);
+    resolve_direction<2, transpose>(on_face[0] || on_face[1]);
+  }
+  template <int DIR, bool transpose> __device__ void resolve_direction(const bool in_constrained_face) {
+    // is any line along DIR constrained at all?  (uniform over the cell: no divergent barrier)
+    const unsigned int others = (constraint_mask & 7u) & ~(1u << DIR);
+    if (others == 0) return;
+    const Number *M = mf->hanging_interpolation[(constraint_mask >> (3 + DIR)) & 1u];
+    const unsigned int row = DIR == 0 ? ix : DIR == 1 ? iy : iz;
+    Number v = values[idx];
+    if (in_constrained_face) v = transpose ? line_t<DIR>(M, values, row) : line<DIR>(M, values, row);
+    __syncthreads();
+    values[idx] = v;
+    __syncthreads();
+  }
+
   // sum_m M[row][m] * a(..m..) along direction DIR through this thread's point
   template <int DIR> __device__ Number line(const Number *M, const Number *a, const unsigned int row) const {
     constexpr int n = n_q_points_1d;

@@ -155,15 +155,28 @@ template <int dim, typename Number = double> struct Point {
 template <int dim> class Triangulation {
  public:
   virtual ~Triangulation() = default;     // the operators dynamic_cast it (bp5/step-64.cu:250)
-  void clear() { subdivisions.assign(dim, 1); refinements = 0; }
+  void clear() { subdivisions.assign(dim, 1); refinements = 0; for (int d = 0; d < 3; ++d) refine_lo[d] = refine_hi[d] = 0; }
   // one block per GPU; this facade drives one block
   unsigned int n_locally_owned_active_cells() const { return (unsigned int)n_global_active_cells(); }
   void refine_global(unsigned int n) { refinements += n; }
   unsigned long long n_global_active_cells() const {
-    unsigned long long n = 1;
-    for (int d = 0; d < dim; ++d) n *= cells(d);
-    return n;
+    unsigned long long n = 1, box = 1;
+    for (int d = 0; d < dim; ++d) { n *= cells(d); box *= (unsigned long long)(refine_hi[d] - refine_lo[d]); }
+    return n + 7 * box;
   }
+  // Local refinement, one level: what flagging every cell with (x-fastest lattice) index in [lo, hi) and calling
+  // execute_coarsening_and_refinement() does in deal.II -- those cells are replaced by their eight children, and the
+  // children's faces on the box's surface carry hanging nodes.  Such a mesh is served by CUDAWrappers::MatrixFree +
+  // FEEvaluationGL (constraint_mask / resolve_hanging_nodes, bp5/fe_evaluation_gl.h:88,150,167), not by the tuned
+  // BP5::PoissonOperator.  Call after refine_global.
+  void refine_cells_in_box(const std::array<unsigned int, 3> &lo, const std::array<unsigned int, 3> &hi) {
+    for (int d = 0; d < 3; ++d) {
+      if (!(lo[d] < hi[d] && hi[d] <= cells(d))) throw ExcMessage("refine_cells_in_box: need lo < hi <= cells");
+      refine_lo[d] = (int)lo[d]; refine_hi[d] = (int)hi[d];
+    }
+  }
+  bool locally_refined() const { return refine_hi[0] > refine_lo[0]; }
+  int refine_lo[3] = {0, 0, 0}, refine_hi[3] = {0, 0, 0};
   unsigned int cells(int d) const { return subdivisions[d] << refinements; }
   std::vector<unsigned int> subdivisions = std::vector<unsigned int>(dim, 1);
   Point<dim> p1, p2;
@@ -208,6 +221,17 @@ template <int dim> class DoFHandler {
   unsigned long long n_dofs() const {
     unsigned long long n = 1;
     for (int d = 0; d < dim; ++d) n *= (unsigned long long)tria->cells(d) * degree + 1;
+    if (tria->locally_refined()) {
+      // minus the coarse nodes that only refined cells touch, plus the children's nodes that are not hanging
+      unsigned long long gone = 1, fine = 1;
+      for (int d = 0; d < dim; ++d) {
+        const unsigned long long lo = tria->refine_lo[d], hi = tria->refine_hi[d];
+        const unsigned long long faces = (lo > 0 ? 1 : 0) + (hi < tria->cells(d) ? 1 : 0);
+        gone *= (hi - lo) * degree + 1 - faces;
+        fine *= 2 * (hi - lo) * degree + 1 - faces;
+      }
+      n = n - gone + fine;
+    }
     return n;
   }
   const Triangulation<dim> &get_triangulation() const { return *tria; }
@@ -346,6 +370,9 @@ template <int dim, int fe_degree, int operator_kind> class MatrixFreeOperator {
                      bool use_coloring = false)
       : do_zero_out(true) {
     const Triangulation<dim> &t = dof_handler.get_triangulation();
+    if (t.locally_refined())
+      throw ExcMessage("locally refined meshes run through CUDAWrappers::MatrixFree + FEEvaluationGL "
+                       "(cuda_matrix_free.cuh); the tuned operators handle conforming meshes");
     bp5_problem_t pr{};
     pr.degree = fe_degree; pr.quadrature = quadrature; pr.operator_kind = operator_kind;
     pr.geometry_mode = BP5_GEOM_STORED;

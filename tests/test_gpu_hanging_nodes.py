@@ -1,0 +1,84 @@
+"""-m gpu: locally refined meshes with hanging nodes through the evaluator interface (constraint_mask /
+resolve_hanging_nodes, bp5/fe_evaluation_gl.h:88,150,167).  examples/bp5_hanging.cu runs the reference's operators,
+written as device functors, on a mesh whose cells in a box are refined once; numbering, right-hand side, operator
+applications (vectors, <= 1e-12) and the merged-CG solve (iteration count +-1) are compared with
+oracle/hanging_oracle.py, which forms the constraints from the 3D prolongation and assembles a sparse matrix."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(p, quad, cells, lo, hi, eps, tmp_path, u=None):
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")], stdout=subprocess.DEVNULL)
+    prefix = os.path.join(str(tmp_path), "h_")
+    if u is not None:
+        np.asarray(u, dtype=np.float64).tofile(prefix + "u.f64")
+    cmd = [os.path.join(ROOT, "build", "examples", "bp5_hanging"), str(p), quad, *map(str, cells), *map(str, lo),
+           *map(str, hi), str(eps), prefix]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert out.stdout.strip().endswith("OK"), out.stdout[-3000:]
+    vals = {m.group(1): float(m.group(2)) for m in (re.match(r"^(\w+) (\S+)$", l.strip()) for l in out.stdout.splitlines()) if m}
+    vec = lambda name: np.fromfile(prefix + name + ".f64")
+    return vals, vec
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+CASES = [(1, (3, 3, 3), (1, 1, 1), (2, 2, 2), 0.0),       # one refined cell in the middle: all six faces constrained
+         (2, (4, 3, 3), (1, 0, 1), (3, 2, 2), 0.1),       # box touching the boundary
+         (3, (3, 3, 2), (0, 0, 0), (2, 2, 1), 0.1),       # refined corner
+         (4, (3, 2, 2), (1, 1, 0), (2, 2, 2), 0.05),      # a column of refined cells
+         (5, (2, 2, 2), (0, 0, 0), (1, 1, 1), 0.1),
+         (6, (3, 2, 2), (1, 0, 0), (2, 1, 2), 0.0),
+         (8, (2, 2, 1), (1, 0, 0), (2, 2, 1), 0.1)]
+
+
+@pytest.mark.parametrize("p,cells,lo,hi,eps", CASES)
+@pytest.mark.parametrize("quad", ["gauss", "gll"])
+def test_hanging_node_mesh_matches_the_oracle(p, cells, lo, hi, eps, quad, tmp_path):
+    import oracle as O
+    from hanging_oracle import HangingMesh
+    hm = HangingMesh(p, cells, lo, hi, quad=O.GAUSS if quad == "gauss" else O.GLL, upper=(1., 1., 1.),
+                     deform=1 if eps else 0, eps=eps)
+    u = np.random.default_rng(p).standard_normal(hm.n_dofs)
+    v, vec = _run(p, quad, cells, lo, hi, eps, tmp_path, u)
+    assert v["n_dofs"] == hm.n_dofs and v["n_cells"] == hm.n_cells
+    assert np.abs(vec("coords").reshape(-1, 3) - hm.dof_coords()).max() <= 1e-13          # same numbering
+    b = hm.rhs()
+    assert _rel(vec("b"), b) <= 1e-12
+    A = hm.matrix()
+    assert _rel(vec("Ab"), hm.vmult(b, A=A)) <= 1e-12
+    assert _rel(vec("Au"), hm.vmult(u, A=A)) <= 1e-12                                      # fp64 operator: 1e-12
+    assert v["merged_vs_plain_rel_diff"] <= 1e-12
+    if quad == "gauss":
+        assert _rel(vec("Hu"), hm.vmult(u, kind=O.HELMHOLTZ)) <= 1e-12
+    x, its, _ = hm.cg(b, tol=1e-8 * np.linalg.norm(b), max_its=1000)
+    assert abs(v["merged_its"] - its) <= 1
+    assert _rel(vec("x"), x) <= 1e-6
+    assert v["norm_x"] == pytest.approx(np.linalg.norm(x), rel=1e-6)
+
+
+def test_tuned_kernel_entry_points_reject_locally_refined_meshes(gpu_ctx):
+    import dealceed_b200 as dc
+    pr = dc.make_problem(2, (3, 3, 3))
+    for d in range(3):
+        pr.refine_lo[d], pr.refine_hi[d] = 1, 2
+    op = dc.PoissonOperator(gpu_ctx, pr)
+    assert op.n_cells == 27 - 1 + 8
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    with pytest.raises(dc.Bp5Error) as e:
+        op.vmult(dst, src)
+    assert "generic functor path" in str(e.value)
+    src.close(); dst.close(); op.close()
+    pr.refine_hi[0] = 9
+    with pytest.raises(dc.Bp5Error):
+        dc.PoissonOperator(gpu_ctx, pr)
