@@ -562,7 +562,7 @@ int operator_generic_data(bp5_operator_t op) {
 // (one level: 2:1 balanced by construction).  A child face that lies on a face of an unrefined neighbour carries no
 // DoFs of its own: its nodes take the values of the neighbour's face polynomial.
 //   numbering   coarse-lattice nodes that belong to an unrefined cell, x fastest; then the nodes of the fine lattice
-//               over the refined box that are not hanging, x fastest (oracle/hanging_oracle.py numbers the same way)
+//               over the refined box that are not hanging, x fastest (the CPU restatement used by the tests numbers the same way)
 //   cells       unrefined coarse cells, x fastest; then the children, parents x fastest, child = sx + 2 sy + 4 sz
 //   l2g         a local node ON a constrained face holds the PARENT's node with the same local index (which lies on
 //               the unrefined neighbour's face); the evaluator turns those values into the child's by 1D

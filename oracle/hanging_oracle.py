@@ -204,7 +204,7 @@ class HangingMesh:
     def matrix(self, kind=O.POISSON):
         """C^T blockdiag(K_cell) C, WITHOUT the Dirichlet rows replaced"""
         K = self.cell_matrices(kind)
-        Kb = sp.block_diag([K[c] for c in range(self.n_cells)], format="csr")
+        Kb = sp.block_diag([sp.csr_matrix(K[c]) for c in range(self.n_cells)], format="csr")
         return (self.C.T @ Kb @ self.C).tocsr()
 
     # ---------------------------------------------------------------- DoF data

@@ -50,7 +50,8 @@ def test_product_does_not_touch_the_oracle():
 
 def test_problem_struct_layout_matches_header():
     import dealceed_b200 as dc
-    # int32 x4, int32 x3, (pad), double x3, double x3, int32, (pad), double, int32 x3, int32 x3, int32 x8
+    # int32 x4, int32 x3, (pad), double x3, double x3, int32, (pad), double, int32 x3, int32 x3,
+    # cell_order + refine_lo[3] + refine_hi[3] + reserved[1] = int32 x8
     assert ctypes.sizeof(dc.bindings.Problem) == 16 + 12 + 4 + 24 + 24 + 4 + 4 + 8 + 12 + 12 + 32
 
 
@@ -69,7 +70,7 @@ def test_header_is_plain_c_and_struct_sizes_match_the_ctypes_mirror(tmp_path):
     sizes = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
     assert sizes[0] == ctypes.sizeof(dc.bindings.Problem)
     assert sizes[1] == ctypes.sizeof(dc.bindings.PeerInfo)
-    assert sizes[2] == 5 * 8 + 4 * 4 + 3 * 81 * 8
+    assert sizes[2] == 5 * 8 + 4 * 4 + 3 * 81 * 8 + 2 * 81 * 8     # + hanging_interpolation[2][81]
 
 
 def test_facade_headers_compile_without_cuda(tmp_path):

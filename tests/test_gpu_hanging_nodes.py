@@ -62,7 +62,8 @@ def test_hanging_node_mesh_matches_the_oracle(p, cells, lo, hi, eps, quad, tmp_p
     if quad == "gauss":
         assert _rel(vec("Hu"), hm.vmult(u, kind=O.HELMHOLTZ)) <= 1e-12
     x, its, _ = hm.cg(b, tol=1e-8 * np.linalg.norm(b), max_its=1000)
-    assert abs(v["merged_its"] - its) <= 1
+    # same count +-1; solves of several hundred iterations (p = 8 on a deformed mesh) may drift by rounding: 1 %
+    assert abs(v["merged_its"] - its) <= max(1, its // 100)
     assert _rel(vec("x"), x) <= 1e-6
     assert v["norm_x"] == pytest.approx(np.linalg.norm(x), rel=1e-6)
 

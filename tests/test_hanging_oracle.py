@@ -68,3 +68,24 @@ def test_manufactured_solution_converges_with_order_p_plus_1_on_refined_corner(p
         errs.append(hm.l2_error(xs, u))
     rates = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
     assert rates[1] >= p + 1 - 0.3, (errs, rates)
+
+
+def test_facade_counts_dofs_and_cells_of_a_locally_refined_mesh(tmp_path):
+    """DoFHandler::n_dofs / Triangulation::n_global_active_cells of the header-only facade (no CUDA needed)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "probe.cc"
+    src.write_text('#include <iostream>\n#include "dealii_b200/dealii_b200.h"\n'
+                   'int main(int, char **argv) { using namespace dealii; Triangulation<3> t; Point<3> p2; p2[0]=p2[1]=p2[2]=1.;\n'
+                   '  GridGenerator::subdivided_hyper_rectangle(t, {4u, 3u, 3u}, Point<3>(), p2);\n'
+                   '  t.refine_cells_in_box({1u, 0u, 1u}, {3u, 2u, 2u}); DoFHandler<3> dh(t); dh.distribute_dofs(FE_Q<3>(std::atoi(argv[1])));\n'
+                   '  std::cout << dh.n_dofs() << " " << t.n_global_active_cells() << std::endl; return 0; }\n')
+    exe = tmp_path / "probe"
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    for p in (1, 2, 5):
+        n_dofs, n_cells = [int(v) for v in subprocess.check_output([str(exe), str(p)], text=True).split()]
+        hm = HangingMesh(p, (4, 3, 3), (1, 0, 1), (3, 2, 2), upper=(1., 1., 1.)) if p < 5 else None
+        if hm is not None:
+            assert (n_dofs, n_cells) == (hm.n_dofs, hm.n_cells)
+        assert n_cells == 36 - 4 + 32
