@@ -102,6 +102,11 @@ template <int dim, typename Number> struct SharedData {
   }
   Number *values;            // n^dim: dof values, then values at the quadrature points
   Number *gradients[dim];    // n^dim each: reference-cell gradient at the quadrature points
+  // the CTA's shared-memory copies of the 1D tables [q*n + i] (MatrixFree's kernels fill them; null: read them from
+  // the kernel parameters).  deal.II keeps these tables in __constant__ memory, where a warp whose lanes want
+  // different rows is served one row at a time; shared memory serves the rows in parallel.
+  const Number *shape_values = nullptr;
+  const Number *co_shape_gradients = nullptr;
 };
 
 // ------------------------------------------------------------------ MatrixFree
@@ -274,9 +279,20 @@ __global__ void __launch_bounds__(Functor::n_q_points)
                        const Number *src, Number *dst) {
   __shared__ Number values[Functor::n_local_dofs];
   __shared__ Number gradients[dim][Functor::n_q_points];
+  __shared__ Number tables[2][Functor::n_dofs_1d * Functor::n_dofs_1d];
   Number *gq[dim];
   for (int d = 0; d < dim; ++d) gq[d] = gradients[d];
   SharedData<dim, Number> shared_data(values, gq);
+  {
+    const unsigned int t = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    if (t < Functor::n_dofs_1d * Functor::n_dofs_1d) {
+      tables[0][t] = gpu_data.shape_values[t];
+      tables[1][t] = gpu_data.co_shape_gradients[t];
+    }
+    shared_data.shape_values = tables[0];
+    shared_data.co_shape_gradients = tables[1];
+    __syncthreads();
+  }
   const unsigned int cell = blockIdx.x;      // whole CTAs only: the functor synchronises
   func(cell, &gpu_data, &shared_data, src, dst);
 }
@@ -345,7 +361,9 @@ class FEEvaluationGL {
 
   __device__ FEEvaluationGL(const unsigned int cell_id, const data_type *data, SharedData<dim, Number> *shdata)
       : n_cells(data->n_cells), padding_length(data->padding_length), constraint_mask(data->constraint_mask[cell_id]),
-        use_coloring(data->use_coloring), values(shdata->values), mf(data) {
+        use_coloring(data->use_coloring), values(shdata->values), mf(data),
+        tab_B(shdata->shape_values ? shdata->shape_values : data->shape_values),
+        tab_D(shdata->co_shape_gradients ? shdata->co_shape_gradients : data->co_shape_gradients) {
     local_to_global = data->local_to_global + padding_length * cell_id;
     inv_jac = data->inv_jacobian + padding_length * cell_id;
     JxW = data->JxW + padding_length * cell_id;
@@ -374,7 +392,7 @@ class FEEvaluationGL {
   // quadrature points (if evaluate_grad) and values the function values there (if evaluate_val;
   // otherwise values still hold the DoF values).
   __device__ void evaluate(const bool evaluate_val, const bool evaluate_grad) {
-    const Number *B = mf->shape_values, *D = mf->co_shape_gradients;
+    const Number *B = tab_B, *D = tab_D;
     constexpr int n = n_q_points_1d, n2 = n * n;
     Number v = values[idx];
     if (!mf->collocation) {
@@ -401,7 +419,7 @@ class FEEvaluationGL {
   // fe_evaluation_gl.h:223-250: values[dof] = sum over quadrature points of the submitted values /
   // gradients tested with the basis (the transpose of evaluate)
   __device__ void integrate(const bool integrate_val, const bool integrate_grad) {
-    const Number *B = mf->shape_values, *D = mf->co_shape_gradients;
+    const Number *B = tab_B, *D = tab_D;
     Number w = integrate_val ? values[idx] : Number(0);
     if (integrate_grad) {
       w += line_t<0>(D, gradients[0], ix);
@@ -521,6 +539,7 @@ class FEEvaluationGL {
   Number *values;
   Number *gradients[dim];
   const data_type *mf;
+  const Number *tab_B, *tab_D;     // 1D tables: the CTA's shared-memory copies if the kernel made them
   unsigned int ix, iy, iz, idx;
 };
 

@@ -54,6 +54,7 @@ class HangingMesh:
         n, n3 = self.n, self.n ** 3
         # 1D parent-to-child interpolation: row a = child node a of child s, column = parent node
         self.I1 = [lagrange_at(self.xi, 0.5 * (s + self.xi)) for s in (0, 1)]
+        self._matrices = {}
         self._number()
         self._cells()
         self._geometry()
@@ -194,18 +195,25 @@ class HangingMesh:
         self.Bq = np.kron(B, np.kron(B, B))                                    # [q, i]
 
     def cell_matrices(self, kind=O.POISSON):
-        K = np.einsum("qei,nqef,qfj->nij", self.gref, self.G, self.gref, optimize=True)
-        if kind == O.HELMHOLTZ:
-            r2 = np.sum(self.xq ** 2, axis=-1)
-            a = 10.0 / (0.05 + 2.0 * r2)                                       # step-64/step-64.cu:100-118
-            K = K + np.einsum("qi,nq,qj->nij", self.Bq, a * self.jxw, self.Bq, optimize=True)
+        n3 = self.n ** 3
+        g2 = self.gref.reshape(3 * n3, n3)                                     # [(q, e), i]
+        K = np.empty((self.n_cells, n3, n3))
+        for c in range(self.n_cells):
+            W = np.einsum("qef,qfj->qej", self.G[c], self.gref).reshape(3 * n3, n3)
+            K[c] = g2.T @ W
+            if kind == O.HELMHOLTZ:
+                r2 = np.sum(self.xq[c] ** 2, axis=-1)
+                a = 10.0 / (0.05 + 2.0 * r2)                                   # step-64/step-64.cu:100-118
+                K[c] += self.Bq.T @ ((a * self.jxw[c])[:, None] * self.Bq)
         return K
 
     def matrix(self, kind=O.POISSON):
         """C^T blockdiag(K_cell) C, WITHOUT the Dirichlet rows replaced"""
-        K = self.cell_matrices(kind)
-        Kb = sp.block_diag([sp.csr_matrix(K[c]) for c in range(self.n_cells)], format="csr")
-        return (self.C.T @ Kb @ self.C).tocsr()
+        if kind not in self._matrices:
+            K = self.cell_matrices(kind)
+            Kb = sp.block_diag([sp.csr_matrix(K[c]) for c in range(self.n_cells)], format="csr")
+            self._matrices[kind] = (self.C.T @ Kb @ self.C).tocsr()
+        return self._matrices[kind]
 
     # ---------------------------------------------------------------- DoF data
     def dof_coords(self):
