@@ -394,7 +394,11 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   int base_cur = (active && tile0 < n_tiles) ? __ldg(cell_base + tile0 * CPT + c) : kNoCell;
   int base_nxt = (active && tile0 + tstride < n_tiles) ? __ldg(cell_base + (tile0 + tstride) * CPT + c) : kNoCell;
 #ifndef BP5_PREFETCH_GATHER
+#ifdef BP5_NO_PREFETCH_P8      // tuning builds (scripts/build_variant.sh)
+#define BP5_PREFETCH_GATHER(P) ((P) != 8)
+#else
 #define BP5_PREFETCH_GATHER(P) 1
+#endif
 #endif
   constexpr bool kPrefetch = BP5_PREFETCH_GATHER(P) != 0;   // values of the next tile in registers one tile ahead
   [[maybe_unused]] double u_nxt[N];
