@@ -260,7 +260,9 @@ class Vector:
 
 def make_problem(degree, cells, quadrature=QUAD_GAUSS, operator_kind=OP_POISSON, lower=(0., 0., 0.), upper=None,
                  deformation=0, eps=0.0, part_grid=(1, 1, 1), part_coord=(0, 0, 0), geometry_mode=GEOM_STORED,
-                 cell_order=CELL_ORDER_DEFAULT):
+                 cell_order=CELL_ORDER_DEFAULT, refine_lo=(0, 0, 0), refine_hi=(0, 0, 0)):
+    """refine_lo / refine_hi: the coarse cells with indices in [lo, hi) are replaced by their eight children (hanging
+    nodes on the box's faces); all zero: conforming mesh"""
     p = Problem()
     p.degree, p.quadrature, p.operator_kind, p.geometry_mode = degree, quadrature, operator_kind, geometry_mode
     if upper is None:
@@ -270,6 +272,8 @@ def make_problem(degree, cells, quadrature=QUAD_GAUSS, operator_kind=OP_POISSON,
         p.part_grid[d] = int(part_grid[d]); p.part_coord[d] = int(part_coord[d])
     p.deformation, p.deformation_eps = int(deformation), float(eps)
     p.cell_order = int(cell_order)
+    for d in range(3):
+        p.refine_lo[d] = int(refine_lo[d]); p.refine_hi[d] = int(refine_hi[d])
     return p
 
 

@@ -172,7 +172,6 @@ int bp5_operator_create(bp5_context_t ctx, const bp5_problem_t *pr, bp5_operator
   int rc;
   if (refined) {
     // hanging nodes: numbering and the generic functor path's arrays only (the tuned kernel handles conforming meshes)
-    op->kernel_name = "generic functor path (locally refined mesh, hanging-node constraints in the evaluator)";
     rc = operator_setup_hanging(op);
   } else {
     rc = apply_choose(op);
@@ -190,6 +189,9 @@ int bp5_operator_destroy(bp5_operator_t op) {
   cudaStreamSynchronize(op->ctx->stream);
   peer_destroy(op);
   cudaFree(op->cell_base);
+  cudaFree(op->cell_mask);
+  cudaFree(op->hanging_cells);
+  cudaFree(op->hanging_interp_dev);
   cudaFree(op->l2g_irr);
   cudaFree(op->mf_l2g); cudaFree(op->mf_constraint_mask); cudaFree(op->mf_inv_jacobian);
   cudaFree(op->mf_jxw); cudaFree(op->mf_q_points);
@@ -235,12 +237,12 @@ int bp5_operator_set_zero_out(bp5_operator_t op, int z) {
   return BP5_OK;
 }
 
-// entry points of the tuned kernel: conforming meshes only
+// entry points that exist for conforming meshes only
 #define BP5_CONFORMING_ONLY(op)                                                                                        \
   do {                                                                                                                 \
     if ((op)->hanging) {                                                                                               \
-      set_error("%s: this operator describes a locally refined mesh, which runs through the generic functor path "   \
-                "(bp5_operator_matrix_free_data + user functors); the tuned kernel handles conforming meshes",         \
+      set_error("%s is not implemented for locally refined meshes (available there: vmult, cell_loop, the CG "      \
+                "solves, vectors, copy_constrained_values, bp5_operator_matrix_free_data for user functors)",         \
                 __func__);                                                                                             \
       return BP5_ERR_UNSUPPORTED;                                                                                      \
     }                                                                                                                  \
@@ -255,7 +257,6 @@ static int check_vec(bp5_operator_t op, bp5_vector_t v) {
 int bp5_operator_cell_loop(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op, "null operator");
-  BP5_CONFORMING_ONLY(op);
   int rc;
   if ((rc = check_vec(op, dst)) || (rc = check_vec(op, src))) return rc;
   BP5_REQUIRE(dst != src, "dst and src must differ");
@@ -275,7 +276,6 @@ int bp5_operator_copy_constrained_values(bp5_operator_t op, bp5_vector_t dst, bp
 int bp5_operator_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op, "null operator");
-  BP5_CONFORMING_ONLY(op);
   int rc;
   if ((rc = check_vec(op, dst)) || (rc = check_vec(op, src))) return rc;
   BP5_REQUIRE(dst != src, "dst and src must differ");
@@ -295,7 +295,6 @@ int bp5_operator_vmult(bp5_operator_t op, bp5_vector_t dst, bp5_vector_t src) {
 int bp5_operator_vmult_ptr(bp5_operator_t op, double *dst, const double *src, int zero_dst) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && dst && src && dst != src, "bad argument");
-  BP5_CONFORMING_ONLY(op);
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   int rc;
   if (zero_dst && (rc = apply_zero_skeleton(op, dst))) return rc;
@@ -307,7 +306,6 @@ int bp5_operator_vmult_ptr(bp5_operator_t op, double *dst, const double *src, in
 int bp5_operator_assemble_rhs(bp5_operator_t op, bp5_vector_t b) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op, "null operator");
-  BP5_CONFORMING_ONLY(op);
   int rc;
   if ((rc = check_vec(op, b))) return rc;
   BP5_CUDA(cudaSetDevice(op->ctx->device));
@@ -368,7 +366,6 @@ int bp5_operator_compute_diagonal(bp5_operator_t op, bp5_vector_t diag, int inve
 
 int bp5_operator_algorithmic_bytes(bp5_operator_t op, double *per_vmult, double *per_cg_it) {
   BP5_REQUIRE(op, "null operator");
-  BP5_CONFORMING_ONLY(op);
   // per DoF 8 (read src) + 8 (write dst) + 8*planes per q-point;
   // CG: read {x,r,p,h,diag} + write {x,r,p,h} = 72, plus the metric.
   const double n3 = (double)op->n * op->n * op->n;
@@ -552,7 +549,6 @@ int bp5_cg_solve(bp5_operator_t op, bp5_vector_t x, bp5_vector_t b, bp5_vector_t
                  double tol, int max_its, int *last_step, double *last_value, double *history, int history_len) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && x && b, "null argument");
-  BP5_CONFORMING_ONLY(op);
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   return cg_solve(op, x, b, diag, variant, control, tol, max_its, last_step, last_value, history, history_len);
   BP5_ABI_GUARD_END
@@ -562,7 +558,6 @@ int bp5_cg_solve_host(bp5_operator_t op, double *x_host, const double *b_host, i
                       int control, double tol, int max_its, int *last_step, double *last_value) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && x_host && b_host, "null argument");
-  BP5_CONFORMING_ONLY(op);
   BP5_REQUIRE(n == op->n_owned && op->n_ghost == 0, "host solve needs a single block and n == n_dofs");
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   bp5_context_t ctx = op->ctx;
@@ -708,7 +703,6 @@ int bp5_cg_step_update(bp5_operator_t op, int iteration) {
 int bp5_cg_step_apply_local(bp5_operator_t op) {
   BP5_ABI_GUARD_BEGIN
   BP5_STEP_GUARD();
-  BP5_CONFORMING_ONLY(op);
   // h (zeroed by the update step) = local cells' part of A d; the caller exchanges halos around this
   return cg_step_apply_local(op);
   BP5_ABI_GUARD_END

@@ -55,12 +55,12 @@ int apply_choose(bp5_operator_t op) {
   return BP5_OK;
 }
 
-template <int P, int QUAD, int HELM, int OVERWRITE, int MLOAD>
+template <int P, int QUAD, int HELM, int OVERWRITE, int MLOAD, int HANG = 0>
 static int launch(bp5_operator_t op, double *dst, const double *src, double *dot_partials, int which) {
   constexpr int CPT = TileCells<P>::value;
   using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = P + 1;
-  auto kernel = bp5_apply_kernel<P, QUAD, HELM, CPT, OVERWRITE, MLOAD>;
+  auto kernel = bp5_apply_kernel<P, QUAD, HELM, CPT, OVERWRITE, MLOAD, HANG>;
   // per instantiation and per device: function attributes belong to the device's context, and the C ABI allows
   // contexts on several devices in one process
   static int blocks_per_sm_of[64] = {0};
@@ -96,6 +96,9 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
     prm.aff[0] = hc[1] * hc[2] / hc[0]; prm.aff[1] = hc[0] * hc[2] / hc[1]; prm.aff[2] = hc[0] * hc[1] / hc[2];
     for (int q = 0; q < N; ++q) prm.wq[q] = op->tab.wq[q];
   }
+  prm.cell_mask = op->cell_mask;
+  for (int sI = 0; sI < 2; ++sI)
+    for (int i = 0; i < N * N; ++i) prm.hang[sI][i] = op->hanging_interp[sI][i];
   fill_kernel_tables<N>(prm.tab, op->tab.B, op->tab.Dt);
   long long grid = (long long)blocks_per_sm * op->ctx->sm_count;
   if (grid > prm.n_tiles - prm.tile_begin) grid = prm.n_tiles - prm.tile_begin;
@@ -126,6 +129,19 @@ static int launch_pm(bp5_operator_t op, double *dst, const double *src, int mode
 #define BP5_LAUNCH_MODE(M)                                                                                       \
   (gll ? (helm ? launch<P, 1, 1, M, MLOAD>(op, dst, src, dp, which) : launch<P, 1, 0, M, MLOAD>(op, dst, src, dp, which))      \
        : (helm ? launch<P, 0, 1, M, MLOAD>(op, dst, src, dp, which) : launch<P, 0, 0, M, MLOAD>(op, dst, src, dp, which)))
+  if constexpr (MLOAD == 0) {
+    if (op->hanging) {          // locally refined mesh: the kernels that resolve hanging-node constraints
+#define BP5_LAUNCH_HANG(M)                                                                                        \
+  (gll ? (helm ? launch<P, 1, 1, M, 0, 1>(op, dst, src, dp, which) : launch<P, 1, 0, M, 0, 1>(op, dst, src, dp, which))      \
+       : (helm ? launch<P, 0, 1, M, 0, 1>(op, dst, src, dp, which) : launch<P, 0, 0, M, 0, 1>(op, dst, src, dp, which)))
+      if (mode == 2) return BP5_LAUNCH_HANG(2);
+      if (mode == 1) return BP5_LAUNCH_HANG(1);
+      if (mode == 0) return BP5_LAUNCH_HANG(0);
+#undef BP5_LAUNCH_HANG
+      set_error("the coloured cell order is not available on locally refined meshes");
+      return BP5_ERR_UNSUPPORTED;
+    }
+  }
   if constexpr (MLOAD == 0) {   // one colour of the coloured cell order: plain adds (apply.cuh, OWMODE >= 3)
     if (mode == 5) return BP5_LAUNCH_MODE(5);
     if (mode == 4) return BP5_LAUNCH_MODE(4);

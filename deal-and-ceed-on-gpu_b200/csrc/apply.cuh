@@ -113,6 +113,10 @@ struct ApplyParams {
   // register allocation of the other kernels, p = 7 lost its third CTA per SM.)
   double aff[3];
   double wq[N];
+  // HANG (locally refined mesh): constraint mask per cell slot and the two 1D parent-to-child interpolation matrices
+  // [s][a * N + b] (operator_setup_hanging).  Appended for the same reason.
+  const unsigned int *cell_mask;
+  double hang[2][N * N];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -271,6 +275,75 @@ __device__ __forceinline__ void contract_in_regs(double (&w)[N], const double *_
 #endif
 }
 
+// ---- hanging-node constraints of the children of a locally refined mesh (HANG kernels only) ----------------------
+// A node on a constrained face was gathered from the unrefined neighbour's face DoF of the same local index; the
+// child's values are the neighbour's face polynomial at the child's nodes: 1D interpolations along the face's two
+// tangential directions (bp5/fe_evaluation_gl.h:150,167, resolve_hanging_nodes).  mask: bit d = face normal to d
+// constrained, bit 3+d = position of the child in its parent (face at node 0 or p; which matrix).
+// Direction by direction every line inside a constrained face is interpolated once; z-lines are the home columns
+// (registers), x- and y-lines go through the layout-A array `arr` like the contractions.  T: the transposes, for the
+// scatter.  Called by ALL threads of a CTA whose tile has a masked cell (barriers inside).
+template <int N, bool T>
+__device__ __forceinline__ void hang_matvec(double (&v)[N], const double *__restrict__ M) {
+  double w[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double sum = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; ++m) sum += (T ? M[m * N + i] : M[i * N + m]) * v[m];
+    w[i] = sum;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = w[i];
+}
+
+template <int N, bool T, int A1, int A2>
+__device__ __forceinline__ void hang_resolve(double (&u)[N], unsigned int mask, bool active, int a, int b, double *arr,
+                                             const double (*hang)[N * N]) {
+  const int hA = b * A1 + a, xA = b * A2 + a * A1, yA = b * A2 + a;
+  const int f0 = ((mask >> 3) & 1u) ? N - 1 : 0, f1 = ((mask >> 4) & 1u) ? N - 1 : 0, f2 = ((mask >> 5) & 1u) ? N - 1 : 0;
+  const bool c0 = (mask & 1u) != 0, c1 = (mask & 2u) != 0, c2 = (mask & 4u) != 0;
+  const double *M0 = hang[(mask >> 3) & 1u], *M1 = hang[(mask >> 4) & 1u], *M2 = hang[(mask >> 5) & 1u];
+  // home column (i=a, j=b): a z-line; it lies in the constrained x-face if a == f0, in the y-face if b == f1
+  const bool z_line = active && ((c0 && a == f0) || (c1 && b == f1));
+  // x-line role (j=a, k=b): in the y-face if a == f1, in the z-face if b == f2
+  const bool x_line = active && ((c1 && a == f1) || (c2 && b == f2));
+  // y-line role (i=a, k=b): in the x-face if a == f0, in the z-face if b == f2
+  const bool y_line = active && ((c0 && a == f0) || (c2 && b == f2));
+  if (!T && z_line) hang_matvec<N, false>(u, M2);
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) arr[hA + k * A2] = u[k];
+  }
+  __syncthreads();
+  // forward: x then y; transpose: y then x (any order is the same operator; this one mirrors the forward pass)
+  if (T ? y_line : x_line) {
+    double v[N];
+    const int at = T ? yA : xA, st = T ? A1 : 1;
+#pragma unroll
+    for (int m = 0; m < N; ++m) v[m] = arr[at + m * st];
+    hang_matvec<N, T>(v, T ? M1 : M0);
+#pragma unroll
+    for (int m = 0; m < N; ++m) arr[at + m * st] = v[m];
+  }
+  __syncthreads();
+  if (T ? x_line : y_line) {
+    double v[N];
+    const int at = T ? xA : yA, st = T ? 1 : A1;
+#pragma unroll
+    for (int m = 0; m < N; ++m) v[m] = arr[at + m * st];
+    hang_matvec<N, T>(v, T ? M0 : M1);
+#pragma unroll
+    for (int m = 0; m < N; ++m) arr[at + m * st] = v[m];
+  }
+  __syncthreads();
+  if (active && mask != 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) u[k] = arr[hA + k * A2];
+  }
+  if (T && z_line) hang_matvec<N, true>(u, M2);
+}
+
 // MLOAD: how the metric reaches the quadrature phase.
 //   0: one TMA bulk copy per tile into shared memory (mbarrier), read back with LDS;
 //   1: plain streaming loads into registers, issued at the start of the tile;
@@ -315,7 +388,9 @@ struct ApplyCfg {
 // zero on entry, its interior may hold anything); 0 = dst += A src everywhere.
 // OVERWRITE + 3 (3, 4, 5): the same with plain read-modify-writes in place of the atomics, for the launches over
 // the tiles of ONE colour of the coloured cell order (cells of a colour share no DoF): bitwise reproducible.
-template <int P, int QUAD, int HELM, int CPT, int OWMODE, int MLOAD = 0>
+// HANG = 1: the cells may carry hanging-node constraints (prm.cell_mask), resolved after the gather and before the
+// scatter; one extra CTA-wide vote per tile, the exchange passes only in tiles that hold a masked cell.
+template <int P, int QUAD, int HELM, int CPT, int OWMODE, int MLOAD = 0, int HANG = 0>
 __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   constexpr int OVERWRITE = OWMODE % 3;
   constexpr bool PLAIN_ADD = OWMODE >= 3;
@@ -418,6 +493,13 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
 
     if constexpr (MLOAD == 1) {
       if (active) load_metric(tile);
+    }
+    [[maybe_unused]] unsigned int hmask = 0;
+    [[maybe_unused]] bool tile_hangs = false;
+    if constexpr (HANG) {
+      hmask = base_cur != kNoCell ? __ldg(prm.cell_mask + tile * CPT + c) : 0u;
+      tile_hangs = __syncthreads_or(hmask != 0) != 0;
+      if (tile_hangs) hang_resolve<N, false, A1, A2>(u, hmask, active, a, b, s0, prm.hang);
     }
     double t[N];   // z-direction data that stays in registers across the quadrature phase
     double mv[N];  // Helmholtz: values at the quadrature points (home column)
@@ -549,17 +631,38 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
       }
       __syncthreads();
       // (5) home: z-transpose in registers, sum the three directions, scatter
-      if (do_scatter) {
-        double o[N];
-        contract_in_regs<N, -1>(o, DTz, t);
+      if constexpr (!HANG) {
+        if (do_scatter) {
+          double o[N];
+          contract_in_regs<N, -1>(o, DTz, t);
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-          double s = o[k] + s1[hA + k * A2] + s2[hB + k * B2];
-          if constexpr (HELM) s += mv[k];
-          double *dp = dst + idx[k];
-          if (col_interior && k > 0 && k < P) *dp = s;     // multiplicity 1: plain store
-          else if constexpr (PLAIN_ADD) *dp += s;          // one colour per launch: no other cell touches this DoF
-          else atomicAdd(dp, s);                           // skeleton: red.global.add.f64
+          for (int k = 0; k < N; ++k) {
+            double s = o[k] + s1[hA + k * A2] + s2[hB + k * B2];
+            if constexpr (HELM) s += mv[k];
+            double *dp = dst + idx[k];
+            if (col_interior && k > 0 && k < P) *dp = s;     // multiplicity 1: plain store
+            else if constexpr (PLAIN_ADD) *dp += s;          // one colour per launch: no other cell touches this DoF
+            else atomicAdd(dp, s);                           // skeleton: red.global.add.f64
+          }
+        }
+      } else {
+        double o[N];
+        if (do_scatter) {
+          contract_in_regs<N, -1>(o, DTz, t);
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            o[k] += s1[hA + k * A2] + s2[hB + k * B2];
+            if constexpr (HELM) o[k] += mv[k];
+          }
+        }
+        if (tile_hangs) hang_resolve<N, true, A1, A2>(o, hmask, active, a, b, s0, prm.hang);   // s0 is free since (2)
+        if (do_scatter) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            double *dp = dst + idx[k];
+            if (col_interior && k > 0 && k < P) *dp = o[k];
+            else atomicAdd(dp, o[k]);
+          }
         }
       }
     } else {
@@ -599,17 +702,36 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
       }
       __syncthreads();
       // (8) home (i=a, j=b): B^T along z in registers, scatter
-      if (do_scatter) {
-        double v[N], o[N];
+      if constexpr (!HANG) {
+        if (do_scatter) {
+          double v[N], o[N];
 #pragma unroll
-        for (int q = 0; q < N; ++q) v[q] = s0[hA + q * A2];
-        contract_in_regs<N, 1>(o, BTz, v);
+          for (int q = 0; q < N; ++q) v[q] = s0[hA + q * A2];
+          contract_in_regs<N, 1>(o, BTz, v);
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-          double *dp = dst + idx[k];
-          if (col_interior && k > 0 && k < P) *dp = o[k];
-          else if constexpr (PLAIN_ADD) *dp += o[k];
-          else atomicAdd(dp, o[k]);
+          for (int k = 0; k < N; ++k) {
+            double *dp = dst + idx[k];
+            if (col_interior && k > 0 && k < P) *dp = o[k];
+            else if constexpr (PLAIN_ADD) *dp += o[k];
+            else atomicAdd(dp, o[k]);
+          }
+        }
+      } else {
+        double o[N];
+        if (do_scatter) {
+          double v[N];
+#pragma unroll
+          for (int q = 0; q < N; ++q) v[q] = s0[hA + q * A2];
+          contract_in_regs<N, 1>(o, BTz, v);
+        }
+        if (tile_hangs) hang_resolve<N, true, A1, A2>(o, hmask, active, a, b, s1, prm.hang);   // s1 is free since (6b)
+        if (do_scatter) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            double *dp = dst + idx[k];
+            if (col_interior && k > 0 && k < P) *dp = o[k];
+            else atomicAdd(dp, o[k]);
+          }
         }
       }
     }
@@ -633,10 +755,10 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   }
 }
 
-template <int P, int QUAD, int HELM, int CPT, int OWMODE, int MLOAD = 0>
+template <int P, int QUAD, int HELM, int CPT, int OWMODE, int MLOAD = 0, int HANG = 0>
 __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
     bp5_apply_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
-  bp5_apply_body<P, QUAD, HELM, CPT, OWMODE, MLOAD>(prm);
+  bp5_apply_body<P, QUAD, HELM, CPT, OWMODE, MLOAD, HANG>(prm);
 }
 
 }  // namespace bp5

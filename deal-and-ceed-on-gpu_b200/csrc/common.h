@@ -127,6 +127,9 @@ struct bp5_operator_s {
   int *constrained = nullptr;   // local owned indices of Dirichlet dofs
   // locally refined mesh (refine_lo/refine_hi of the problem): generic functor path only, see operator_setup_hanging
   bool hanging = false;
+  void *hanging_cells = nullptr;                  // device int4[n_cells]: (lattice index x, y, z, level) per cell
+  double *hanging_interp_dev = nullptr;           // device copy of hanging_interp
+  unsigned int *cell_mask = nullptr;              // [n_tiles * cells_per_tile] constraint mask per cell slot (tuned kernel)
   double hanging_interp[2][bp5::kMaxN * bp5::kMaxN] = {};   // [s][a * n + b] = l_b((s + xi_a) / 2): parent-to-child, 1D
   std::vector<double> hanging_coords;             // [n_owned][3] mapped support point of every DoF
   int64_t n_constrained = 0;

@@ -103,25 +103,16 @@ __device__ __forceinline__ double det3(const double J[3][3]) {
          J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
 }
 
-// One block per local cell (lexicographic); `slot` is the cell's position in the processing order
-// (cell_slot()).  Writes metric[tile][cell in tile][planes][n3] at that position and, for
-// irregular cells (cell_base < 0), the explicit index table l2g_irr[table][n3].
-__global__ void setup_cells_kernel(BlockGeom g, const int *__restrict__ cell_base, const long long *__restrict__ slot_of,
-                                   int *__restrict__ l2g_irr, double *__restrict__ metric) {
-  extern __shared__ double sm[];
+// The merged coefficient G = JxW J^-1 J^-T (+ a(x) JxW for Helmholtz) of lattice cell (cx, cy, cz) of `g` at this
+// thread's quadrature point, written at processing-order position `slot` of the metric tiles (whole CTA:
+// cell_jacobian synchronises).
+__device__ void write_cell_metric(const BlockGeom &g, double *sm, int cx, int cy, int cz, long long slot,
+                                  double *__restrict__ metric) {
   const int n = g.n, n2 = n * n, n3 = n2 * n;
-  const long long cell = blockIdx.x;
-  const int lcx = cell % g.lc[0], lcy = (cell / g.lc[0]) % g.lc[1], lcz = cell / ((long long)g.lc[0] * g.lc[1]);
   const int t = threadIdx.x;
   const int i = t % n, j = (t / n) % n, k = t / n2;
-  const long long slot = slot_of[cell];
-  const int base = cell_base[slot];
-  if (t < n3 && base < 0)
-    l2g_irr[(long long)(-(base + 1)) * n3 + t] =
-        (int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
-  if (metric == nullptr) return;     // geometry on the fly: only the index tables are needed (uniform per block)
   double J[3][3], xr[3];
-  cell_jacobian(g, c_tab.B, c_tab.Dg, sm, g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz, J, xr);
+  cell_jacobian(g, c_tab.B, c_tab.Dg, sm, cx, cy, cz, J, xr);
   if (t >= n3) return;
   const double det = det3(J);
   const double id = 1.0 / det;
@@ -151,6 +142,26 @@ __global__ void setup_cells_kernel(BlockGeom g, const int *__restrict__ cell_bas
     const double p2 = xr[0] * xr[0] + xr[1] * xr[1] + xr[2] * xr[2];
     out[6LL * n3] = 10.0 / (0.05 + 2.0 * p2) * jxw;
   }
+}
+
+// One block per local cell (lexicographic); `slot` is the cell's position in the processing order
+// (cell_slot()).  Writes metric[tile][cell in tile][planes][n3] at that position and, for
+// irregular cells (cell_base < 0), the explicit index table l2g_irr[table][n3].
+__global__ void setup_cells_kernel(BlockGeom g, const int *__restrict__ cell_base, const long long *__restrict__ slot_of,
+                                   int *__restrict__ l2g_irr, double *__restrict__ metric) {
+  extern __shared__ double sm[];
+  const int n = g.n, n2 = n * n, n3 = n2 * n;
+  const long long cell = blockIdx.x;
+  const int lcx = cell % g.lc[0], lcy = (cell / g.lc[0]) % g.lc[1], lcz = cell / ((long long)g.lc[0] * g.lc[1]);
+  const int t = threadIdx.x;
+  const int i = t % n, j = (t / n) % n, k = t / n2;
+  const long long slot = slot_of[cell];
+  const int base = cell_base[slot];
+  if (t < n3 && base < 0)
+    l2g_irr[(long long)(-(base + 1)) * n3 + t] =
+        (int)local_dof_index(g, lcx * g.p + i, lcy * g.p + j, lcz * g.p + k);
+  if (metric == nullptr) return;     // geometry on the fly: only the index tables are needed (uniform per block)
+  write_cell_metric(g, sm, g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz, slot, metric);
 }
 
 // Right-hand side b_i = int phi_i * 1 with QGauss(p+1) (c_tab must hold the
@@ -243,6 +254,12 @@ static int cell_color(int cx, int cy, int cz) { return (cx & 1) | ((cy & 1) << 1
 
 void operator_plan_tiles(bp5_operator_t op) {
   const int cpt = op->cells_per_tile;
+  if (op->hanging) {     // locally refined mesh: one block, cells in the order of operator_setup_hanging
+    op->n_boundary_cells = 0;
+    op->n_boundary_tiles = 0;
+    op->n_tiles = (op->n_cells + cpt - 1) / cpt;
+    return;
+  }
   if (op->prob.cell_order == BP5_CELL_ORDER_COLORED) {
     // colour-major order, every colour padded to whole tiles (single block: no boundary cells)
     op->n_boundary_cells = 0;
@@ -361,6 +378,11 @@ int operator_setup_device(bp5_operator_t op) {
   return BP5_OK;
 }
 
+__global__ void set_constrained_kernel(const int *__restrict__ list, long long n, double value, double *__restrict__ v);
+__global__ void hanging_rhs_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells,
+                                   const unsigned int *__restrict__ masks, const unsigned int *__restrict__ l2g, int pad,
+                                   const double *__restrict__ interp, double *__restrict__ b);
+
 int operator_assemble_rhs(bp5_operator_t op, double *b_dev) {
   bp5_context_t ctx = op->ctx;
   const int n = op->n, n3 = n * n * n;
@@ -369,6 +391,24 @@ int operator_assemble_rhs(bp5_operator_t op, double *b_dev) {
   make_tables(op->p, BP5_QUAD_GAUSS, tg);   // the reference always assembles with QGauss(p+1), step-64.cu:380
   BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &tg, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
   BP5_CUDA(cudaMemsetAsync(b_dev, 0, sizeof(double) * (op->n_owned + op->n_ghost), ctx->stream));
+  if (op->hanging) {
+    BlockGeom g0 = g, g1 = g;
+    for (int d = 0; d < 3; ++d) { g0.c0[d] = g1.c0[d] = 0; g1.h[d] = 0.5 * g0.h[d]; }
+    const int threads = ((n3 + 31) / 32) * 32;
+    hanging_rhs_kernel<<<(unsigned)op->n_cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
+        g0, g1, static_cast<const int4 *>(op->hanging_cells), op->mf_constraint_mask, op->mf_l2g, op->mf_padding,
+        op->hanging_interp_dev, b_dev);
+    BP5_CHECK_LAUNCH();
+    if (op->n_constrained > 0) {
+      set_constrained_kernel<<<(unsigned)((op->n_constrained + 255) / 256), 256, 0, ctx->stream>>>(op->constrained,
+                                                                                                op->n_constrained, 0.0, b_dev);
+      BP5_CHECK_LAUNCH();
+    }
+    ctx->launches += 2;
+    BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+    BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BP5_OK;
+  }
   const int ex = op->lc[0] + op->has_hi[0], ey = op->lc[1] + op->has_hi[1], ez = op->lc[2] + op->has_hi[2];
   const int threads = ((n3 + 31) / 32) * 32;
   rhs_kernel<<<(unsigned)((long long)ex * ey * ez), threads, sizeof(double) * 8 * n3, ctx->stream>>>(g, ex, ey, ez, b_dev);
@@ -572,10 +612,12 @@ int operator_generic_data(bp5_operator_t op) {
 //               1D interpolation matrix along d).  Unrefined cells: 0.
 __global__ void hanging_geometry_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells, int pad,
                                         double *__restrict__ inv_jac, double *__restrict__ jxw,
-                                        double *__restrict__ qpts) {
+                                        double *__restrict__ qpts, double *__restrict__ metric) {
   extern __shared__ double sm[];
   const int4 c = cells[blockIdx.x];
   write_generic_geometry(c.w ? g1 : g0, sm, c.x, c.y, c.z, blockIdx.x, gridDim.x, pad, inv_jac, jxw, qpts);
+  __syncthreads();
+  write_cell_metric(c.w ? g1 : g0, sm, c.x, c.y, c.z, blockIdx.x, metric);     // tuned kernel: cells in the same order
 }
 
 static void host_map_point(const bp5_problem_t &pr, const double *x, double *y) {
@@ -711,6 +753,11 @@ int operator_setup_hanging(bp5_operator_t op) {
   BP5_REQUIRE(cell == n_cells, "internal error: cell count of the locally refined mesh");
   // ---- sizes, Dirichlet set, 1D parent-to-child interpolation
   op->n_owned = N; op->n_ghost = 0; op->n_global = N; op->n_cells = n_cells;
+  op->hanging = true;
+  {
+    const int rc = apply_choose(op);     // cells per tile, tile plan (operator_plan_tiles), kernel name
+    if (rc != BP5_OK) return rc;
+  }
   std::sort(cons.begin(), cons.end());
   op->n_constrained = (int64_t)cons.size();
   BP5_CUDA(cudaMalloc(&op->constrained, sizeof(int) * std::max<size_t>(cons.size(), 1)));
@@ -736,18 +783,94 @@ int operator_setup_hanging(bp5_operator_t op) {
   BP5_CUDA(cudaMemsetAsync(op->mf_inv_jacobian, 0, sizeof(double) * 9 * cells * pad, ctx->stream));
   BP5_CUDA(cudaMemsetAsync(op->mf_jxw, 0, sizeof(double) * cells * pad, ctx->stream));
   BP5_CUDA(cudaMemsetAsync(op->mf_q_points, 0, sizeof(double) * 3 * cells * pad, ctx->stream));
+  // ---- the tuned kernel's view of the same cells (apply.cuh, HANG): every cell through an explicit index table
+  // (cell_base < 0 selects table -(base + 1) of l2g_irr), the stored metric in cell order, one constraint mask per
+  // cell slot (tile padding: no cell, mask 0)
+  {
+    const int64_t padded = op->n_tiles * op->cells_per_tile;
+    std::vector<int> base((size_t)padded, INT_MIN), table((size_t)n_cells * n3);
+    std::vector<unsigned int> slot_mask((size_t)padded, 0u);
+    for (int64_t cI = 0; cI < n_cells; ++cI) {
+      base[(size_t)cI] = -(int)cI - 1;
+      slot_mask[(size_t)cI] = mask[(size_t)cI];
+      for (int t = 0; t < n3; ++t) table[(size_t)cI * n3 + t] = (int)l2g[(size_t)cI * pad + t];
+    }
+    op->n_irregular = n_cells;
+    BP5_CUDA(cudaMalloc(&op->cell_base, sizeof(int) * padded));
+    BP5_CUDA(cudaMalloc(&op->cell_mask, sizeof(unsigned int) * padded));
+    BP5_CUDA(cudaMalloc(&op->l2g_irr, sizeof(int) * table.size()));
+    BP5_CUDA(cudaMemcpyAsync(op->cell_base, base.data(), sizeof(int) * padded, cudaMemcpyHostToDevice, ctx->stream));
+    BP5_CUDA(cudaMemcpyAsync(op->cell_mask, slot_mask.data(), sizeof(unsigned int) * padded, cudaMemcpyHostToDevice, ctx->stream));
+    BP5_CUDA(cudaMemcpyAsync(op->l2g_irr, table.data(), sizeof(int) * table.size(), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t mbytes = sizeof(double) * op->n_tiles * op->tile_doubles;
+    BP5_CUDA(cudaMalloc(&op->metric, mbytes));
+    BP5_CUDA(cudaMemsetAsync(op->metric, 0, mbytes, ctx->stream));
+    BP5_CUDA(cudaStreamSynchronize(ctx->stream));     // the host vectors above go out of scope
+  }
   BlockGeom g0 = make_geom(op), g1 = g0;
   for (int d = 0; d < 3; ++d) { g0.c0[d] = g1.c0[d] = 0; g1.h[d] = 0.5 * g0.h[d]; }
   BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
   const int threads = ((n3 + 31) / 32) * 32;
   hanging_geometry_kernel<<<(unsigned)cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
-      g0, g1, desc_dev, pad, op->mf_inv_jacobian, op->mf_jxw, op->mf_q_points);
+      g0, g1, desc_dev, pad, op->mf_inv_jacobian, op->mf_jxw, op->mf_q_points, op->metric);
   BP5_CHECK_LAUNCH();
   ctx->launches++;
+  BP5_CUDA(cudaMalloc(&op->hanging_interp_dev, sizeof(double) * 2 * kMaxN * kMaxN));
+  BP5_CUDA(cudaMemcpyAsync(op->hanging_interp_dev, op->hanging_interp, sizeof(double) * 2 * kMaxN * kMaxN,
+                           cudaMemcpyHostToDevice, ctx->stream));
   BP5_CUDA(cudaStreamSynchronize(ctx->stream));
-  BP5_CUDA(cudaFree(desc_dev));
-  op->hanging = true;
+  op->hanging_cells = desc_dev;      // kept for assemble_rhs
   return BP5_OK;
+}
+
+// b_i = int phi_i with QGauss(p+1) on a locally refined mesh (c_tab must hold the GAUSS tables): per cell the local
+// integrals, the transposed hanging-node constraints (what constraints.distribute_local_to_global does at
+// bp5/step-64.cu:411), scatter-add.  One thread per local node.
+__global__ void hanging_rhs_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells,
+                                   const unsigned int *__restrict__ masks, const unsigned int *__restrict__ l2g, int pad,
+                                   const double *__restrict__ interp, double *__restrict__ b) {
+  extern __shared__ double sm[];
+  const int4 c = cells[blockIdx.x];
+  const BlockGeom &g = c.w ? g1 : g0;
+  const int n = g.n, n2 = n * n, n3 = n2 * n;
+  const int t = threadIdx.x;
+  const int i = t % n, j = (t / n) % n, k = t / n2;
+  double J[3][3], xr[3];
+  cell_jacobian(g, c_tab.B, c_tab.Dg, sm, c.x, c.y, c.z, J, xr);
+  double *w0 = sm, *w1 = sm + n3;
+  if (t < n3) w0[t] = det3(J) * c_tab.wq[i] * c_tab.wq[j] * c_tab.wq[k];
+  __syncthreads();
+  if (t < n3) { double s = 0; for (int m = 0; m < n; ++m) s += c_tab.B[m * n + i] * w0[(k * n + j) * n + m]; w1[t] = s; }
+  __syncthreads();
+  if (t < n3) { double s = 0; for (int m = 0; m < n; ++m) s += c_tab.B[m * n + j] * w1[(k * n + m) * n + i]; w0[t] = s; }
+  __syncthreads();
+  if (t < n3) { double s = 0; for (int m = 0; m < n; ++m) s += c_tab.B[m * n + k] * w0[(m * n + j) * n + i]; w1[t] = s; }
+  __syncthreads();
+  // transposed constraints, direction by direction (mask uniform per cell)
+  const unsigned int mask = masks[blockIdx.x];
+  if (mask != 0) {
+    const int pos[3] = {i, j, k}, stride[3] = {1, n, n2};
+    bool on_face[3];
+    for (int d = 0; d < 3; ++d) on_face[d] = ((mask >> d) & 1u) && pos[d] == (((mask >> (3 + d)) & 1u) ? n - 1 : 0);
+    for (int d = 0; d < 3; ++d) {
+      if (((mask & 7u) & ~(1u << d)) == 0) continue;
+      const double *M = interp + ((mask >> (3 + d)) & 1u) * kMaxN * kMaxN;
+      double v = 0.0;
+      const bool in_face = t < n3 && (on_face[(d + 1) % 3] || on_face[(d + 2) % 3]);
+      if (t < n3) {
+        v = w1[t];
+        if (in_face) {
+          v = 0.0;
+          const int base = t - pos[d] * stride[d];
+          for (int m = 0; m < n; ++m) v += M[m * n + pos[d]] * w1[base + m * stride[d]];
+        }
+      }
+      __syncthreads();
+      if (t < n3) w1[t] = v;
+      __syncthreads();
+    }
+  }
+  if (t < n3) atomicAdd(&b[l2g[(long long)blockIdx.x * pad + t]], w1[t]);
 }
 
 // ---------------------------------------------------------------------------

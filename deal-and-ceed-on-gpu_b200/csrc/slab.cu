@@ -300,7 +300,7 @@ struct SlabPlan {
 // that share its SMs slow it down by more than the saved HBM passes give back, and every slab boundary costs ~10 us.
 bool slab_supported(bp5_operator_t op) {
   if (op->prob.geometry_mode != BP5_GEOM_STORED || op->metric == nullptr) return false;
-  if (op->prob.cell_order != BP5_CELL_ORDER_DEFAULT) return false;
+  if (op->prob.cell_order != BP5_CELL_ORDER_DEFAULT || op->hanging) return false;
   return op->prob.part_grid[0] * op->prob.part_grid[1] * op->prob.part_grid[2] == 1;
 }
 

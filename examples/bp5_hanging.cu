@@ -77,6 +77,32 @@ int run(bool collocation, const std::vector<unsigned int> &cells, const std::arr
   double num = 0., den = 0.;
   for (std::size_t i = 0; i < h.size(); ++i) { num += (h[i] - h2[i]) * (h[i] - h2[i]); den += h[i] * h[i]; }
   std::cout << "merged_vs_plain_rel_diff " << std::sqrt(num / den) << std::endl;
+  {  // the library's tuned operator on the same mesh (same numbering): right-hand side, vmult, merged CG
+    BP5::PoissonOperator<dim, fe_degree> lib_op(dof_handler, constraints, collocation ? BP5_QUAD_GLL : BP5_QUAD_GAUSS);
+    VectorType bl, yl, xl;
+    lib_op.initialize_dof_vector(bl);
+    yl.reinit(bl); xl.reinit(bl);
+    lib_op.assemble_rhs(bl);
+    lib_op.vmult(yl, bl);
+    std::vector<double> hb, hl;
+    b.copy_to_host(hb); bl.copy_to_host(hl);
+    double nb = 0., db = 0., ny = 0., dy = 0.;
+    for (std::size_t i = 0; i < hb.size(); ++i) { nb += (hb[i] - hl[i]) * (hb[i] - hl[i]); db += hb[i] * hb[i]; }
+    yl.copy_to_host(hl);
+    for (std::size_t i = 0; i < h.size(); ++i) { ny += (h[i] - hl[i]) * (h[i] - hl[i]); dy += h[i] * h[i]; }
+    std::cout << "library_rhs_rel_diff " << std::sqrt(nb / db) << std::endl;
+    std::cout << "library_vmult_rel_diff " << std::sqrt(ny / dy) << std::endl;
+    DiagonalMatrix<VectorType> pl;
+    pl.get_vector().reinit(bl);
+    pl.get_vector() = 1.;
+    SolverControl cl(1000, 1e-8 * bl.l2_norm());
+    lib_op.do_zero_out = false;
+    xl = 0.;
+    SolverCGFullMerge<VectorType> sl(cl);
+    sl.solve(lib_op, xl, bl, pl);
+    std::cout << "library_merged_its " << cl.last_step() << std::endl;
+    std::cout << "library_norm_x " << xl.l2_norm() << std::endl;
+  }
   std::cout << "norm_b " << b.l2_norm() << std::endl;
   std::cout << "norm_Ab " << y.l2_norm() << std::endl;
   std::vector<double> uh(dof_handler.n_dofs());

@@ -166,9 +166,9 @@ template <int dim> class Triangulation {
   }
   // Local refinement, one level: what flagging every cell with (x-fastest lattice) index in [lo, hi) and calling
   // execute_coarsening_and_refinement() does in deal.II -- those cells are replaced by their eight children, and the
-  // children's faces on the box's surface carry hanging nodes.  Such a mesh is served by CUDAWrappers::MatrixFree +
-  // FEEvaluationGL (constraint_mask / resolve_hanging_nodes, bp5/fe_evaluation_gl.h:88,150,167), not by the tuned
-  // BP5::PoissonOperator.  Call after refine_global.
+  // children's faces on the box's surface carry hanging nodes, which both paths resolve: CUDAWrappers::MatrixFree +
+  // FEEvaluationGL (constraint_mask / resolve_hanging_nodes, bp5/fe_evaluation_gl.h:88,150,167) and the tuned
+  // BP5::PoissonOperator / Step64::HelmholtzOperator.  One block (no communicator).  Call after refine_global.
   void refine_cells_in_box(const std::array<unsigned int, 3> &lo, const std::array<unsigned int, 3> &hi) {
     for (int d = 0; d < 3; ++d) {
       if (!(lo[d] < hi[d] && hi[d] <= cells(d))) throw ExcMessage("refine_cells_in_box: need lo < hi <= cells");
@@ -370,11 +370,9 @@ template <int dim, int fe_degree, int operator_kind> class MatrixFreeOperator {
                      bool use_coloring = false)
       : do_zero_out(true) {
     const Triangulation<dim> &t = dof_handler.get_triangulation();
-    if (t.locally_refined())
-      throw ExcMessage("locally refined meshes run through CUDAWrappers::MatrixFree + FEEvaluationGL "
-                       "(cuda_matrix_free.cuh); the tuned operators handle conforming meshes");
     bp5_problem_t pr{};
     pr.degree = fe_degree; pr.quadrature = quadrature; pr.operator_kind = operator_kind;
+    for (int d = 0; d < 3; ++d) { pr.refine_lo[d] = t.refine_lo[d]; pr.refine_hi[d] = t.refine_hi[d]; }
     pr.geometry_mode = BP5_GEOM_STORED;
     pr.cell_order = use_coloring ? BP5_CELL_ORDER_COLORED : BP5_CELL_ORDER_DEFAULT;
     comm = t.communicator;

@@ -59,6 +59,8 @@ def test_hanging_node_mesh_matches_the_oracle(p, cells, lo, hi, eps, quad, tmp_p
     assert _rel(vec("Ab"), hm.vmult(b, A=A)) <= 1e-12
     assert _rel(vec("Au"), hm.vmult(u, A=A)) <= 1e-12                                      # fp64 operator: 1e-12
     assert v["merged_vs_plain_rel_diff"] <= 1e-12
+    # the library's tuned operator through the facade, same mesh and numbering
+    assert v["library_rhs_rel_diff"] <= 1e-12 and v["library_vmult_rel_diff"] <= 1e-12
     if quad == "gauss":
         assert _rel(vec("Hu"), hm.vmult(u, kind=O.HELMHOLTZ)) <= 1e-12
     x, its, _ = hm.cg(b, tol=1e-8 * np.linalg.norm(b), max_its=1000)
@@ -66,20 +68,63 @@ def test_hanging_node_mesh_matches_the_oracle(p, cells, lo, hi, eps, quad, tmp_p
     assert abs(v["merged_its"] - its) <= max(1, its // 100)
     assert _rel(vec("x"), x) <= 1e-6
     assert v["norm_x"] == pytest.approx(np.linalg.norm(x), rel=1e-6)
+    assert abs(v["library_merged_its"] - its) <= max(1, its // 100)
+    assert v["library_norm_x"] == pytest.approx(np.linalg.norm(x), rel=1e-6)
 
 
-def test_tuned_kernel_entry_points_reject_locally_refined_meshes(gpu_ctx):
+@pytest.mark.parametrize("p,cells,lo,hi,eps", CASES)
+@pytest.mark.parametrize("quad", [0, 1])
+def test_tuned_kernel_on_a_locally_refined_mesh_matches_the_oracle(gpu_ctx, p, cells, lo, hi, eps, quad):
+    """the same meshes through the TUNED cell kernel (apply.cuh, HANG: constraints resolved between gather /
+    contractions / scatter) behind the plain operator API: vmult, accumulate semantics, right-hand side, Helmholtz,
+    merged and standard CG"""
     import dealceed_b200 as dc
-    pr = dc.make_problem(2, (3, 3, 3))
-    for d in range(3):
-        pr.refine_lo[d], pr.refine_hi[d] = 1, 2
-    op = dc.PoissonOperator(gpu_ctx, pr)
-    assert op.n_cells == 27 - 1 + 8
-    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
-    with pytest.raises(dc.Bp5Error) as e:
+    import oracle as O
+    from hanging_oracle import HangingMesh
+    hm = HangingMesh(p, cells, lo, hi, quad=quad, upper=(1., 1., 1.), deform=1 if eps else 0, eps=eps)
+    rng = np.random.default_rng(p + 10 * quad)
+    u, w = rng.standard_normal(hm.n_dofs), rng.standard_normal(hm.n_dofs)
+    for kind in ((O.POISSON, O.HELMHOLTZ) if quad == 0 else (O.POISSON,)):
+        op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=quad, operator_kind=kind, upper=(1., 1., 1.),
+                                                         deformation=1 if eps else 0, eps=eps, refine_lo=lo, refine_hi=hi))
+        assert (op.n_owned, op.n_cells) == (hm.n_dofs, hm.n_cells)
+        assert np.abs(op.dof_coordinates() - hm.dof_coords()).max() <= 1e-13
+        A = hm.matrix(kind)
+        src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        src.import_host(u)
         op.vmult(dst, src)
-    assert "generic functor path" in str(e.value)
-    src.close(); dst.close(); op.close()
-    pr.refine_hi[0] = 9
+        assert _rel(dst.to_host(), hm.vmult(u, kind, A)) <= 1e-12
+        dst.import_host(w)
+        op.cell_loop(dst, src)                                      # dst += A src, no Dirichlet copy
+        assert _rel(dst.to_host(), w + A @ u) <= 1e-12
+        b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+        op.assemble_rhs(b)
+        bo = hm.rhs()
+        assert _rel(b.to_host(), bo) <= 1e-12
+        xo, its, _ = hm.cg(bo, kind=kind, tol=1e-8 * np.linalg.norm(bo), max_its=1000)
+        for Solver, zero in ((dc.SolverCGFullMerge, False), (dc.SolverCG, True)):
+            ctl = dc.SolverControl(1000, 1e-8 * np.linalg.norm(bo))
+            op.do_zero_out = zero
+            x.set(0.0)
+            Solver(ctl).solve(op, x, b)
+            assert abs(ctl.last_step() - its) <= max(1, its // 100)
+            assert _rel(x.to_host(), xo) <= 1e-6
+        for v in (src, dst, b, x):
+            v.close()
+        op.close()
+
+
+def test_entry_points_without_a_locally_refined_implementation_say_so(gpu_ctx):
+    import dealceed_b200 as dc
+    op = dc.PoissonOperator(gpu_ctx, dc.make_problem(2, (3, 3, 3), refine_lo=(1, 1, 1), refine_hi=(2, 2, 2)))
+    assert op.n_cells == 27 - 1 + 8
+    d = op.initialize_dof_vector()
+    with pytest.raises(dc.Bp5Error) as e:
+        op.compute_diagonal(d)
+    assert "locally refined" in str(e.value)
+    d.close(); op.close()
     with pytest.raises(dc.Bp5Error):
-        dc.PoissonOperator(gpu_ctx, pr)
+        dc.PoissonOperator(gpu_ctx, dc.make_problem(2, (3, 3, 3), refine_lo=(1, 1, 1), refine_hi=(9, 2, 2)))
+    with pytest.raises(dc.Bp5Error):
+        dc.PoissonOperator(gpu_ctx, dc.make_problem(2, (3, 3, 3), refine_lo=(1, 1, 1), refine_hi=(2, 2, 2),
+                                                    cell_order=dc.CELL_ORDER_COLORED))
