@@ -298,7 +298,7 @@ __device__ __forceinline__ void hang_matvec(double (&v)[N], const double *__rest
 }
 
 template <int N, bool T, int A1, int A2>
-__device__ __forceinline__ void hang_resolve(double (&u)[N], unsigned int mask, bool active, int a, int b, double *arr,
+__device__ __noinline__ void hang_resolve(double (&u)[N], unsigned int mask, bool active, int a, int b, double *arr,
                                              const double (*hang)[N * N]) {
   const int hA = b * A1 + a, xA = b * A2 + a * A1, yA = b * A2 + a;
   const int f0 = ((mask >> 3) & 1u) ? N - 1 : 0, f1 = ((mask >> 4) & 1u) ? N - 1 : 0, f2 = ((mask >> 5) & 1u) ? N - 1 : 0;

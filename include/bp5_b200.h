@@ -75,9 +75,9 @@ typedef struct bp5_problem {
   int32_t cell_order;      /* BP5_CELL_ORDER_* (single block, stored geometry) */
   int32_t refine_lo[3];    /* locally refined mesh: the coarse cells with indices in [refine_lo, refine_hi) are replaced */
   int32_t refine_hi[3];    /* by their eight children (hanging nodes on the box's faces); all zero: conforming mesh.    */
-                           /* Such an operator serves the generic functor path only (bp5_operator_matrix_free_data,     */
-                           /* vectors, copy_constrained_values, stepwise CG); the tuned kernel's entry points return    */
-                           /* BP5_ERR_UNSUPPORTED.  Single block, stored geometry.                                      */
+                           /* vmult, cell_loop, assemble_rhs, the CG solves and bp5_operator_matrix_free_data (user     */
+                           /* functors) work on such an operator; diagonal, L2 norm, coefficient export return          */
+                           /* BP5_ERR_UNSUPPORTED.  Single block, stored geometry, default cell order.                  */
   int32_t reserved[1];     /* must be zero */
 } bp5_problem_t;
 
