@@ -344,6 +344,36 @@ def measure_small_mesh(dc, torch, ctx, stream, args):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
+def measure_refined_mesh(dc, torch, ctx, stream, args):
+    """Merged CG through the tuned kernel on a locally refined mesh (hanging nodes on the faces of the refined box,
+    the `constraint_mask` slot of bp5/fe_evaluation_gl.h:88,150,167): (cells/2)^3 coarse cells, the corner octant refined
+    once.  Reported under "variants"; never fatal."""
+    try:
+        cells = max(8, args.cells // 2)
+        op = dc.PoissonOperator(ctx, dc.make_problem(args.degree, (cells,) * 3, quadrature=dc.QUAD_GLL, refine_lo=(0, 0, 0),
+                                                     refine_hi=(cells // 2,) * 3))
+        b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+        op.assemble_rhs(b)
+        control = dc.IterationNumberControl(MAX_ITS, 1e-6 * b.l2_norm())
+        op.do_zero_out = False
+        solver = dc.SolverCGFullMerge(control)
+        x.set(0.0); solver.solve(op, x, b, history=False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        x.set(0.0); solver.solve(op, x, b, history=False)
+        its = control.last_step()
+        e1.record(stream); e1.synchronize()
+        secs = e0.elapsed_time(e1) * 1e-3
+        out = {"workload": f"BP5 p={args.degree} GLL, {cells}^3 coarse cells with the corner {cells // 2}^3 refined once = "
+                           f"{op.n_cells} cells, {op.n_owned} DoFs (hanging nodes), merged CG, tuned kernel",
+               "dofs": op.n_owned, "cells": op.n_cells, "value": op.n_owned * its / secs / 1e9, "unit": UNIT,
+               "ms_per_iteration": secs / max(1, its) * 1e3, "x_l2": x.l2_norm()}
+        b.close(); x.close(); op.close()
+        return out
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def measure_user_functor(hbm_peak):
     """What staying on the reference's device-functor API costs (examples/bp5_functors.cu bench mode): the user-written
     LocalPoissonOperator on CUDAWrappers::MatrixFree / FEEvaluationGL (one CTA per cell, deal.II-layout arrays) against
@@ -407,10 +437,11 @@ def run_b200(args):
             r["e2e"] = measure_e2e(dc, torch, ctx, stream, op, max(1, min(args.steps, 3)), args.warmup)
         results[qname] = r
         op.close()
-    helm = affine = small = None
+    helm = affine = small = refined = None
     if not args.no_variants:
         helm = measure_helmholtz(dc, torch, ctx, stream)
         small = measure_small_mesh(dc, torch, ctx, stream, args)
+        refined = measure_refined_mesh(dc, torch, ctx, stream, args)
         if not args.deformation:
             affine = measure_affine_otf(dc, torch, ctx, stream, args, hbm_peak)
     ctx.close()
@@ -487,6 +518,8 @@ def run_b200(args):
         variants["geometry_on_the_fly_affine"] = affine
     if small is not None:
         variants["strong_small_mesh_n1"] = small
+    if refined is not None:
+        variants["locally_refined_mesh"] = refined
     if not args.no_variants:
         variants["user_functor"] = measure_user_functor(hbm_peak)
     out["variants"] = variants

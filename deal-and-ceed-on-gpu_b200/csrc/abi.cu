@@ -585,7 +585,7 @@ int bp5_operator_matrix_free_data(bp5_operator_t op, bp5_matrix_free_data_t *out
   BP5_REQUIRE(op->n_ghost == 0, "the generic functor path handles a single block");
   BP5_CUDA(cudaSetDevice(op->ctx->device));
   int rc;
-  if (!op->hanging && (rc = operator_generic_data(op))) return rc;
+  if ((rc = op->hanging ? operator_generic_data_hanging(op) : operator_generic_data(op))) return rc;
   std::memset(out, 0, sizeof(*out));
   for (int sI = 0; sI < 2; ++sI)
     for (int i = 0; i < op->n * op->n; ++i) out->hanging_interpolation[sI][i] = op->hanging_interp[sI][i];

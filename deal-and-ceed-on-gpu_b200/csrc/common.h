@@ -166,6 +166,7 @@ struct bp5_operator_s {
 
 namespace bp5 {
 // setup.cu
+int operator_generic_data_hanging(bp5_operator_t op);   // the same arrays for a locally refined mesh, on first use
 int operator_setup_hanging(bp5_operator_t op);      // locally refined mesh: numbering + generic-path arrays
 void operator_plan_tiles(bp5_operator_t op);       // fills n_boundary_cells, n_boundary_tiles, n_tiles
 int operator_setup_device(bp5_operator_t op);

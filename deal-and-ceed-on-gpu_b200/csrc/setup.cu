@@ -380,7 +380,7 @@ int operator_setup_device(bp5_operator_t op) {
 
 __global__ void set_constrained_kernel(const int *__restrict__ list, long long n, double value, double *__restrict__ v);
 __global__ void hanging_rhs_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells,
-                                   const unsigned int *__restrict__ masks, const unsigned int *__restrict__ l2g, int pad,
+                                   const unsigned int *__restrict__ masks, const int *__restrict__ l2g, int pad,
                                    const double *__restrict__ interp, double *__restrict__ b);
 
 int operator_assemble_rhs(bp5_operator_t op, double *b_dev) {
@@ -396,8 +396,7 @@ int operator_assemble_rhs(bp5_operator_t op, double *b_dev) {
     for (int d = 0; d < 3; ++d) { g0.c0[d] = g1.c0[d] = 0; g1.h[d] = 0.5 * g0.h[d]; }
     const int threads = ((n3 + 31) / 32) * 32;
     hanging_rhs_kernel<<<(unsigned)op->n_cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
-        g0, g1, static_cast<const int4 *>(op->hanging_cells), op->mf_constraint_mask, op->mf_l2g, op->mf_padding,
-        op->hanging_interp_dev, b_dev);
+        g0, g1, static_cast<const int4 *>(op->hanging_cells), op->cell_mask, op->l2g_irr, n3, op->hanging_interp_dev, b_dev);
     BP5_CHECK_LAUNCH();
     if (op->n_constrained > 0) {
       set_constrained_kernel<<<(unsigned)((op->n_constrained + 255) / 256), 256, 0, ctx->stream>>>(op->constrained,
@@ -610,14 +609,53 @@ int operator_generic_data(bp5_operator_t op) {
 //   mask        bit d (0..2): the child's face normal to d on the parent's boundary is constrained;
 //               bit 3 + d: the child's position s_d in the parent (selects the face: low if 0, high if 1, and the
 //               1D interpolation matrix along d).  Unrefined cells: 0.
-__global__ void hanging_geometry_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells, int pad,
-                                        double *__restrict__ inv_jac, double *__restrict__ jxw,
-                                        double *__restrict__ qpts, double *__restrict__ metric) {
+// the stored metric of the tuned kernel, cells in the order of the descriptors (= processing order)
+__global__ void hanging_metric_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells,
+                                      double *__restrict__ metric) {
   extern __shared__ double sm[];
   const int4 c = cells[blockIdx.x];
+  write_cell_metric(c.w ? g1 : g0, sm, c.x, c.y, c.z, blockIdx.x, metric);
+}
+// the generic functor path's arrays (deal.II layout), built on first use: geometry per cell, the index tables padded to
+// padding_length, the masks
+__global__ void hanging_geometry_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells, int pad,
+                                        const int *__restrict__ tables, const unsigned int *__restrict__ slot_mask,
+                                        unsigned int *__restrict__ l2g, unsigned int *__restrict__ masks,
+                                        double *__restrict__ inv_jac, double *__restrict__ jxw,
+                                        double *__restrict__ qpts) {
+  extern __shared__ double sm[];
+  const int4 c = cells[blockIdx.x];
+  const int n3 = g0.n * g0.n * g0.n;
+  if ((int)threadIdx.x < n3) l2g[(long long)blockIdx.x * pad + threadIdx.x] = (unsigned int)tables[(long long)blockIdx.x * n3 + threadIdx.x];
+  if (threadIdx.x == 0) masks[blockIdx.x] = slot_mask[blockIdx.x];
   write_generic_geometry(c.w ? g1 : g0, sm, c.x, c.y, c.z, blockIdx.x, gridDim.x, pad, inv_jac, jxw, qpts);
-  __syncthreads();
-  write_cell_metric(c.w ? g1 : g0, sm, c.x, c.y, c.z, blockIdx.x, metric);     // tuned kernel: cells in the same order
+}
+
+int operator_generic_data_hanging(bp5_operator_t op) {
+  if (op->mf_l2g) return BP5_OK;
+  bp5_context_t ctx = op->ctx;
+  const int n3 = op->n * op->n * op->n, pad = op->mf_padding;
+  const size_t cells = (size_t)op->n_cells;
+  BP5_CUDA(cudaMalloc(&op->mf_l2g, sizeof(unsigned int) * cells * pad));
+  BP5_CUDA(cudaMalloc(&op->mf_constraint_mask, sizeof(unsigned int) * cells));
+  BP5_CUDA(cudaMalloc(&op->mf_inv_jacobian, sizeof(double) * 9 * cells * pad));
+  BP5_CUDA(cudaMalloc(&op->mf_jxw, sizeof(double) * cells * pad));
+  BP5_CUDA(cudaMalloc(&op->mf_q_points, sizeof(double) * 3 * cells * pad));
+  BP5_CUDA(cudaMemsetAsync(op->mf_l2g, 0, sizeof(unsigned int) * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->mf_inv_jacobian, 0, sizeof(double) * 9 * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->mf_jxw, 0, sizeof(double) * cells * pad, ctx->stream));
+  BP5_CUDA(cudaMemsetAsync(op->mf_q_points, 0, sizeof(double) * 3 * cells * pad, ctx->stream));
+  BlockGeom g0 = make_geom(op), g1 = g0;
+  for (int d = 0; d < 3; ++d) { g0.c0[d] = g1.c0[d] = 0; g1.h[d] = 0.5 * g0.h[d]; }
+  BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = ((n3 + 31) / 32) * 32;
+  hanging_geometry_kernel<<<(unsigned)cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
+      g0, g1, static_cast<const int4 *>(op->hanging_cells), pad, op->l2g_irr, op->cell_mask, op->mf_l2g,
+      op->mf_constraint_mask, op->mf_inv_jacobian, op->mf_jxw, op->mf_q_points);
+  BP5_CHECK_LAUNCH();
+  ctx->launches++;
+  BP5_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BP5_OK;
 }
 
 static void host_map_point(const bp5_problem_t &pr, const double *x, double *y) {
@@ -703,7 +741,8 @@ int operator_setup_hanging(bp5_operator_t op) {
   int pad = 1;
   while (pad < n3) pad <<= 1;
   op->mf_padding = pad;
-  std::vector<unsigned int> l2g((size_t)n_cells * pad, 0u), mask((size_t)n_cells, 0u);
+  std::vector<int> l2g((size_t)n_cells * n3, 0);      // [cell][n3]: the tuned kernel's index tables
+  std::vector<unsigned int> mask((size_t)n_cells, 0u);
   std::vector<int4> desc((size_t)n_cells);
   int64_t cell = 0;
   for (int cz = 0; cz < c[2]; ++cz)
@@ -712,7 +751,7 @@ int operator_setup_hanging(bp5_operator_t op) {
         if (in_box(cx, cy, cz)) continue;
         for (int t = 0; t < n3; ++t) {
           const int64_t kx = (int64_t)cx * p + t % n, ky = (int64_t)cy * p + (t / n) % n, kz = (int64_t)cz * p + t / (n * n);
-          l2g[(size_t)cell * pad + t] = (unsigned int)coarse_id[(size_t)(kx + nc[0] * (ky + nc[1] * kz))];
+          l2g[(size_t)cell * n3 + t] = coarse_id[(size_t)(kx + nc[0] * (ky + nc[1] * kz))];
         }
         desc[(size_t)cell] = make_int4(cx, cy, cz, 0);
         ++cell;
@@ -745,7 +784,7 @@ int operator_setup_hanging(bp5_operator_t op) {
               id = fine_id[(size_t)(fx + nf[0] * (fy + nf[1] * fz))];
             }
             BP5_REQUIRE(id >= 0, "internal error: cell node without a DoF on the locally refined mesh");
-            l2g[(size_t)cell * pad + t] = (unsigned int)id;
+            l2g[(size_t)cell * n3 + t] = id;
           }
           desc[(size_t)cell] = make_int4(2 * px + sd[0], 2 * py + sd[1], 2 * pz + sd[2], 1);
           ++cell;
@@ -768,33 +807,22 @@ int operator_setup_hanging(bp5_operator_t op) {
       lagrange_eval(n, op->tab.xi, 0.5 * (s + op->tab.xi[a]), val, der);
       for (int b = 0; b < n; ++b) op->hanging_interp[s][a * n + b] = val[b];
     }
-  // ---- arrays in deal.II's layout
   const size_t cells = (size_t)n_cells;
   int4 *desc_dev = nullptr;
   BP5_CUDA(cudaMalloc(&desc_dev, sizeof(int4) * cells));
   BP5_CUDA(cudaMemcpyAsync(desc_dev, desc.data(), sizeof(int4) * cells, cudaMemcpyHostToDevice, ctx->stream));
-  BP5_CUDA(cudaMalloc(&op->mf_l2g, sizeof(unsigned int) * cells * pad));
-  BP5_CUDA(cudaMalloc(&op->mf_constraint_mask, sizeof(unsigned int) * cells));
-  BP5_CUDA(cudaMalloc(&op->mf_inv_jacobian, sizeof(double) * 9 * cells * pad));
-  BP5_CUDA(cudaMalloc(&op->mf_jxw, sizeof(double) * cells * pad));
-  BP5_CUDA(cudaMalloc(&op->mf_q_points, sizeof(double) * 3 * cells * pad));
-  BP5_CUDA(cudaMemcpyAsync(op->mf_l2g, l2g.data(), sizeof(unsigned int) * cells * pad, cudaMemcpyHostToDevice, ctx->stream));
-  BP5_CUDA(cudaMemcpyAsync(op->mf_constraint_mask, mask.data(), sizeof(unsigned int) * cells, cudaMemcpyHostToDevice, ctx->stream));
-  BP5_CUDA(cudaMemsetAsync(op->mf_inv_jacobian, 0, sizeof(double) * 9 * cells * pad, ctx->stream));
-  BP5_CUDA(cudaMemsetAsync(op->mf_jxw, 0, sizeof(double) * cells * pad, ctx->stream));
-  BP5_CUDA(cudaMemsetAsync(op->mf_q_points, 0, sizeof(double) * 3 * cells * pad, ctx->stream));
   // ---- the tuned kernel's view of the same cells (apply.cuh, HANG): every cell through an explicit index table
   // (cell_base < 0 selects table -(base + 1) of l2g_irr), the stored metric in cell order, one constraint mask per
   // cell slot (tile padding: no cell, mask 0)
   {
     const int64_t padded = op->n_tiles * op->cells_per_tile;
-    std::vector<int> base((size_t)padded, INT_MIN), table((size_t)n_cells * n3);
+    std::vector<int> base((size_t)padded, INT_MIN);
     std::vector<unsigned int> slot_mask((size_t)padded, 0u);
     for (int64_t cI = 0; cI < n_cells; ++cI) {
       base[(size_t)cI] = -(int)cI - 1;
       slot_mask[(size_t)cI] = mask[(size_t)cI];
-      for (int t = 0; t < n3; ++t) table[(size_t)cI * n3 + t] = (int)l2g[(size_t)cI * pad + t];
     }
+    const std::vector<int> &table = l2g;
     op->n_irregular = n_cells;
     BP5_CUDA(cudaMalloc(&op->cell_base, sizeof(int) * padded));
     BP5_CUDA(cudaMalloc(&op->cell_mask, sizeof(unsigned int) * padded));
@@ -811,8 +839,7 @@ int operator_setup_hanging(bp5_operator_t op) {
   for (int d = 0; d < 3; ++d) { g0.c0[d] = g1.c0[d] = 0; g1.h[d] = 0.5 * g0.h[d]; }
   BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
   const int threads = ((n3 + 31) / 32) * 32;
-  hanging_geometry_kernel<<<(unsigned)cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
-      g0, g1, desc_dev, pad, op->mf_inv_jacobian, op->mf_jxw, op->mf_q_points, op->metric);
+  hanging_metric_kernel<<<(unsigned)cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(g0, g1, desc_dev, op->metric);
   BP5_CHECK_LAUNCH();
   ctx->launches++;
   BP5_CUDA(cudaMalloc(&op->hanging_interp_dev, sizeof(double) * 2 * kMaxN * kMaxN));
@@ -827,7 +854,7 @@ int operator_setup_hanging(bp5_operator_t op) {
 // integrals, the transposed hanging-node constraints (what constraints.distribute_local_to_global does at
 // bp5/step-64.cu:411), scatter-add.  One thread per local node.
 __global__ void hanging_rhs_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells,
-                                   const unsigned int *__restrict__ masks, const unsigned int *__restrict__ l2g, int pad,
+                                   const unsigned int *__restrict__ masks, const int *__restrict__ l2g, int pad,
                                    const double *__restrict__ interp, double *__restrict__ b) {
   extern __shared__ double sm[];
   const int4 c = cells[blockIdx.x];

@@ -21,7 +21,8 @@ for p in degrees:
         op = dc.PoissonOperator(ctx, dc.make_problem(p, (nc, nc, nc), quadrature=quad, geometry_mode=geom,
                                                      deformation=1 if eps else 0, eps=eps,
                                                      cell_order=int(os.environ.get('PROBE_COLORED', '0')),
-                                                     **(dict(refine_lo=(0, 0, 0), refine_hi=(nc // 2,) * 3) if os.environ.get('PROBE_REFINE') else {})))
+                                                     **(dict(refine_lo=(0, 0, 0), refine_hi=((nc,) * 3 if os.environ.get('PROBE_REFINE') == 'full' else (nc // 2,) * 3))
+                                                        if os.environ.get('PROBE_REFINE') else {})))
         n = op.n_owned
         src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
         src.import_host(np.random.default_rng(0).standard_normal(n))
