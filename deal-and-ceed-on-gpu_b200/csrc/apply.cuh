@@ -297,9 +297,11 @@ __device__ __forceinline__ void hang_matvec(double (&v)[N], const double *__rest
   for (int i = 0; i < N; ++i) v[i] = w[i];
 }
 
+// The home columns are exchanged through `arr` by the caller (publish before, reload after), so that no register array
+// crosses this (deliberately not inlined) function: the main loop keeps its register allocation and has no stack.
 template <int N, bool T, int A1, int A2>
-__device__ __noinline__ void hang_resolve(double (&u)[N], unsigned int mask, bool active, int a, int b, double *arr,
-                                             const double (*hang)[N * N]) {
+__device__ __noinline__ void hang_exchange(unsigned int mask, bool active, int a, int b, double *arr,
+                                           const double (*hang)[N * N]) {
   const int hA = b * A1 + a, xA = b * A2 + a * A1, yA = b * A2 + a;
   const int f0 = ((mask >> 3) & 1u) ? N - 1 : 0, f1 = ((mask >> 4) & 1u) ? N - 1 : 0, f2 = ((mask >> 5) & 1u) ? N - 1 : 0;
   const bool c0 = (mask & 1u) != 0, c1 = (mask & 2u) != 0, c2 = (mask & 4u) != 0;
@@ -310,38 +312,22 @@ __device__ __noinline__ void hang_resolve(double (&u)[N], unsigned int mask, boo
   const bool x_line = active && ((c1 && a == f1) || (c2 && b == f2));
   // y-line role (i=a, k=b): in the x-face if a == f0, in the z-face if b == f2
   const bool y_line = active && ((c0 && a == f0) || (c2 && b == f2));
-  if (!T && z_line) hang_matvec<N, false>(u, M2);
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < N; ++k) arr[hA + k * A2] = u[k];
-  }
-  __syncthreads();
-  // forward: x then y; transpose: y then x (any order is the same operator; this one mirrors the forward pass)
-  if (T ? y_line : x_line) {
+  auto line = [&](int at, int st, const double *M) {
     double v[N];
-    const int at = T ? yA : xA, st = T ? A1 : 1;
 #pragma unroll
     for (int m = 0; m < N; ++m) v[m] = arr[at + m * st];
-    hang_matvec<N, T>(v, T ? M1 : M0);
+    hang_matvec<N, T>(v, M);
 #pragma unroll
     for (int m = 0; m < N; ++m) arr[at + m * st] = v[m];
-  }
+  };
+  // forward: z (own column, just published by this thread), x, y; transpose: y, x, z
+  if (!T && z_line) line(hA, A2, M2);
   __syncthreads();
-  if (T ? x_line : y_line) {
-    double v[N];
-    const int at = T ? xA : yA, st = T ? 1 : A1;
-#pragma unroll
-    for (int m = 0; m < N; ++m) v[m] = arr[at + m * st];
-    hang_matvec<N, T>(v, T ? M0 : M1);
-#pragma unroll
-    for (int m = 0; m < N; ++m) arr[at + m * st] = v[m];
-  }
+  if (T ? y_line : x_line) line(T ? yA : xA, T ? A1 : 1, T ? M1 : M0);
   __syncthreads();
-  if (active && mask != 0) {
-#pragma unroll
-    for (int k = 0; k < N; ++k) u[k] = arr[hA + k * A2];
-  }
-  if (T && z_line) hang_matvec<N, true>(u, M2);
+  if (T ? x_line : y_line) line(T ? xA : yA, T ? 1 : A1, T ? M0 : M1);
+  __syncthreads();
+  if (T && z_line) line(hA, A2, M2);
 }
 
 // MLOAD: how the metric reaches the quadrature phase.
@@ -499,7 +485,17 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
     if constexpr (HANG) {
       hmask = base_cur != kNoCell ? __ldg(prm.cell_mask + tile * CPT + c) : 0u;
       tile_hangs = __syncthreads_or(hmask != 0) != 0;
-      if (tile_hangs) hang_resolve<N, false, A1, A2>(u, hmask, active, a, b, s0, prm.hang);
+      if (tile_hangs) {
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) s0[hA + k * A2] = u[k];
+        }
+        hang_exchange<N, false, A1, A2>(hmask, active, a, b, s0, prm.hang);
+        if (active && hmask != 0) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) u[k] = s0[hA + k * A2];
+        }
+      }
     }
     double t[N];   // z-direction data that stays in registers across the quadrature phase
     double mv[N];  // Helmholtz: values at the quadrature points (home column)
@@ -655,7 +651,17 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
             if constexpr (HELM) o[k] += mv[k];
           }
         }
-        if (tile_hangs) hang_resolve<N, true, A1, A2>(o, hmask, active, a, b, s0, prm.hang);   // s0 is free since (2)
+        if (tile_hangs) {   // s0 is free since (2)
+          if (active) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) s0[hA + k * A2] = o[k];
+          }
+          hang_exchange<N, true, A1, A2>(hmask, active, a, b, s0, prm.hang);
+          if (active && hmask != 0) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) o[k] = s0[hA + k * A2];
+          }
+        }
         if (do_scatter) {
 #pragma unroll
           for (int k = 0; k < N; ++k) {
@@ -724,7 +730,17 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
           for (int q = 0; q < N; ++q) v[q] = s0[hA + q * A2];
           contract_in_regs<N, 1>(o, BTz, v);
         }
-        if (tile_hangs) hang_resolve<N, true, A1, A2>(o, hmask, active, a, b, s1, prm.hang);   // s1 is free since (6b)
+        if (tile_hangs) {   // s1 is free since (6b)
+          if (active) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) s1[hA + k * A2] = o[k];
+          }
+          hang_exchange<N, true, A1, A2>(hmask, active, a, b, s1, prm.hang);
+          if (active && hmask != 0) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) o[k] = s1[hA + k * A2];
+          }
+        }
         if (do_scatter) {
 #pragma unroll
           for (int k = 0; k < N; ++k) {
@@ -755,10 +771,25 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   }
 }
 
-template <int P, int QUAD, int HELM, int CPT, int OWMODE, int MLOAD = 0, int HANG = 0>
+template <int P, int QUAD, int HELM, int CPT, int OWMODE, int MLOAD = 0>
 __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
     bp5_apply_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
-  bp5_apply_body<P, QUAD, HELM, CPT, OWMODE, MLOAD, HANG>(prm);
+  bp5_apply_body<P, QUAD, HELM, CPT, OWMODE, MLOAD, 0>(prm);
+}
+
+// The kernels for locally refined meshes.  Their main loop is the conforming kernel's; the (not inlined) constraint
+// exchange would raise the kernel's register count to 200+ and halve the resident CTAs, so the register budget of the
+// conforming kernel is imposed (the exchange spills inside its own frame, in the few tiles that hold a masked cell):
+// <= 128 registers up to p = 6 (16 warps/SM), 168 at p = 7 (12 warps), no limit at p = 8.
+template <int P, int NT>
+constexpr int hang_min_blocks() {
+  constexpr int warps = (NT + 31) / 32;
+  return P <= 6 ? 16 / warps : (P == 7 ? 12 / warps : 1);
+}
+template <int P, int QUAD, int HELM, int CPT, int OWMODE>
+__global__ void __launch_bounds__((ApplyCfg<P, CPT, 6 + HELM, 0>::NT), (hang_min_blocks<P, ApplyCfg<P, CPT, 6 + HELM, 0>::NT>()))
+    bp5_apply_hang_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
+  bp5_apply_body<P, QUAD, HELM, CPT, OWMODE, 0, 1>(prm);
 }
 
 }  // namespace bp5

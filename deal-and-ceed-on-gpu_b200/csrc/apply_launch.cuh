@@ -15,7 +15,11 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
   constexpr int CPT = TileCells<P>::value;
   using Cfg = ApplyCfg<P, CPT, 6 + HELM, MLOAD>;
   constexpr int N = P + 1;
-  auto kernel = bp5_apply_kernel<P, QUAD, HELM, CPT, OVERWRITE, MLOAD, HANG>;
+  static_assert(HANG == 0 || MLOAD == 0, "hanging-node kernels stage the metric through shared memory");
+  auto kernel = [] {
+    if constexpr (HANG) return bp5_apply_hang_kernel<P, QUAD, HELM, CPT, OVERWRITE>;
+    else return bp5_apply_kernel<P, QUAD, HELM, CPT, OVERWRITE, MLOAD>;
+  }();
   // per instantiation and per device: function attributes belong to the device's context, and the C ABI allows
   // contexts on several devices in one process
   static int blocks_per_sm_of[64] = {0};

@@ -64,11 +64,12 @@ def test_hanging_node_mesh_matches_the_oracle(p, cells, lo, hi, eps, quad, tmp_p
     if quad == "gauss":
         assert _rel(vec("Hu"), hm.vmult(u, kind=O.HELMHOLTZ)) <= 1e-12
     x, its, _ = hm.cg(b, tol=1e-8 * np.linalg.norm(b), max_its=1000)
-    # same count +-1; solves of several hundred iterations (p = 8 on a deformed mesh) may drift by rounding: 1 %
-    assert abs(v["merged_its"] - its) <= max(1, its // 100)
+    # same count +-1; the count of a solve of several hundred iterations (p = 8 on a deformed mesh: 270) moves by +-3
+    # from run to run on the GPU itself (the atomics sum in a different order every time): 2 %
+    assert abs(v["merged_its"] - its) <= max(1, its // 50)
     assert _rel(vec("x"), x) <= 1e-6
     assert v["norm_x"] == pytest.approx(np.linalg.norm(x), rel=1e-6)
-    assert abs(v["library_merged_its"] - its) <= max(1, its // 100)
+    assert abs(v["library_merged_its"] - its) <= max(1, its // 50)
     assert v["library_norm_x"] == pytest.approx(np.linalg.norm(x), rel=1e-6)
 
 
@@ -107,7 +108,7 @@ def test_tuned_kernel_on_a_locally_refined_mesh_matches_the_oracle(gpu_ctx, p, c
             op.do_zero_out = zero
             x.set(0.0)
             Solver(ctl).solve(op, x, b)
-            assert abs(ctl.last_step() - its) <= max(1, its // 100)
+            assert abs(ctl.last_step() - its) <= max(1, its // 50)      # +-1; 2 % for solves of hundreds of iterations
             assert _rel(x.to_host(), xo) <= 1e-6
         for v in (src, dst, b, x):
             v.close()
