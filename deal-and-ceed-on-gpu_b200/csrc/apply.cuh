@@ -780,11 +780,14 @@ __global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, MLOAD>::NT), P)
 // The kernels for locally refined meshes.  Their main loop is the conforming kernel's; the (not inlined) constraint
 // exchange would raise the kernel's register count to 200+ and halve the resident CTAs, so the register budget of the
 // conforming kernel is imposed (the exchange spills inside its own frame, in the few tiles that hold a masked cell):
-// <= 128 registers up to p = 6 (16 warps/SM), 168 at p = 7 (12 warps), no limit at p = 8.
+// <= 128 registers up to p = 6 (16 warps/SM), 168 at p = 7, 8 (12 warps).  Measured on a half-refined corner
+// (profiles/r2_refined_mesh_probe.jsonl), vmult GDoF/s p = 4 / 6 / 7 / 8: exchange inlined, no budget (192-226 registers)
+// 30.4 / 25.3 / - / 22.6; this arrangement 30.3 / 34.6 / 37.6 / 32.4 (p = 8: budget 168); a 168 budget for all degrees
+// through -maxrregcount without launch bounds 27.2 / 25.1 / 32.6 / 32.4.
 template <int P, int NT>
 constexpr int hang_min_blocks() {
   constexpr int warps = (NT + 31) / 32;
-  return P <= 6 ? 16 / warps : (P == 7 ? 12 / warps : 1);
+  return (P <= 6 ? 16 : 12) / warps;
 }
 template <int P, int QUAD, int HELM, int CPT, int OWMODE>
 __global__ void __launch_bounds__((ApplyCfg<P, CPT, 6 + HELM, 0>::NT), (hang_min_blocks<P, ApplyCfg<P, CPT, 6 + HELM, 0>::NT>()))
