@@ -117,6 +117,9 @@ struct ApplyParams {
   // [s][a * N + b] (operator_setup_hanging).  Appended for the same reason.
   const unsigned int *cell_mask;
   double hang[2][N * N];
+  // cell_mask word, bits 8..10: stride class of an affine cell of a refined mesh (idx = base + i + j sy + k sz with
+  // the class's strides: the numbering of a refined mesh is piecewise lexicographic)
+  int hang_sy[8], hang_sz[8];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -374,8 +377,9 @@ struct ApplyCfg {
 // zero on entry, its interior may hold anything); 0 = dst += A src everywhere.
 // OVERWRITE + 3 (3, 4, 5): the same with plain read-modify-writes in place of the atomics, for the launches over
 // the tiles of ONE colour of the coloured cell order (cells of a colour share no DoF): bitwise reproducible.
-// HANG = 1: the cells may carry hanging-node constraints (prm.cell_mask), resolved after the gather and before the
-// scatter; one extra CTA-wide vote per tile, the exchange passes only in tiles that hold a masked cell.
+// HANG (locally refined meshes): 1 = the cells may carry hanging-node constraints (prm.cell_mask), resolved after the
+// gather and before the scatter -- one extra CTA-wide vote per tile, the exchange passes only in tiles that hold a masked
+// cell; 2 = no constrained cell in the tile range, only the per-cell stride classes of the refined numbering.
 template <int P, int QUAD, int HELM, int CPT, int OWMODE, int MLOAD = 0, int HANG = 0>
 __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   constexpr int OVERWRITE = OWMODE % 3;
@@ -462,8 +466,16 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
 #endif
 #endif
   constexpr bool kPrefetch = BP5_PREFETCH_GATHER(P) != 0;   // values of the next tile in registers one tile ahead
+  // HANG: the mask words travel with the cell descriptors (they select the strides of the gather)
+  [[maybe_unused]] unsigned int w_cur = 0, w_nxt = 0;
+  if constexpr (HANG) {
+    w_cur = (active && tile0 < n_tiles) ? __ldg(prm.cell_mask + tile0 * CPT + c) : 0u;
+    w_nxt = (active && tile0 + tstride < n_tiles) ? __ldg(prm.cell_mask + (tile0 + tstride) * CPT + c) : 0u;
+  }
+  auto off_of = [&](unsigned int w) { return HANG ? a + b * prm.hang_sy[(w >> 8) & 7u] : ab_off; };
+  auto sz_of = [&](unsigned int w) { return HANG ? prm.hang_sz[(w >> 8) & 7u] : sz; };
   [[maybe_unused]] double u_nxt[N];
-  if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
+  if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_cur, off_of(w_cur), ab_irr, sz_of(w_cur));
 
   uint32_t parity = 0;
   [[maybe_unused]] double dot_acc = 0.0;
@@ -471,19 +483,22 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
     double u[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) u[k] = kPrefetch ? u_nxt[k] : 0.0;
-    if constexpr (!kPrefetch) gather_column<N>(u, src, l2g_irr, base_cur, ab_off, ab_irr, sz);
+    if constexpr (!kPrefetch) gather_column<N>(u, src, l2g_irr, base_cur, off_of(w_cur), ab_irr, sz_of(w_cur));
     // issue next tile's gather and the descriptor load of the tile after it
-    if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_nxt, ab_off, ab_irr, sz);
+    if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_nxt, off_of(w_nxt), ab_irr, sz_of(w_nxt));
     const int base_n2 =
         (active && tile + 2 * tstride < n_tiles) ? __ldg(cell_base + (tile + 2 * tstride) * CPT + c) : kNoCell;
+    [[maybe_unused]] unsigned int w_n2 = 0;
+    if constexpr (HANG)
+      w_n2 = (active && tile + 2 * tstride < n_tiles) ? __ldg(prm.cell_mask + (tile + 2 * tstride) * CPT + c) : 0u;
 
     if constexpr (MLOAD == 1) {
       if (active) load_metric(tile);
     }
     [[maybe_unused]] unsigned int hmask = 0;
     [[maybe_unused]] bool tile_hangs = false;
-    if constexpr (HANG) {
-      hmask = base_cur != kNoCell ? __ldg(prm.cell_mask + tile * CPT + c) : 0u;
+    if constexpr (HANG == 1) {
+      hmask = w_cur & 63u;
       tile_hangs = __syncthreads_or(hmask != 0) != 0;
       if (tile_hangs) {
         if (active) {
@@ -610,7 +625,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
     }
 
     int idx[N];
-    column_indices<N>(idx, l2g_irr, base_cur, ab_off, ab_irr, sz);
+    column_indices<N>(idx, l2g_irr, base_cur, off_of(w_cur), ab_irr, sz_of(w_cur));
     const bool col_interior = OVERWRITE != 0 && a > 0 && a < P && b > 0 && b < P;
     const bool do_scatter = base_cur != kNoCell;
 
@@ -627,7 +642,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
       }
       __syncthreads();
       // (5) home: z-transpose in registers, sum the three directions, scatter
-      if constexpr (!HANG) {
+      if constexpr (HANG != 1) {
         if (do_scatter) {
           double o[N];
           contract_in_regs<N, -1>(o, DTz, t);
@@ -708,7 +723,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
       }
       __syncthreads();
       // (8) home (i=a, j=b): B^T along z in registers, scatter
-      if constexpr (!HANG) {
+      if constexpr (HANG != 1) {
         if (do_scatter) {
           double v[N], o[N];
 #pragma unroll
@@ -753,6 +768,7 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
     }
     base_cur = base_nxt;
     base_nxt = base_n2;
+    if constexpr (HANG) { w_cur = w_nxt; w_nxt = w_n2; }
   }
   if constexpr (OVERWRITE == 2) {
     // CTA-wide sum in a fixed order (warp shuffles, then warp 0 over the per-warp sums)
@@ -793,6 +809,12 @@ template <int P, int QUAD, int HELM, int CPT, int OWMODE>
 __global__ void __launch_bounds__((ApplyCfg<P, CPT, 6 + HELM, 0>::NT), (hang_min_blocks<P, ApplyCfg<P, CPT, 6 + HELM, 0>::NT>()))
     bp5_apply_hang_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
   bp5_apply_body<P, QUAD, HELM, CPT, OWMODE, 0, 1>(prm);
+}
+// the affine cells of a refined mesh: the conforming kernel plus the stride class per cell
+template <int P, int QUAD, int HELM, int CPT, int OWMODE>
+__global__ void BP5_LAUNCH_BOUNDS((ApplyCfg<P, CPT, 6 + HELM, 0>::NT), P)
+    bp5_apply_strided_kernel(const __grid_constant__ ApplyParams<P + 1> prm) {
+  bp5_apply_body<P, QUAD, HELM, CPT, OWMODE, 0, 2>(prm);
 }
 
 }  // namespace bp5

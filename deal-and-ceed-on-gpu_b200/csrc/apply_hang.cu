@@ -1,5 +1,5 @@
-// Instantiations of the cell kernel that resolve hanging-node constraints (HANG = 1, apply.cuh) for locally refined
-// meshes.  A separate translation unit only so that it compiles in parallel with apply.cu.
+// Instantiations of the cell kernel for locally refined meshes (apply.cuh): HANG = 1 resolves hanging-node constraints
+// (the first tile group), HANG = 2 only knows the stride classes of the refined numbering (all other tiles).  A separate translation unit only so that it compiles in parallel with apply.cu.
 #include "apply_launch.cuh"
 
 namespace bp5 {
@@ -8,11 +8,16 @@ template <int P>
 static int launch_hanging_p(bp5_operator_t op, double *dst, const double *src, int mode, double *dp, int which) {
   const bool gll = op->prob.quadrature == BP5_QUAD_GLL;
   const bool helm = op->prob.operator_kind == BP5_OP_HELMHOLTZ;
-  if (mode == 2) return BP5_LAUNCH_QH(P, 2, 0, 1);
-  if (mode == 1) return BP5_LAUNCH_QH(P, 1, 0, 1);
-  if (mode == 0) return BP5_LAUNCH_QH(P, 0, 0, 1);
-  set_error("the coloured cell order is not available on locally refined meshes");
-  return BP5_ERR_UNSUPPORTED;
+  BP5_REQUIRE(mode >= 0 && mode <= 2, "the coloured cell order is not available on locally refined meshes");
+  BP5_REQUIRE(which == 1 || which == 2, "launch_hanging: one of the two tile groups at a time");
+  if (which == 1) {     // tiles [0, n_boundary_tiles): constrained cells and cells with an index table
+    if (mode == 2) return BP5_LAUNCH_QH(P, 2, 0, 1);
+    if (mode == 1) return BP5_LAUNCH_QH(P, 1, 0, 1);
+    return BP5_LAUNCH_QH(P, 0, 0, 1);
+  }
+  if (mode == 2) return BP5_LAUNCH_QH(P, 2, 0, 2);
+  if (mode == 1) return BP5_LAUNCH_QH(P, 1, 0, 2);
+  return BP5_LAUNCH_QH(P, 0, 0, 2);
 }
 
 int launch_hanging(bp5_operator_t op, double *dst, const double *src, int mode, double *dp, int which) {

@@ -17,7 +17,8 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
   constexpr int N = P + 1;
   static_assert(HANG == 0 || MLOAD == 0, "hanging-node kernels stage the metric through shared memory");
   auto kernel = [] {
-    if constexpr (HANG) return bp5_apply_hang_kernel<P, QUAD, HELM, CPT, OVERWRITE>;
+    if constexpr (HANG == 1) return bp5_apply_hang_kernel<P, QUAD, HELM, CPT, OVERWRITE>;
+    else if constexpr (HANG == 2) return bp5_apply_strided_kernel<P, QUAD, HELM, CPT, OVERWRITE>;
     else return bp5_apply_kernel<P, QUAD, HELM, CPT, OVERWRITE, MLOAD>;
   }();
   // per instantiation and per device: function attributes belong to the device's context, and the C ABI allows
@@ -56,6 +57,7 @@ static int launch(bp5_operator_t op, double *dst, const double *src, double *dot
     for (int q = 0; q < N; ++q) prm.wq[q] = op->tab.wq[q];
   }
   prm.cell_mask = op->cell_mask;
+  for (int cl = 0; cl < 8; ++cl) { prm.hang_sy[cl] = op->hang_sy[cl]; prm.hang_sz[cl] = op->hang_sz[cl]; }
   for (int sI = 0; sI < 2; ++sI)
     for (int i = 0; i < N * N; ++i) prm.hang[sI][i] = op->hanging_interp[sI][i];
   fill_kernel_tables<N>(prm.tab, op->tab.B, op->tab.Dt);

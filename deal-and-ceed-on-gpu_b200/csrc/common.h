@@ -129,6 +129,8 @@ struct bp5_operator_s {
   bool hanging = false;
   void *hanging_cells = nullptr;                  // device int4[n_cells]: (lattice index x, y, z, level) per cell
   double *hanging_interp_dev = nullptr;           // device copy of hanging_interp
+  int64_t hanging_affine_cells = 0;               // cells of a refined mesh with an affine descriptor
+  int hang_sy[8] = {0}, hang_sz[8] = {0};         // stride classes of the affine cells of a refined mesh (cell_mask bits 8..10)
   unsigned int *cell_mask = nullptr;              // [n_tiles * cells_per_tile] constraint mask per cell slot (tuned kernel)
   double hanging_interp[2][bp5::kMaxN * bp5::kMaxN] = {};   // [s][a * n + b] = l_b((s + xi_a) / 2): parent-to-child, 1D
   std::vector<double> hanging_coords;             // [n_owned][3] mapped support point of every DoF

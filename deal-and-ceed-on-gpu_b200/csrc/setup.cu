@@ -254,10 +254,11 @@ static int cell_color(int cx, int cy, int cz) { return (cx & 1) | ((cy & 1) << 1
 
 void operator_plan_tiles(bp5_operator_t op) {
   const int cpt = op->cells_per_tile;
-  if (op->hanging) {     // locally refined mesh: one block, cells in the order of operator_setup_hanging
-    op->n_boundary_cells = 0;
-    op->n_boundary_tiles = 0;
-    op->n_tiles = (op->n_cells + cpt - 1) / cpt;
+  if (op->hanging) {
+    // locally refined mesh (one block): the cells that need the constraint exchange or an index table
+    // (n_boundary_cells, counted by operator_setup_hanging) first, padded to whole tiles, then the affine ones
+    op->n_boundary_tiles = (op->n_boundary_cells + cpt - 1) / cpt;
+    op->n_tiles = op->n_boundary_tiles + (op->n_cells - op->n_boundary_cells + cpt - 1) / cpt;
     return;
   }
   if (op->prob.cell_order == BP5_CELL_ORDER_COLORED) {
@@ -395,7 +396,7 @@ int operator_assemble_rhs(bp5_operator_t op, double *b_dev) {
     BlockGeom g0 = g, g1 = g;
     for (int d = 0; d < 3; ++d) { g0.c0[d] = g1.c0[d] = 0; g1.h[d] = 0.5 * g0.h[d]; }
     const int threads = ((n3 + 31) / 32) * 32;
-    hanging_rhs_kernel<<<(unsigned)op->n_cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
+    hanging_rhs_kernel<<<(unsigned)(op->n_tiles * op->cells_per_tile), threads, sizeof(double) * 8 * n3, ctx->stream>>>(
         g0, g1, static_cast<const int4 *>(op->hanging_cells), op->cell_mask, op->l2g_irr, n3, op->hanging_interp_dev, b_dev);
     BP5_CHECK_LAUNCH();
     if (op->n_constrained > 0) {
@@ -613,22 +614,28 @@ int operator_generic_data(bp5_operator_t op) {
 __global__ void hanging_metric_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells,
                                       double *__restrict__ metric) {
   extern __shared__ double sm[];
-  const int4 c = cells[blockIdx.x];
+  const int4 c = cells[blockIdx.x];      // one CTA per cell SLOT of the processing order
+  if (c.w < 0) return;                   // tile padding
   write_cell_metric(c.w ? g1 : g0, sm, c.x, c.y, c.z, blockIdx.x, metric);
 }
 // the generic functor path's arrays (deal.II layout), built on first use: geometry per cell, the index tables padded to
 // padding_length, the masks
+// (one CTA per cell slot; the arrays are compact: cell = slot minus the padding between the two groups of cells)
 __global__ void hanging_geometry_kernel(BlockGeom g0, BlockGeom g1, const int4 *__restrict__ cells, int pad,
+                                        long long n_first, long long first_padded, long long n_cells,
                                         const int *__restrict__ tables, const unsigned int *__restrict__ slot_mask,
                                         unsigned int *__restrict__ l2g, unsigned int *__restrict__ masks,
                                         double *__restrict__ inv_jac, double *__restrict__ jxw,
                                         double *__restrict__ qpts) {
   extern __shared__ double sm[];
-  const int4 c = cells[blockIdx.x];
+  const long long slot = blockIdx.x;
+  const int4 c = cells[slot];
+  if (c.w < 0) return;
+  const long long cell = slot < first_padded ? slot : slot - (first_padded - n_first);
   const int n3 = g0.n * g0.n * g0.n;
-  if ((int)threadIdx.x < n3) l2g[(long long)blockIdx.x * pad + threadIdx.x] = (unsigned int)tables[(long long)blockIdx.x * n3 + threadIdx.x];
-  if (threadIdx.x == 0) masks[blockIdx.x] = slot_mask[blockIdx.x];
-  write_generic_geometry(c.w ? g1 : g0, sm, c.x, c.y, c.z, blockIdx.x, gridDim.x, pad, inv_jac, jxw, qpts);
+  if ((int)threadIdx.x < n3) l2g[cell * pad + threadIdx.x] = (unsigned int)tables[slot * n3 + threadIdx.x];
+  if (threadIdx.x == 0) masks[cell] = slot_mask[slot] & 63u;     // without the stride class
+  write_generic_geometry(c.w ? g1 : g0, sm, c.x, c.y, c.z, cell, n_cells, pad, inv_jac, jxw, qpts);
 }
 
 int operator_generic_data_hanging(bp5_operator_t op) {
@@ -649,8 +656,10 @@ int operator_generic_data_hanging(bp5_operator_t op) {
   for (int d = 0; d < 3; ++d) { g0.c0[d] = g1.c0[d] = 0; g1.h[d] = 0.5 * g0.h[d]; }
   BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
   const int threads = ((n3 + 31) / 32) * 32;
-  hanging_geometry_kernel<<<(unsigned)cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
-      g0, g1, static_cast<const int4 *>(op->hanging_cells), pad, op->l2g_irr, op->cell_mask, op->mf_l2g,
+  const long long padded = op->n_tiles * op->cells_per_tile;
+  hanging_geometry_kernel<<<(unsigned)padded, threads, sizeof(double) * 8 * n3, ctx->stream>>>(
+      g0, g1, static_cast<const int4 *>(op->hanging_cells), pad, op->n_boundary_cells,
+      op->n_boundary_tiles * op->cells_per_tile, op->n_cells, op->l2g_irr, op->cell_mask, op->mf_l2g,
       op->mf_constraint_mask, op->mf_inv_jacobian, op->mf_jxw, op->mf_q_points);
   BP5_CHECK_LAUNCH();
   ctx->launches++;
@@ -793,10 +802,6 @@ int operator_setup_hanging(bp5_operator_t op) {
   // ---- sizes, Dirichlet set, 1D parent-to-child interpolation
   op->n_owned = N; op->n_ghost = 0; op->n_global = N; op->n_cells = n_cells;
   op->hanging = true;
-  {
-    const int rc = apply_choose(op);     // cells per tile, tile plan (operator_plan_tiles), kernel name
-    if (rc != BP5_OK) return rc;
-  }
   std::sort(cons.begin(), cons.end());
   op->n_constrained = (int64_t)cons.size();
   BP5_CUDA(cudaMalloc(&op->constrained, sizeof(int) * std::max<size_t>(cons.size(), 1)));
@@ -807,26 +812,56 @@ int operator_setup_hanging(bp5_operator_t op) {
       lagrange_eval(n, op->tab.xi, 0.5 * (s + op->tab.xi[a]), val, der);
       for (int b = 0; b < n; ++b) op->hanging_interp[s][a * n + b] = val[b];
     }
-  const size_t cells = (size_t)n_cells;
-  int4 *desc_dev = nullptr;
-  BP5_CUDA(cudaMalloc(&desc_dev, sizeof(int4) * cells));
-  BP5_CUDA(cudaMemcpyAsync(desc_dev, desc.data(), sizeof(int4) * cells, cudaMemcpyHostToDevice, ctx->stream));
-  // ---- the tuned kernel's view of the same cells (apply.cuh, HANG): every cell through an explicit index table
-  // (cell_base < 0 selects table -(base + 1) of l2g_irr), the stored metric in cell order, one constraint mask per
-  // cell slot (tile padding: no cell, mask 0)
-  {
-    const int64_t padded = op->n_tiles * op->cells_per_tile;
-    std::vector<int> base((size_t)padded, INT_MIN);
-    std::vector<unsigned int> slot_mask((size_t)padded, 0u);
-    for (int64_t cI = 0; cI < n_cells; ++cI) {
-      base[(size_t)cI] = -(int)cI - 1;
-      slot_mask[(size_t)cI] = mask[(size_t)cI];
+  // ---- the tuned kernel's view of the same cells (apply.cuh, HANG).
+  // The numbering is piecewise lexicographic: a cell without a constrained face whose n^3 indices are
+  // base + i + j sy + k sz gets the affine descriptor (base >= 0) and the class of its stride pair (at most 8 classes,
+  // cell_mask bits 8..10).  The others -- children with a constrained face, cells across a seam of the numbering --
+  // go through an index table (cell_base < 0 selects table -(base + 1) of l2g_irr) and come FIRST in the processing
+  // order, padded to whole tiles like the boundary cells of a partitioned block: tiles [0, n_boundary_tiles) run the
+  // kernel with the constraint exchange (HANG = 1), the rest the one without (HANG = 2).
+  std::vector<int> cls((size_t)n_cells, -1), base_of((size_t)n_cells, 0);
+  int n_classes = 0;
+  int64_t n_first = 0;
+  for (int64_t cI = 0; cI < n_cells; ++cI) {
+    bool affine = mask[(size_t)cI] == 0;
+    const int *id = &l2g[(size_t)cI * n3];
+    const int b0 = id[0], sy = id[n] - b0, sz = id[n * n] - b0;
+    for (int t = 0; t < n3 && affine; ++t) affine = id[t] == b0 + t % n + sy * ((t / n) % n) + sz * (t / (n * n));
+    if (affine) {
+      int cl = 0;
+      while (cl < n_classes && !(op->hang_sy[cl] == sy && op->hang_sz[cl] == sz)) ++cl;
+      if (cl == n_classes && n_classes < 8) { op->hang_sy[cl] = sy; op->hang_sz[cl] = sz; ++n_classes; }
+      if (cl < n_classes) { cls[(size_t)cI] = cl; base_of[(size_t)cI] = b0; }
     }
-    const std::vector<int> &table = l2g;
-    op->n_irregular = n_cells;
+    if (cls[(size_t)cI] < 0) ++n_first;
+  }
+  op->n_boundary_cells = n_first;
+  op->hanging_affine_cells = n_cells - n_first;
+  {
+    const int rc = apply_choose(op);     // cells per tile, tile plan (operator_plan_tiles), kernel name
+    if (rc != BP5_OK) return rc;
+  }
+  const int64_t padded = op->n_tiles * op->cells_per_tile, first_padded = op->n_boundary_tiles * op->cells_per_tile;
+  int4 *desc_dev = nullptr;
+  {
+    std::vector<int> base((size_t)padded, INT_MIN), table((size_t)padded * n3, 0);
+    std::vector<unsigned int> slot_mask((size_t)padded, 0u);
+    std::vector<int4> slot_desc((size_t)padded, make_int4(0, 0, 0, -1));     // w < 0: tile padding
+    int64_t next_first = 0, next_rest = first_padded;
+    for (int64_t cI = 0; cI < n_cells; ++cI) {
+      const bool first = cls[(size_t)cI] < 0;
+      const int64_t slot = first ? next_first++ : next_rest++;
+      base[(size_t)slot] = first ? -(int)slot - 1 : base_of[(size_t)cI];
+      slot_mask[(size_t)slot] = first ? mask[(size_t)cI] : (unsigned int)cls[(size_t)cI] << 8;
+      slot_desc[(size_t)slot] = desc[(size_t)cI];
+      std::copy_n(&l2g[(size_t)cI * n3], n3, &table[(size_t)slot * n3]);
+    }
+    op->n_irregular = padded;
+    BP5_CUDA(cudaMalloc(&desc_dev, sizeof(int4) * padded));
     BP5_CUDA(cudaMalloc(&op->cell_base, sizeof(int) * padded));
     BP5_CUDA(cudaMalloc(&op->cell_mask, sizeof(unsigned int) * padded));
     BP5_CUDA(cudaMalloc(&op->l2g_irr, sizeof(int) * table.size()));
+    BP5_CUDA(cudaMemcpyAsync(desc_dev, slot_desc.data(), sizeof(int4) * padded, cudaMemcpyHostToDevice, ctx->stream));
     BP5_CUDA(cudaMemcpyAsync(op->cell_base, base.data(), sizeof(int) * padded, cudaMemcpyHostToDevice, ctx->stream));
     BP5_CUDA(cudaMemcpyAsync(op->cell_mask, slot_mask.data(), sizeof(unsigned int) * padded, cudaMemcpyHostToDevice, ctx->stream));
     BP5_CUDA(cudaMemcpyAsync(op->l2g_irr, table.data(), sizeof(int) * table.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -839,7 +874,7 @@ int operator_setup_hanging(bp5_operator_t op) {
   for (int d = 0; d < 3; ++d) { g0.c0[d] = g1.c0[d] = 0; g1.h[d] = 0.5 * g0.h[d]; }
   BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
   const int threads = ((n3 + 31) / 32) * 32;
-  hanging_metric_kernel<<<(unsigned)cells, threads, sizeof(double) * 8 * n3, ctx->stream>>>(g0, g1, desc_dev, op->metric);
+  hanging_metric_kernel<<<(unsigned)padded, threads, sizeof(double) * 8 * n3, ctx->stream>>>(g0, g1, desc_dev, op->metric);
   BP5_CHECK_LAUNCH();
   ctx->launches++;
   BP5_CUDA(cudaMalloc(&op->hanging_interp_dev, sizeof(double) * 2 * kMaxN * kMaxN));
@@ -857,7 +892,8 @@ __global__ void hanging_rhs_kernel(BlockGeom g0, BlockGeom g1, const int4 *__res
                                    const unsigned int *__restrict__ masks, const int *__restrict__ l2g, int pad,
                                    const double *__restrict__ interp, double *__restrict__ b) {
   extern __shared__ double sm[];
-  const int4 c = cells[blockIdx.x];
+  const int4 c = cells[blockIdx.x];      // one CTA per cell slot
+  if (c.w < 0) return;                   // tile padding
   const BlockGeom &g = c.w ? g1 : g0;
   const int n = g.n, n2 = n * n, n3 = n2 * n;
   const int t = threadIdx.x;
@@ -874,7 +910,7 @@ __global__ void hanging_rhs_kernel(BlockGeom g0, BlockGeom g1, const int4 *__res
   if (t < n3) { double s = 0; for (int m = 0; m < n; ++m) s += c_tab.B[m * n + k] * w0[(m * n + j) * n + i]; w1[t] = s; }
   __syncthreads();
   // transposed constraints, direction by direction (mask uniform per cell)
-  const unsigned int mask = masks[blockIdx.x];
+  const unsigned int mask = masks[blockIdx.x] & 63u;
   if (mask != 0) {
     const int pos[3] = {i, j, k}, stride[3] = {1, n, n2};
     bool on_face[3];
