@@ -129,3 +129,35 @@ def test_entry_points_without_a_locally_refined_implementation_say_so(gpu_ctx):
     with pytest.raises(dc.Bp5Error):
         dc.PoissonOperator(gpu_ctx, dc.make_problem(2, (3, 3, 3), refine_lo=(1, 1, 1), refine_hi=(2, 2, 2),
                                                     cell_order=dc.CELL_ORDER_COLORED))
+
+
+def test_tuned_kernel_matches_the_committed_hanging_fixture(gpu_ctx):
+    """tests/golden/hanging_cases.npz alone (no oracle on the box needed): vmult, Helmholtz, right-hand side, CG count"""
+    import dealceed_b200 as dc
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "hanging_cases.npz"))
+    for key in sorted(k[:-5] for k in gold.files if k.endswith("_spec")):
+        p, quad = int(key[1]), int(key[4])
+        spec = [int(v) for v in gold[key + "_spec"]]
+        eps = float(gold[key + "_eps"])
+        u = np.random.default_rng(p).standard_normal(int(gold[key + "_n"][0]))
+        for kind, name in ((dc.OP_POISSON, "_Au"), (dc.OP_HELMHOLTZ, "_Hu")):
+            if key + name not in gold.files:
+                continue
+            op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, spec[0:3], quadrature=quad, operator_kind=kind, upper=(1., 1., 1.),
+                                                             deformation=1 if eps else 0, eps=eps, refine_lo=spec[3:6],
+                                                             refine_hi=spec[6:9]))
+            assert (op.n_owned, op.n_cells) == tuple(gold[key + "_n"])
+            src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+            src.import_host(u)
+            op.vmult(dst, src)
+            assert _rel(dst.to_host(), gold[key + name]) <= 1e-12, key + name
+            if kind == dc.OP_POISSON:
+                b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
+                op.assemble_rhs(b)
+                assert _rel(b.to_host(), gold[key + "_b"]) <= 1e-12
+                ctl = dc.SolverControl(1000, 1e-8 * b.l2_norm())
+                op.do_zero_out = False
+                dc.SolverCGFullMerge(ctl).solve(op, x, b)
+                assert abs(ctl.last_step() - int(gold[key + "_its"])) <= 1
+                b.close(); x.close()
+            src.close(); dst.close(); op.close()

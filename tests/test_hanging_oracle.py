@@ -89,3 +89,18 @@ def test_facade_counts_dofs_and_cells_of_a_locally_refined_mesh(tmp_path):
         if hm is not None:
             assert (n_dofs, n_cells) == (hm.n_dofs, hm.n_cells)
         assert n_cells == 36 - 4 + 32
+
+
+def test_hanging_oracle_reproduces_its_committed_fixture():
+    """tests/golden/hanging_cases.npz (scripts/make_golden_hanging.py): regression pin of the restatement itself"""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "hanging_cases.npz"))
+    for key in sorted(k[:-5] for k in gold.files if k.endswith("_spec")):
+        p, quad = int(key[1]), int(key[4])
+        spec = gold[key + "_spec"]
+        eps = float(gold[key + "_eps"])
+        hm = HangingMesh(p, spec[0:3], spec[3:6], spec[6:9], quad=quad, upper=(1., 1., 1.), deform=1 if eps else 0, eps=eps)
+        assert (hm.n_dofs, hm.n_cells) == tuple(gold[key + "_n"])
+        u = np.random.default_rng(p).standard_normal(hm.n_dofs)
+        assert np.linalg.norm(hm.vmult(u) - gold[key + "_Au"]) <= 1e-13 * np.linalg.norm(gold[key + "_Au"])
+        assert np.linalg.norm(hm.rhs() - gold[key + "_b"]) <= 1e-13 * np.linalg.norm(gold[key + "_b"])
