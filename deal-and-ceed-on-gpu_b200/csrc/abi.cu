@@ -242,7 +242,7 @@ int bp5_operator_set_zero_out(bp5_operator_t op, int z) {
   do {                                                                                                                 \
     if ((op)->hanging) {                                                                                               \
       set_error("%s is not implemented for locally refined meshes (available there: vmult, cell_loop, the CG "      \
-                "solves, vectors, copy_constrained_values, bp5_operator_matrix_free_data for user functors)",         \
+                "solves, assemble_rhs, l2_norm, vectors, bp5_operator_matrix_free_data for user functors)"  ,         \
                 __func__);                                                                                             \
       return BP5_ERR_UNSUPPORTED;                                                                                      \
     }                                                                                                                  \
@@ -345,7 +345,6 @@ int bp5_operator_export_global_indices(bp5_operator_t op, int64_t *host_out) {
 int bp5_operator_l2_norm_sqr(bp5_operator_t op, bp5_vector_t u, double *out) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op && out, "null argument");
-  BP5_CONFORMING_ONLY(op);
   int rc;
   if ((rc = check_vec(op, u))) return rc;
   BP5_CUDA(cudaSetDevice(op->ctx->device));

@@ -1029,23 +1029,68 @@ struct L2Tables {
   double w[kMaxN + 1];
 };
 
-__global__ void l2_norm_kernel(BlockGeom g, L2Tables tb, const double *__restrict__ u, double *__restrict__ partial) {
+// Locally refined meshes (hang.cells != nullptr): one CTA per cell SLOT; the cell's lattice position and level, its
+// index table and constraint mask come from the descriptors of operator_setup_hanging, and the hanging-node constraints
+// are resolved on the gathered values (forward interpolation, direction by direction) before the quadrature.
+struct L2Hanging {
+  const int4 *cells; const int *tables; const unsigned int *masks; const double *interp; double half[3];
+};
+__global__ void l2_norm_kernel(BlockGeom g, L2Tables tb, L2Hanging hang, const double *__restrict__ u,
+                               double *__restrict__ partial) {
   extern __shared__ double sm[];
   const int n = g.n, n2 = n * n, n3 = n2 * n, nq = tb.nq;
   double *U = sm, *X = sm + n3;                      // X[3][n3]
   double *red = X + 3 * n3;                          // [32]
   const long long cell = blockIdx.x;
-  const int lcx = cell % g.lc[0], lcy = (cell / g.lc[0]) % g.lc[1], lcz = cell / ((long long)g.lc[0] * g.lc[1]);
+  int lcx = cell % g.lc[0], lcy = (cell / g.lc[0]) % g.lc[1], lcz = cell / ((long long)g.lc[0] * g.lc[1]);
+  double h[3] = {g.h[0], g.h[1], g.h[2]};
+  unsigned int mask = 0;
+  if (hang.cells != nullptr) {
+    const int4 d = hang.cells[cell];
+    if (d.w < 0) { if (threadIdx.x == 0) partial[cell] = 0.0; return; }     // tile padding
+    lcx = d.x; lcy = d.y; lcz = d.z;
+    if (d.w) { h[0] = hang.half[0]; h[1] = hang.half[1]; h[2] = hang.half[2]; }
+    mask = hang.masks[cell] & 63u;
+  }
   const int c[3] = {g.c0[0] + lcx, g.c0[1] + lcy, g.c0[2] + lcz};
   for (int t = threadIdx.x; t < n3; t += blockDim.x) {
     const int loc[3] = {t % n, (t / n) % n, t / n2};
-    U[t] = u[local_dof_index(g, lcx * g.p + loc[0], lcy * g.p + loc[1], lcz * g.p + loc[2])];
+    U[t] = hang.cells != nullptr ? u[hang.tables[cell * n3 + t]]
+                                 : u[local_dof_index(g, lcx * g.p + loc[0], lcy * g.p + loc[1], lcz * g.p + loc[2])];
     double x[3], y[3];
-    for (int d = 0; d < 3; ++d) x[d] = g.lo[d] + g.h[d] * (c[d] + c_tab.xi[loc[d]]);
+    for (int d = 0; d < 3; ++d) x[d] = g.lo[d] + h[d] * (c[d] + c_tab.xi[loc[d]]);
     map_point(g, x, y);
     for (int d = 0; d < 3; ++d) X[d * n3 + t] = y[d];
   }
   __syncthreads();
+  if (mask != 0) {      // uniform per CTA
+    const int stride[3] = {1, n, n2};
+    for (int d = 0; d < 3; ++d) {
+      if (((mask & 7u) & ~(1u << d)) == 0) continue;
+      const double *M = hang.interp + ((mask >> (3 + d)) & 1u) * kMaxN * kMaxN;
+      double v[2] = {0.0, 0.0};       // blockDim.x >= n3 / 2 always (threads = (p+2)^3 rounded up)
+      int slot = 0;
+      for (int t = threadIdx.x; t < n3; t += blockDim.x, ++slot) {
+        const int pos[3] = {t % n, (t / n) % n, t / n2};
+        bool in_face = false;
+        for (int e = 1; e <= 2; ++e) {
+          const int o = (d + e) % 3;
+          in_face |= ((mask >> o) & 1u) && pos[o] == (((mask >> (3 + o)) & 1u) ? n - 1 : 0);
+        }
+        double val = U[t];
+        if (in_face) {
+          val = 0.0;
+          const int base = t - pos[d] * stride[d];
+          for (int m = 0; m < n; ++m) val += M[pos[d] * n + m] * U[base + m * stride[d]];
+        }
+        v[slot] = val;
+      }
+      __syncthreads();
+      slot = 0;
+      for (int t = threadIdx.x; t < n3; t += blockDim.x, ++slot) U[t] = v[slot];
+      __syncthreads();
+    }
+  }
   double contrib = 0.0;
   const int t = threadIdx.x;
   if (t < nq * nq * nq) {
@@ -1104,16 +1149,25 @@ int operator_l2_norm_sqr(bp5_operator_t op, const double *u_dev, double *out) {
     lagrange_eval(n, op->tab.xi, xq[q], val, der);
     for (int i = 0; i < n; ++i) { tb.B[q * n + i] = val[i]; tb.D[q * n + i] = der[i]; }
   }
+  // one CTA per cell; on a locally refined mesh per cell slot of the processing order (padding slots add zero)
+  const long long n_blocks = op->hanging ? op->n_tiles * op->cells_per_tile : op->n_cells;
+  L2Hanging hang{};
+  BlockGeom gk = g;
+  if (op->hanging) {
+    hang.cells = static_cast<const int4 *>(op->hanging_cells);
+    hang.tables = op->l2g_irr; hang.masks = op->cell_mask; hang.interp = op->hanging_interp_dev;
+    for (int d = 0; d < 3; ++d) { gk.c0[d] = 0; hang.half[d] = 0.5 * g.h[d]; }
+  }
   double *partial = nullptr;
-  BP5_CUDA(cudaMalloc(&partial, sizeof(double) * (op->n_cells + 1)));
+  BP5_CUDA(cudaMalloc(&partial, sizeof(double) * (n_blocks + 1)));
   BP5_CUDA(cudaMemcpyToSymbolAsync(c_tab, &op->tab, sizeof(Tables1D), 0, cudaMemcpyHostToDevice, ctx->stream));
   const int threads = ((nq * nq * nq + 31) / 32) * 32;
-  l2_norm_kernel<<<(unsigned)op->n_cells, threads, sizeof(double) * (4 * n3 + 32), ctx->stream>>>(g, tb, u_dev, partial);
+  l2_norm_kernel<<<(unsigned)n_blocks, threads, sizeof(double) * (4 * n3 + 32), ctx->stream>>>(gk, tb, hang, u_dev, partial);
   BP5_CHECK_LAUNCH();
-  sum_in_order_kernel<<<1, 256, 0, ctx->stream>>>(partial, op->n_cells, partial + op->n_cells);
+  sum_in_order_kernel<<<1, 256, 0, ctx->stream>>>(partial, n_blocks, partial + n_blocks);
   BP5_CHECK_LAUNCH();
   ctx->launches += 2;
-  BP5_CUDA(cudaMemcpyAsync(out, partial + op->n_cells, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BP5_CUDA(cudaMemcpyAsync(out, partial + n_blocks, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   BP5_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(partial);
   return BP5_OK;

@@ -41,6 +41,23 @@ def lagrange_at(xi, x):
     return out
 
 
+def lagrange_deriv_at(xi, x):
+    """[len(x), n] derivatives of the Lagrange basis on the nodes xi at the points x"""
+    xi = np.asarray(xi, dtype=np.float64); x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    n = len(xi)
+    out = np.zeros((len(x), n))
+    for i in range(n):
+        for j in range(n):
+            if j == i:
+                continue
+            term = np.full(len(x), 1.0 / (xi[i] - xi[j]))
+            for m in range(n):
+                if m != i and m != j:
+                    term *= (x - xi[m]) / (xi[i] - xi[m])
+            out[:, i] += term
+    return out
+
+
 class HangingMesh:
     def __init__(self, p, cells, refine_lo, refine_hi, quad=O.GAUSS, lower=(0., 0., 0.), upper=None, deform=0, eps=0.0):
         self.p, self.n, self.quad = p, p + 1, quad
@@ -274,6 +291,25 @@ class HangingMesh:
         loc = (self.C @ uh).reshape(self.n_cells, -1)
         uq = loc @ self.Bq.T
         return float(np.sqrt(np.sum((uq - u(self.xq)) ** 2 * self.jxw)))
+
+    def l2_norm(self, uh):
+        """||u_h||_L2 with QGauss(p+2), per-cell norms rounded to float before they are squared and added, as
+        output_results does it in the reference (bp5/step-64.cu:603-615)"""
+        n, nq = self.n, self.n + 1
+        xg, wg = np.polynomial.legendre.leggauss(nq)
+        xg, wg = 0.5 * (xg + 1.0), 0.5 * wg
+        B2, D2 = lagrange_at(self.xi, xg), lagrange_deriv_at(self.xi, xg)
+        loc = (self.C @ uh).reshape(self.n_cells, n, n, n)
+        Xr = self.X.reshape(self.n_cells, n, n, n, 3)
+        val = np.einsum("ai,bj,ck,nkji->ncba", B2, B2, B2, loc).reshape(self.n_cells, -1)
+        J = np.empty((self.n_cells, nq ** 3, 3, 3))
+        J[..., 0] = np.einsum("ai,bj,ck,nkjid->ncbad", D2, B2, B2, Xr).reshape(self.n_cells, -1, 3)
+        J[..., 1] = np.einsum("ai,bj,ck,nkjid->ncbad", B2, D2, B2, Xr).reshape(self.n_cells, -1, 3)
+        J[..., 2] = np.einsum("ai,bj,ck,nkjid->ncbad", B2, B2, D2, Xr).reshape(self.n_cells, -1, 3)
+        w3 = (wg[:, None, None] * wg[None, :, None] * wg[None, None, :]).ravel()
+        cell_sq = np.sum(val ** 2 * np.linalg.det(J) * w3[None, :], axis=1)
+        cell_norm = np.sqrt(np.maximum(cell_sq, 0.0)).astype(np.float32).astype(np.float64)
+        return float(np.sqrt(np.sum(cell_norm ** 2)))
 
     def cg(self, b, kind=O.POISSON, tol=0.0, max_its=200):
         """textbook CG on the operator of vmult (Dirichlet rows identity), zero start: iteration count and solution"""

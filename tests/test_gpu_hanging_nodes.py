@@ -98,6 +98,7 @@ def test_tuned_kernel_on_a_locally_refined_mesh_matches_the_oracle(gpu_ctx, p, c
         dst.import_host(w)
         op.cell_loop(dst, src)                                      # dst += A src, no Dirichlet copy
         assert _rel(dst.to_host(), w + A @ u) <= 1e-12
+        assert op.l2_norm(src) == pytest.approx(hm.l2_norm(u), rel=1e-6)     # per-cell norms pass through float
         b, x = op.initialize_dof_vector(), op.initialize_dof_vector()
         op.assemble_rhs(b)
         bo = hm.rhs()
@@ -123,6 +124,8 @@ def test_entry_points_without_a_locally_refined_implementation_say_so(gpu_ctx):
     with pytest.raises(dc.Bp5Error) as e:
         op.compute_diagonal(d)
     assert "locally refined" in str(e.value)
+    with pytest.raises(dc.Bp5Error):
+        op.coefficients()
     d.close(); op.close()
     with pytest.raises(dc.Bp5Error):
         dc.PoissonOperator(gpu_ctx, dc.make_problem(2, (3, 3, 3), refine_lo=(1, 1, 1), refine_hi=(9, 2, 2)))

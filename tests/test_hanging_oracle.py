@@ -23,6 +23,7 @@ def test_conforming_limits_reproduce_the_pinned_oracle(p, quad):
         ref = m0.vmult(u, kind=kind)
         assert np.linalg.norm(h0.vmult(u, kind) - ref) <= 1e-12 * np.linalg.norm(ref)
     assert np.linalg.norm(h0.rhs() - m0.rhs()) <= 1e-13 * np.linalg.norm(m0.rhs())
+    assert h0.l2_norm(u) == pytest.approx(m0.l2_norm(u), rel=1e-12)
     # box = whole domain: the mesh with twice the cells (no interior interface, no hanging node)
     m1 = O.OracleMesh(p, tuple(2 * c for c in cells), quad=quad, deform=1, eps=0.1, upper=tuple(float(c) for c in cells))
     h1 = HangingMesh(p, cells, (0, 0, 0), cells, quad=quad, deform=1, eps=0.1)
