@@ -7,6 +7,8 @@
 //
 //   bp5_step64 [--degree 5] [--cycle-min 7] [--cycle-max 24] [--iterations 200]
 //              [--repetitions 10] [--min-run 0] [--quadrature gauss|gll]
+//              [--refine-corner 1]   (not in the reference: the octant of cells at the origin is refined once more,
+//                                     a locally refined mesh with hanging nodes on the octant's inner faces)
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -19,6 +21,7 @@ using VectorType = LinearAlgebra::distributed::Vector<double, MemorySpace::CUDA>
 struct Options {
   unsigned degree = 5, cycle_min = 7, cycle_max = 24, n_iterations = 200, n_repetitions = 10, min_run = 0;
   int quadrature = BP5_QUAD_GAUSS;
+  int refine_corner = 0;
 };
 
 template <int dim, int fe_degree>
@@ -43,6 +46,11 @@ class PoissonProblem {
       triangulation.clear();
       GridGenerator::subdivided_hyper_rectangle(triangulation, subdivisions, Point<dim>(), p2);
       triangulation.refine_global(n_refine);
+      if (opt.refine_corner) {      // what set_refine_flag() on those cells + execute_coarsening_and_refinement() does
+        std::array<unsigned, 3> hi;
+        for (unsigned d = 0; d < dim; ++d) hi[d] = std::max(1u, triangulation.cells(d) / 2);
+        triangulation.refine_cells_in_box({0u, 0u, 0u}, hi);
+      }
 
       setup_system();
       pcout << "   Number of active cells:       " << triangulation.n_global_active_cells() << std::endl
@@ -134,6 +142,7 @@ int main(int argc, char *argv[]) {
       else if (k == "--iterations") o.n_iterations = std::atoi(v);
       else if (k == "--repetitions") o.n_repetitions = std::atoi(v);
       else if (k == "--min-run") o.min_run = std::atoi(v);
+      else if (k == "--refine-corner") o.refine_corner = std::atoi(v);
       else if (k == "--quadrature") o.quadrature = std::strcmp(v, "gll") == 0 ? BP5_QUAD_GLL : BP5_QUAD_GAUSS;
       else throw ExcMessage("unknown option " + k);
     }

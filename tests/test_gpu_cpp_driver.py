@@ -39,6 +39,32 @@ def test_bp5_driver_reproduces_ladder_fixture():
                 assert float(norm) == pytest.approx(g["x_l2"], rel=1e-5)
 
 
+def test_bp5_driver_on_a_locally_refined_mesh_matches_the_hanging_oracle():
+    """the reference's driver with the corner octant of ladder cycle 7 (3 x 2 x 2 cells) refined once more: DoF count,
+    iteration count of both solvers and the two printed norms against oracle/hanging_oracle.py"""
+    import numpy as np
+    import oracle as O
+    from hanging_oracle import HangingMesh
+    _build()
+    p = 3
+    hm = HangingMesh(p, (3, 2, 2), (0, 0, 0), (1, 1, 1), quad=O.GAUSS, upper=(3., 2., 2.))
+    b = hm.rhs()
+    x, its, _ = hm.cg(b, tol=1e-6 * np.linalg.norm(b), max_its=200)
+    out = subprocess.run([os.path.join(ROOT, "build", "examples", "bp5_step64"), "--degree", str(p), "--cycle-min", "7",
+                          "--cycle-max", "7", "--repetitions", "1", "--refine-corner", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    text = out.stdout
+    assert f"Number of active cells:       {hm.n_cells}" in text and f"Number of degrees of freedom: {hm.n_dofs}" in text
+    solved = re.findall(r"Solved in (\d+) iterations with time \S+ and DoFs/s \S+ norm (\S+)", text)
+    assert len(solved) == 2
+    for it, norm in solved:
+        assert abs(int(it) - its) <= 1
+        assert float(norm) == pytest.approx(np.linalg.norm(x), rel=1e-5)
+    # after the vmult block the driver's solution vector still holds the merged solve's x
+    assert float(re.search(r"solution norm: (\S+)", text).group(1)) == pytest.approx(hm.l2_norm(x), rel=1e-4)
+
+
 def test_step64_driver_reproduces_tutorial_iterations():
     _build()
     out = subprocess.run([os.path.join(ROOT, "build", "examples", "step64_helmholtz"), "2"], capture_output=True, text=True,
