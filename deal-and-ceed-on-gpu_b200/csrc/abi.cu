@@ -242,7 +242,7 @@ int bp5_operator_set_zero_out(bp5_operator_t op, int z) {
   do {                                                                                                                 \
     if ((op)->hanging) {                                                                                               \
       set_error("%s is not implemented for locally refined meshes (available there: vmult, cell_loop, the CG "      \
-                "solves, assemble_rhs, l2_norm, vectors, bp5_operator_matrix_free_data for user functors)"  ,         \
+                "solves, assemble_rhs, l2_norm, the diagonal, vectors, bp5_operator_matrix_free_data)"       ,         \
                 __func__);                                                                                             \
       return BP5_ERR_UNSUPPORTED;                                                                                      \
     }                                                                                                                  \
@@ -355,7 +355,6 @@ int bp5_operator_l2_norm_sqr(bp5_operator_t op, bp5_vector_t u, double *out) {
 int bp5_operator_compute_diagonal(bp5_operator_t op, bp5_vector_t diag, int invert) {
   BP5_ABI_GUARD_BEGIN
   BP5_REQUIRE(op, "null operator");
-  BP5_CONFORMING_ONLY(op);
   int rc;
   if ((rc = check_vec(op, diag))) return rc;
   BP5_CUDA(cudaSetDevice(op->ctx->device));

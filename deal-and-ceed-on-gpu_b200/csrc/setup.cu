@@ -942,15 +942,30 @@ __global__ void hanging_rhs_kernel(BlockGeom g0, BlockGeom g1, const int4 *__res
 //   sum_q  grad phi_i(q)^T G(q) grad phi_i(q)  (+ a JxW phi_i(q)^2 for Helmholtz)
 // evaluated directly from the stored metric (one CTA per cell slot, one thread per node; set-up cost only),
 // accumulated over the cells sharing the node; Dirichlet rows are 1 (vmult copies them, bp5/step-64.cu:275).
+// Locally refined meshes: `words` is the per-slot mask word (constraint bits 0..5, stride class bits 8..10) and
+// class_sy / class_sz the stride classes; the positions on a constrained face of a child are left to
+// hanging_diagonal_kernel.
+struct DiagHanging { const unsigned int *words; int class_sy[8], class_sz[8]; };
+__device__ __forceinline__ bool on_constrained_face(unsigned int mask, int n, int a, int b, int c) {
+  const int pos[3] = {a, b, c};
+  bool r = false;
+  for (int d = 0; d < 3; ++d) r |= ((mask >> d) & 1u) && pos[d] == (((mask >> (3 + d)) & 1u) ? n - 1 : 0);
+  return r;
+}
 __global__ void diagonal_kernel(int n, int planes, int cpt, long long tile_doubles, const int *__restrict__ cell_base,
                                 const int *__restrict__ l2g_irr, const double *__restrict__ metric, int sy, int sz,
-                                double *__restrict__ diag) {
+                                DiagHanging hang, double *__restrict__ diag) {
   const int n2 = n * n, n3 = n2 * n;
   const long long slot = blockIdx.x;
   const int base = cell_base[slot];
   const int t = threadIdx.x;
   if (base == INT_MIN || t >= n3) return;
   const int a = t % n, b = (t / n) % n, c = t / n2;
+  if (hang.words != nullptr) {
+    const unsigned int w = hang.words[slot];
+    if (on_constrained_face(w & 63u, n, a, b, c)) return;
+    sy = hang.class_sy[(w >> 8) & 7u]; sz = hang.class_sz[(w >> 8) & 7u];
+  }
   const double *G = metric + (slot / cpt) * tile_doubles + (slot % cpt) * (long long)planes * n3;
   double s = 0.0;
   for (int qz = 0; qz < n; ++qz) {
@@ -972,6 +987,84 @@ __global__ void diagonal_kernel(int n, int planes, int cpt, long long tile_doubl
   const long long idx = base >= 0 ? (long long)base + a + (long long)b * sy + (long long)c * sz
                                   : (long long)l2g_irr[(long long)(-(base + 1)) * n3 + t];
   atomicAdd(&diag[idx], s);
+}
+
+// Diagonal entries that come through hanging-node constraints: the coarse DoF j in slot t0 of a constrained child face
+// contributes c_j^T K c_j, c_j = (constraint resolution) e_t0 = the trace of j's basis function on the child's nodes.
+// One CTA per (slot of the first tile group, local position t0), one thread per node / quadrature point:
+// resolve the unit vector, interpolate to the quadrature points, collocation gradient, the quadratic form
+// sum_q grad^T G grad (+ mass term) -- no transposes needed.
+__global__ void hanging_diagonal_kernel(int n, int planes, int cpt, long long tile_doubles,
+                                        const unsigned int *__restrict__ words, const int *__restrict__ tables,
+                                        const double *__restrict__ metric, const double *__restrict__ interp,
+                                        double *__restrict__ diag) {
+  extern __shared__ double sm[];
+  const int n2 = n * n, n3 = n2 * n;
+  const long long slot = blockIdx.x / n3;
+  const int t0 = (int)(blockIdx.x % n3);
+  const unsigned int mask = words[slot] & 63u;
+  if (mask == 0 || !on_constrained_face(mask, n, t0 % n, (t0 / n) % n, t0 / n2)) return;     // uniform per CTA
+  double *v = sm, *w = sm + n3, *red = sm + 2 * n3;
+  const int t = threadIdx.x;
+  const int pos[3] = {t % n, (t / n) % n, t / n2}, stride[3] = {1, n, n2};
+  if (t < n3) v[t] = t == t0 ? 1.0 : 0.0;
+  __syncthreads();
+  for (int d = 0; d < 3; ++d) {          // forward constraint resolution, direction by direction
+    if (((mask & 7u) & ~(1u << d)) == 0) continue;
+    const double *M = interp + ((mask >> (3 + d)) & 1u) * kMaxN * kMaxN;
+    double val = 0.0;
+    if (t < n3) {
+      val = v[t];
+      bool in_face = false;
+      for (int e = 1; e <= 2; ++e) {
+        const int o = (d + e) % 3;
+        in_face |= ((mask >> o) & 1u) && pos[o] == (((mask >> (3 + o)) & 1u) ? n - 1 : 0);
+      }
+      if (in_face) {
+        val = 0.0;
+        const int base = t - pos[d] * stride[d];
+        for (int m = 0; m < n; ++m) val += M[pos[d] * n + m] * v[base + m * stride[d]];
+      }
+    }
+    __syncthreads();
+    if (t < n3) v[t] = val;
+    __syncthreads();
+  }
+  // values at the quadrature points: B along x, y, z (v -> w -> v -> w)
+  for (int d = 0; d < 3; ++d) {
+    double *src = (d & 1) ? w : v, *dst = (d & 1) ? v : w;
+    if (t < n3) {
+      double sum = 0.0;
+      const int base = t - pos[d] * stride[d];
+      for (int m = 0; m < n; ++m) sum += c_tab.B[pos[d] * n + m] * src[base + m * stride[d]];
+      dst[t] = sum;
+    }
+    __syncthreads();
+  }
+  double contrib = 0.0;
+  if (t < n3) {
+    const double *uq = w;                  // after three passes the values sit in w
+    double g[3];
+    for (int d = 0; d < 3; ++d) {
+      double sum = 0.0;
+      const int base = t - pos[d] * stride[d];
+      for (int m = 0; m < n; ++m) sum += c_tab.Dt[pos[d] * n + m] * uq[base + m * stride[d]];
+      g[d] = sum;
+    }
+    const double *G = metric + (slot / cpt) * tile_doubles + (slot % cpt) * (long long)planes * n3;
+    contrib = G[t] * g[0] * g[0] + G[n3 + t] * g[1] * g[1] + G[2 * n3 + t] * g[2] * g[2] +
+              2.0 * (G[3 * n3 + t] * g[0] * g[1] + G[4 * n3 + t] * g[0] * g[2] + G[5 * n3 + t] * g[1] * g[2]);
+    if (planes == 7) contrib += G[6 * n3 + t] * uq[t] * uq[t];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+  if ((t & 31) == 0) red[t >> 5] = contrib;
+  __syncthreads();
+  if (t == 0) {
+    double sum = 0.0;
+    for (int wI = 0; wI < (int)(blockDim.x + 31) / 32; ++wI) sum += red[wI];
+    atomicAdd(&diag[tables[slot * n3 + t0]], sum);
+  }
 }
 
 __global__ void set_constrained_kernel(const int *__restrict__ list, long long n, double value, double *__restrict__ v) {
@@ -996,11 +1089,26 @@ int operator_diagonal(bp5_operator_t op, double *diag_dev, bool invert) {
   BP5_CUDA(cudaMemsetAsync(diag_dev, 0, sizeof(double) * (op->n_owned + op->n_ghost), ctx->stream));
   const long long slots = op->n_tiles * op->cells_per_tile;
   const int threads = ((n3 + 31) / 32) * 32;
+  DiagHanging hang{};
+  if (op->hanging) {
+    hang.words = op->cell_mask;
+    for (int cl = 0; cl < 8; ++cl) { hang.class_sy[cl] = op->hang_sy[cl]; hang.class_sz[cl] = op->hang_sz[cl]; }
+  }
   diagonal_kernel<<<(unsigned)slots, threads, 0, ctx->stream>>>(n, op->metric_planes, op->cells_per_tile, op->tile_doubles,
                                                               op->cell_base, op->l2g_irr, op->metric, op->od[0],
-                                                              op->od[0] * op->od[1], diag_dev);
+                                                              op->od[0] * op->od[1], hang, diag_dev);
   BP5_CHECK_LAUNCH();
   ctx->launches++;
+  if (op->hanging && op->n_boundary_tiles > 0) {
+    // the constrained faces of the children: all of them sit in the first tile group
+    const long long first_slots = op->n_boundary_tiles * op->cells_per_tile;
+    BP5_REQUIRE(first_slots * n3 < (long long)2147483647, "too many constrained cells for one launch");
+    hanging_diagonal_kernel<<<(unsigned)(first_slots * n3), threads, sizeof(double) * (2 * n3 + 32), ctx->stream>>>(
+        n, op->metric_planes, op->cells_per_tile, op->tile_doubles, op->cell_mask, op->l2g_irr, op->metric,
+        op->hanging_interp_dev, diag_dev);
+    BP5_CHECK_LAUNCH();
+    ctx->launches++;
+  }
   if (op->n_constrained > 0) {
     set_constrained_kernel<<<(unsigned)((op->n_constrained + 255) / 256), 256, 0, ctx->stream>>>(op->constrained,
                                                                                               op->n_constrained, 1.0, diag_dev);

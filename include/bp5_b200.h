@@ -75,9 +75,9 @@ typedef struct bp5_problem {
   int32_t cell_order;      /* BP5_CELL_ORDER_* (single block, stored geometry) */
   int32_t refine_lo[3];    /* locally refined mesh: the coarse cells with indices in [refine_lo, refine_hi) are replaced */
   int32_t refine_hi[3];    /* by their eight children (hanging nodes on the box's faces); all zero: conforming mesh.    */
-                           /* vmult, cell_loop, assemble_rhs, l2_norm, the CG solves and bp5_operator_matrix_free_data  */
-                           /* (user functors) work on such an operator; diagonal and coefficient export return          */
-                           /* BP5_ERR_UNSUPPORTED.  Single block, stored geometry, default cell order.                  */
+                           /* vmult, cell_loop, assemble_rhs, l2_norm, the diagonal, the CG solves and                   */
+                           /* bp5_operator_matrix_free_data (user functors) work on such an operator; the coefficient   */
+                           /* export returns BP5_ERR_UNSUPPORTED.  Single block, stored geometry, default cell order.                  */
   int32_t reserved[1];     /* must be zero */
 } bp5_problem_t;
 

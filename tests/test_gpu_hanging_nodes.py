@@ -111,7 +111,19 @@ def test_tuned_kernel_on_a_locally_refined_mesh_matches_the_oracle(gpu_ctx, p, c
             Solver(ctl).solve(op, x, b)
             assert abs(ctl.last_step() - its) <= max(1, its // 50)      # +-1; 2 % for solves of hundreds of iterations
             assert _rel(x.to_host(), xo) <= 1e-6
-        for v in (src, dst, b, x):
+        # Jacobi diagonal: diag(C^T K C) -- the coarse DoFs of constrained faces collect c_j^T K c_j from the children
+        dg = op.initialize_dof_vector()
+        op.compute_diagonal(dg)
+        dref = A.diagonal().copy()
+        dref[hm.boundary_mask()] = 1.0
+        assert _rel(dg.to_host(), dref) <= 1e-12
+        op.compute_diagonal(dg, invert=True)
+        ctl = dc.SolverControl(1000, 1e-8 * np.linalg.norm(bo))
+        op.do_zero_out = False
+        x.set(0.0)
+        dc.SolverCGFullMerge(ctl).solve(op, x, b, preconditioner=dg)
+        assert _rel(x.to_host(), xo) <= 1e-6
+        for v in (src, dst, b, x, dg):
             v.close()
         op.close()
 
@@ -122,10 +134,8 @@ def test_entry_points_without_a_locally_refined_implementation_say_so(gpu_ctx):
     assert op.n_cells == 27 - 1 + 8
     d = op.initialize_dof_vector()
     with pytest.raises(dc.Bp5Error) as e:
-        op.compute_diagonal(d)
-    assert "locally refined" in str(e.value)
-    with pytest.raises(dc.Bp5Error):
         op.coefficients()
+    assert "locally refined" in str(e.value)
     d.close(); op.close()
     with pytest.raises(dc.Bp5Error):
         dc.PoissonOperator(gpu_ctx, dc.make_problem(2, (3, 3, 3), refine_lo=(1, 1, 1), refine_hi=(9, 2, 2)))
