@@ -521,6 +521,10 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
       if (active) {
 #pragma unroll
         for (int k = 0; k < N; ++k) s0[hA + k * A2] = u[k];
+#ifdef BP5_GLL_DOUBLE_PUBLISH      // tuning builds: a second copy in layout B for the y-lines (no 2.8x conflict read of s0)
+#pragma unroll
+        for (int k = 0; k < N; ++k) s2[hB + k * B2] = u[k];
+#endif
         contract_in_regs<N, -1>(t, Dz, u);
         if constexpr (HELM) {
 #pragma unroll
@@ -535,7 +539,11 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
         contract_to_smem<N, RC, -1>(s1 + xA, 1, Dx, v);
 #pragma unroll
+#ifdef BP5_GLL_DOUBLE_PUBLISH
+        for (int j = 0; j < N; ++j) v[j] = s2[yB + j * B1];
+#else
         for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
+#endif
         contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, v);
       }
       __syncthreads();
