@@ -858,6 +858,7 @@ int operator_setup_hanging(bp5_operator_t op) {
     }
     op->n_irregular = padded;
     BP5_CUDA(cudaMalloc(&desc_dev, sizeof(int4) * padded));
+    op->hanging_cells = desc_dev;      // owned by the operator from here on (kept for assemble_rhs, l2_norm, ...)
     BP5_CUDA(cudaMalloc(&op->cell_base, sizeof(int) * padded));
     BP5_CUDA(cudaMalloc(&op->cell_mask, sizeof(unsigned int) * padded));
     BP5_CUDA(cudaMalloc(&op->l2g_irr, sizeof(int) * table.size()));
@@ -881,7 +882,6 @@ int operator_setup_hanging(bp5_operator_t op) {
   BP5_CUDA(cudaMemcpyAsync(op->hanging_interp_dev, op->hanging_interp, sizeof(double) * 2 * kMaxN * kMaxN,
                            cudaMemcpyHostToDevice, ctx->stream));
   BP5_CUDA(cudaStreamSynchronize(ctx->stream));
-  op->hanging_cells = desc_dev;      // kept for assemble_rhs
   return BP5_OK;
 }
 
