@@ -388,9 +388,50 @@ class FEEvaluationGL {
     else atomicAdd(&dst[j], values[idx]);     // red.global.add.f64
   }
 
-  // fe_evaluation_gl.h:190-214.  Afterwards gradients[d] hold the reference-cell gradient at the
-  // quadrature points (if evaluate_grad) and values the function values there (if evaluate_val;
-  // otherwise values still hold the DoF values).
+  // fe_evaluation_gl.h:190-214.  Afterwards gradients[d] hold the reference-cell gradient at the quadrature points
+  // (if evaluate_grad) and values the function values there (with Gauss quadrature always, with collocation they are
+  // the DoF values anyway).
+  // Every 1D contraction is done by the n^2 threads whose index along the direction is zero: each reads its line
+  // once, multiplies by the n x n table in registers (uniform reads of the kernel parameters) and writes the line --
+  // 2 shared accesses per point and direction instead of the n + 1 of the one-thread-per-output form of deal.II's
+  // evaluator (define DEALII_B200_POINTWISE_EVALUATE to get that form back; same results up to summation order).
+#ifndef DEALII_B200_POINTWISE_EVALUATE
+  __device__ void evaluate(const bool evaluate_val, const bool evaluate_grad) {
+    const Number *B = mf->shape_values, *D = mf->co_shape_gradients;
+    (void)evaluate_val;
+    if (!mf->collocation) {
+      line_pass<0, false>(B, values, gradients[0]); __syncthreads();
+      line_pass<1, false>(B, gradients[0], gradients[1]); __syncthreads();
+      line_pass<2, false>(B, gradients[1], values); __syncthreads();
+    }
+    if (evaluate_grad) {
+      line_pass<0, false>(D, values, gradients[0]);
+      line_pass<1, false>(D, values, gradients[1]);
+      line_pass<2, false>(D, values, gradients[2]);
+      __syncthreads();
+    }
+  }
+
+  // fe_evaluation_gl.h:223-250: values[dof] = sum over quadrature points of the submitted values /
+  // gradients tested with the basis (the transpose of evaluate)
+  __device__ void integrate(const bool integrate_val, const bool integrate_grad) {
+    const Number *B = mf->shape_values, *D = mf->co_shape_gradients;
+    if (integrate_grad) {
+      line_pass<0, true>(D, gradients[0], gradients[0]);       // in place: a line has one owner
+      line_pass<1, true>(D, gradients[1], gradients[1]);
+      line_pass<2, true>(D, gradients[2], gradients[2]);
+      __syncthreads();
+      Number w = integrate_val ? values[idx] : Number(0);
+      w += gradients[0][idx] + gradients[1][idx] + gradients[2][idx];
+      values[idx] = w;
+      __syncthreads();
+    }
+    if (mf->collocation) return;
+    line_pass<0, true>(B, values, gradients[0]); __syncthreads();
+    line_pass<1, true>(B, gradients[0], gradients[1]); __syncthreads();
+    line_pass<2, true>(B, gradients[1], values); __syncthreads();
+  }
+#else
   __device__ void evaluate(const bool evaluate_val, const bool evaluate_grad) {
     const Number *B = tab_B, *D = tab_D;
     constexpr int n = n_q_points_1d, n2 = n * n;
@@ -437,6 +478,8 @@ class FEEvaluationGL {
     w = line_t<1>(B, gradients[1], iy); gradients[2][idx] = w; __syncthreads();
     w = line_t<2>(B, gradients[2], iz); values[idx] = w; __syncthreads();
   }
+
+#endif
 
   __device__ value_type get_value(const unsigned int q_point) const { return values[q_point]; }
   __device__ value_type get_dof_value(const unsigned int dof) const { return values[dof]; }
@@ -506,6 +549,24 @@ class FEEvaluationGL {
     __syncthreads();
     values[idx] = v;
     __syncthreads();
+  }
+
+  // dst(line) = M src(line) (or M^T) for the line along DIR through this thread's point, done by the thread whose own
+  // index along DIR is zero; src == dst is allowed (the line is read completely before it is written)
+  template <int DIR, bool transpose> __device__ void line_pass(const Number *M, const Number *src, Number *dst) const {
+    constexpr int n = n_q_points_1d;
+    constexpr int stride = DIR == 0 ? 1 : DIR == 1 ? n : n * n;
+    if ((DIR == 0 ? ix : DIR == 1 ? iy : iz) != 0) return;
+    Number v[n];
+#pragma unroll
+    for (int m = 0; m < n; ++m) v[m] = src[idx + m * stride];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      Number sum = 0.;
+#pragma unroll
+      for (int m = 0; m < n; ++m) sum += (transpose ? M[m * n + i] : M[i * n + m]) * v[m];
+      dst[idx + i * stride] = sum;
+    }
   }
 
   // sum_m M[row][m] * a(..m..) along direction DIR through this thread's point
