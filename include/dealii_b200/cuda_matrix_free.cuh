@@ -102,9 +102,10 @@ template <int dim, typename Number> struct SharedData {
   }
   Number *values;            // n^dim: dof values, then values at the quadrature points
   Number *gradients[dim];    // n^dim each: reference-cell gradient at the quadrature points
-  // the CTA's shared-memory copies of the 1D tables [q*n + i] (MatrixFree's kernels fill them; null: read them from
-  // the kernel parameters).  deal.II keeps these tables in __constant__ memory, where a warp whose lanes want
-  // different rows is served one row at a time; shared memory serves the rows in parallel.
+  // the CTA's shared-memory copies of the 1D tables [q*n + i], filled by MatrixFree's kernels for the
+  // one-thread-per-output evaluator (DEALII_B200_POINTWISE_EVALUATE); null: the tables are read from the kernel
+  // parameters.  deal.II keeps them in __constant__ memory, where a warp whose lanes want different rows is served one
+  // row at a time; the default evaluator reads them uniformly (line-owner contractions) and needs no copy.
   const Number *shape_values = nullptr;
   const Number *co_shape_gradients = nullptr;
 };
@@ -279,10 +280,11 @@ __global__ void __launch_bounds__(Functor::n_q_points)
                        const Number *src, Number *dst) {
   __shared__ Number values[Functor::n_local_dofs];
   __shared__ Number gradients[dim][Functor::n_q_points];
-  __shared__ Number tables[2][Functor::n_dofs_1d * Functor::n_dofs_1d];
   Number *gq[dim];
   for (int d = 0; d < dim; ++d) gq[d] = gradients[d];
   SharedData<dim, Number> shared_data(values, gq);
+#ifdef DEALII_B200_POINTWISE_EVALUATE      // the one-thread-per-output evaluator reads table rows per lane: stage them
+  __shared__ Number tables[2][Functor::n_dofs_1d * Functor::n_dofs_1d];
   {
     const unsigned int t = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
     if (t < Functor::n_dofs_1d * Functor::n_dofs_1d) {
@@ -293,6 +295,7 @@ __global__ void __launch_bounds__(Functor::n_q_points)
     shared_data.co_shape_gradients = tables[1];
     __syncthreads();
   }
+#endif
   const unsigned int cell = blockIdx.x;      // whole CTAs only: the functor synchronises
   func(cell, &gpu_data, &shared_data, src, dst);
 }
