@@ -425,7 +425,7 @@ def run_b200(args):
     order = [args.quadrature] + ([] if args.no_variants else [q for q in ("gll", "gauss") if q != args.quadrature])
     results = {}
     for qi, qname in enumerate(order):
-        geom = dc.GEOM_ON_THE_FLY if (args.geometry == "otf" and qname == "gll") else dc.GEOM_STORED
+        geom = dc.GEOM_ON_THE_FLY if args.geometry == "otf" else dc.GEOM_STORED
         op = dc.PoissonOperator(ctx, dc.make_problem(args.degree, (args.cells,) * 3, quadrature=quad_ids[qname],
                                                      deformation=1 if args.deformation else 0, eps=args.deformation,
                                                      geometry_mode=geom))

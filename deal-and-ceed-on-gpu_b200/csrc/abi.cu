@@ -91,12 +91,6 @@ int bp5_operator_create(bp5_context_t ctx, const bp5_problem_t *pr, bp5_operator
   BP5_REQUIRE(pr->quadrature == BP5_QUAD_GAUSS || pr->quadrature == BP5_QUAD_GLL, "unknown quadrature");
   BP5_REQUIRE(pr->operator_kind == BP5_OP_POISSON || pr->operator_kind == BP5_OP_HELMHOLTZ, "unknown operator");
   BP5_REQUIRE(pr->geometry_mode == BP5_GEOM_STORED || pr->geometry_mode == BP5_GEOM_ON_THE_FLY, "unknown geometry mode");
-  if (pr->geometry_mode == BP5_GEOM_ON_THE_FLY &&
-      (pr->operator_kind != BP5_OP_POISSON || (pr->quadrature != BP5_QUAD_GLL && pr->deformation != 0))) {
-    set_error("on-the-fly geometry is implemented for the Poisson operator: Gauss-Lobatto collocation on any mesh, "
-              "both quadratures on undeformed (affine) meshes");
-    return BP5_ERR_UNSUPPORTED;
-  }
   BP5_REQUIRE(pr->deformation == 0 || pr->deformation == 1, "unknown deformation");
   BP5_REQUIRE(pr->cell_order == BP5_CELL_ORDER_DEFAULT || pr->cell_order == BP5_CELL_ORDER_COLORED, "unknown cell order");
   BP5_REQUIRE(pr->reserved[0] == 0, "reserved fields of bp5_problem_t must be zero");

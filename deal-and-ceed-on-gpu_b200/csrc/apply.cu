@@ -46,8 +46,13 @@ int apply_choose(bp5_operator_t op) {
   snprintf(name, sizeof(name), "bp5_apply_kernel<p=%d,%s,%s,cells_per_tile=%d,%s>", op->p,
            op->prob.quadrature == BP5_QUAD_GLL ? "gll-collocation" : "gauss",
            op->prob.operator_kind == BP5_OP_HELMHOLTZ ? "helmholtz" : "poisson", cpt, kPath[op->metric_path]);
-  if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY && !otf_affine)
-    snprintf(name, sizeof(name), "bp5_apply_otf_kernel<p=%d,gll-collocation,poisson,cells_per_tile=%d,geometry=on-the-fly>", op->p, cpt);
+  if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY && !otf_affine) {
+    const bool special = op->prob.quadrature == BP5_QUAD_GLL && op->prob.operator_kind == BP5_OP_POISSON;
+    snprintf(name, sizeof(name), "%s<p=%d,%s,%s,cells_per_tile=%d,geometry=on-the-fly>",
+             special ? "bp5_apply_otf_kernel" : "bp5_apply_otfg_kernel", op->p,
+             op->prob.quadrature == BP5_QUAD_GLL ? "gll-collocation" : "gauss",
+             op->prob.operator_kind == BP5_OP_HELMHOLTZ ? "helmholtz" : "poisson", cpt);
+  }
   op->kernel_name = name;
   return BP5_OK;
 }
@@ -97,7 +102,7 @@ static int launch_p(bp5_operator_t op, double *dst, const double *src, int mode,
 // src . (A src) there (see bp5_apply_kernel, OVERWRITE == 2).
 static int apply_dispatch(bp5_operator_t op, double *dst, const double *src, int mode, double *dot_partials, int which) {
   if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY && op->metric_path != 3)
-    return apply_cell_loop_otf(op, dst, src, mode, dot_partials, which);
+    return apply_cell_loop_otfg(op, dst, src, mode, dot_partials, which);
   switch (op->p) {
     case 1: return launch_p<1>(op, dst, src, mode, dot_partials, which);
     case 2: return launch_p<2>(op, dst, src, mode, dot_partials, which);

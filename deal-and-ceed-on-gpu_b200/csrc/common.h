@@ -186,6 +186,8 @@ int apply_choose(bp5_operator_t op);                 // picks cells_per_tile + k
 int apply_cell_loop(bp5_operator_t op, double *dst, const double *src, bool overwrite_interior,
                     double *dot_partials = nullptr, int which = 0);
 int apply_cell_loop_otf(bp5_operator_t op, double *dst, const double *src, int mode, double *dot_partials, int which);
+// the general on-the-fly kernel (apply_otfg.cu): Gauss quadrature and / or Helmholtz; collocation + Poisson forwards to apply_cell_loop_otf
+int apply_cell_loop_otfg(bp5_operator_t op, double *dst, const double *src, int mode, double *dot_partials, int which);
 int apply_copy_constrained_dot(bp5_operator_t op, double *dst, const double *src, double *partials);
 int apply_zero_skeleton(bp5_operator_t op, double *dst);
 int apply_copy_constrained(bp5_operator_t op, double *dst, const double *src);

@@ -368,13 +368,63 @@ def test_on_the_fly_geometry_affine_fast_path(gpu_ctx, p, quad):
     assert relerr(outs[dc.GEOM_ON_THE_FLY], outs[dc.GEOM_STORED]) <= 1e-13
 
 
-def test_on_the_fly_geometry_rejects_unsupported_combinations(gpu_ctx):
+@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("quad,kind", [(0, 0), (0, 1), (1, 1)])
+def test_on_the_fly_geometry_general_kernel(gpu_ctx, p, quad, kind):
+    """geometry on the fly for the reference's default quadrature QGauss(p+1) (bp5/step-64.cu:243-247) and for the
+    Helmholtz operator (step-64/step-64.cu:201-219, coefficient a(x) evaluated at the recomputed quadrature
+    points): the CTA rebuilds the tile's coefficient in shared memory from the nodal coordinates.  Deformed and
+    affine (anisotropic) meshes, ragged tile counts, a single cell: == stored metric to 1e-13, == oracle, dst += A src,
+    merged-CG iteration parity (fused d.Ad path)."""
     dc = _dc()
-    for kw in (dict(quadrature=dc.QUAD_GAUSS, deformation=1, eps=0.1),
-               dict(quadrature=dc.QUAD_GLL, operator_kind=dc.OP_HELMHOLTZ)):
-        with pytest.raises(dc.Bp5Error) as e:
-            dc.PoissonOperator(gpu_ctx, dc.make_problem(3, (2, 2, 2), geometry_mode=dc.GEOM_ON_THE_FLY, **kw))
-        assert e.value.code == dc.ERR_UNSUPPORTED
+    import oracle as O
+    for cells, deform, upper in (((3, 2, 2), 1, None), ((2, 3, 1), 0, (1.5, 2.0, 0.75)), ((1, 1, 1), 1, None)):
+        if deform == 0 and kind == 0:
+            continue                                    # Poisson on affine meshes: the constant-Jacobian fast path
+        m = O.OracleMesh(p, cells, quad=quad, deform=deform, eps=0.1, upper=upper)
+        u = np.random.default_rng(30 + p).standard_normal(m.n_dofs)
+        ref = m.vmult(u, kind=kind)
+        outs = {}
+        for mode in (dc.GEOM_STORED, dc.GEOM_ON_THE_FLY):
+            op = dc.PoissonOperator(gpu_ctx, dc.make_problem(p, cells, quadrature=quad, operator_kind=kind, deformation=deform,
+                                                             eps=0.1, upper=upper, geometry_mode=mode))
+            outs[mode] = _vmult(gpu_ctx, op, u)
+            assert relerr(outs[mode], ref) <= TOL, (p, cells, deform, mode)
+            if mode == dc.GEOM_ON_THE_FLY:
+                assert "bp5_apply_otfg_kernel" in op.kernel_name and "on-the-fly" in op.kernel_name
+                assert op.algorithmic_bytes()[0] == 16.0 * op.n_owned + 24.0 * op.n_owned
+                with pytest.raises(dc.Bp5Error):
+                    op.coefficients()                       # nothing stored
+                # dst += A src (do_zero_out = false, bp5/step-64.cu:270-271)
+                src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+                w = np.random.default_rng(40 + p).standard_normal(m.n_dofs)
+                src.import_host(u); dst.import_host(w)
+                op.do_zero_out = False
+                op.vmult(dst, src)
+                assert relerr(dst.to_host(), m.vmult(u, kind=kind, dst=w.copy())) <= TOL
+                src.close(); dst.close()
+                b = op.initialize_dof_vector(); x = op.initialize_dof_vector()
+                op.assemble_rhs(b)
+                bh = b.to_host()
+                if np.linalg.norm(bh) > 0:
+                    tol = 1e-8 * np.linalg.norm(bh)
+                    ctl = dc.SolverControl(1000, tol)
+                    dc.SolverCGFullMerge(ctl).solve(op, x, b)
+                    xo, its, _, _, _ = m.cg(bh, kind=kind, variant=1, control=1, tol=tol, max_its=1000)
+                    assert abs(ctl.last_step() - its) <= 1
+                    assert relerr(x.to_host(), xo) <= 1e-7
+                b.close(); x.close()
+            op.close()
+        # (interpolation to the Gauss points, then the collocation derivative: one more rounding stage than the
+        # stored metric's direct derivative matrix)
+        assert relerr(outs[dc.GEOM_ON_THE_FLY], outs[dc.GEOM_STORED]) <= 2e-13
+
+
+def test_on_the_fly_geometry_rejects_refined_meshes(gpu_ctx):
+    dc = _dc()
+    with pytest.raises(dc.Bp5Error):
+        dc.PoissonOperator(gpu_ctx, dc.make_problem(3, (4, 4, 4), geometry_mode=dc.GEOM_ON_THE_FLY, quadrature=1,
+                                                     refine_lo=(0, 0, 0), refine_hi=(2, 2, 2)))
 
 
 @pytest.mark.parametrize("p,quad,kind", [(2, 0, 0), (3, 1, 0), (4, 0, 1), (5, 1, 0)])
