@@ -19,11 +19,17 @@ int apply_choose(bp5_operator_t op) {
   int cpt = cells_per_tile_for(op->p);
   BP5_REQUIRE(cpt > 0, "degree must be 1..8");
   if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY) {
+    // collocation + Poisson: the four-fields-at-once kernel (apply_otf.cuh) up to p = 4, the general kernel above
+    // (p = 5: 21.9 against 19.9, p = 6: 23.3 against 20.9 GDoF/s per vmult on a deformed mesh)
+    op->otf_general = !(op->prob.quadrature == BP5_QUAD_GLL && op->prob.operator_kind == BP5_OP_POISSON) || op->p >= 5;
+#ifdef BP5_TUNING_ENV        // tuning builds only
+    if (const char *v = getenv("BP5_OTF_GENERAL"))   // 0 / 1: which kernel takes collocation + Poisson
+      op->otf_general = atoi(v) != 0 || !(op->prob.quadrature == BP5_QUAD_GLL && op->prob.operator_kind == BP5_OP_POISSON);
+#endif
     switch (op->p) {
-      case 1: cpt = OtfTileCells<1>::value; break; case 2: cpt = OtfTileCells<2>::value; break;
-      case 3: cpt = OtfTileCells<3>::value; break; case 4: cpt = OtfTileCells<4>::value; break;
-      case 5: cpt = OtfTileCells<5>::value; break; case 6: cpt = OtfTileCells<6>::value; break;
-      case 7: cpt = OtfTileCells<7>::value; break; case 8: cpt = OtfTileCells<8>::value; break;
+#define BP5_OTF_CASE(P) case P: cpt = op->otf_general ? OtfgTileCells<P>::value : OtfTileCells<P>::value; break;
+      BP5_OTF_CASE(1) BP5_OTF_CASE(2) BP5_OTF_CASE(3) BP5_OTF_CASE(4) BP5_OTF_CASE(5) BP5_OTF_CASE(6) BP5_OTF_CASE(7) BP5_OTF_CASE(8)
+#undef BP5_OTF_CASE
     }
   }
   const int n3 = op->n * op->n * op->n;
@@ -47,7 +53,7 @@ int apply_choose(bp5_operator_t op) {
            op->prob.quadrature == BP5_QUAD_GLL ? "gll-collocation" : "gauss",
            op->prob.operator_kind == BP5_OP_HELMHOLTZ ? "helmholtz" : "poisson", cpt, kPath[op->metric_path]);
   if (op->prob.geometry_mode == BP5_GEOM_ON_THE_FLY && !otf_affine) {
-    const bool special = op->prob.quadrature == BP5_QUAD_GLL && op->prob.operator_kind == BP5_OP_POISSON;
+    const bool special = !op->otf_general;
     snprintf(name, sizeof(name), "%s<p=%d,%s,%s,cells_per_tile=%d,geometry=on-the-fly>",
              special ? "bp5_apply_otf_kernel" : "bp5_apply_otfg_kernel", op->p,
              op->prob.quadrature == BP5_QUAD_GLL ? "gll-collocation" : "gauss",

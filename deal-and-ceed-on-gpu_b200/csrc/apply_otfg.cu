@@ -7,8 +7,8 @@ namespace bp5 {
 
 template <int P, int QUAD, int HELM, int OVERWRITE>
 static int launch_otfg(bp5_operator_t op, double *dst, const double *src, double *dot_partials, int which) {
-  constexpr int CPT = OtfTileCells<P>::value;
-  using Cfg = ApplyOtfgCfg<P, HELM, CPT>;
+  constexpr int CPT = OtfgTileCells<P>::value;
+  using Cfg = ApplyOtfgCfg<P, HELM, CPT, QUAD>;
   constexpr int N = P + 1;
   auto kernel = bp5_apply_otfg_kernel<P, QUAD, HELM, CPT, OVERWRITE>;
   // per instantiation and per device (function attributes belong to the device's context)
@@ -65,7 +65,8 @@ template <int P>
 static int launch_otfg_p(bp5_operator_t op, double *dst, const double *src, int mode, double *dp, int which) {
   const bool gll = op->prob.quadrature == BP5_QUAD_GLL;
   const bool helm = op->prob.operator_kind == BP5_OP_HELMHOLTZ;
-  if (gll && !helm) return apply_cell_loop_otf(op, dst, src, mode, dp, which);
+  if (!op->otf_general) return apply_cell_loop_otf(op, dst, src, mode, dp, which);
+  if (gll && !helm) return launch_otfg_m<P, 1, 0>(op, dst, src, mode, dp, which);
   if (gll) return launch_otfg_m<P, 1, 1>(op, dst, src, mode, dp, which);
   if (helm) return launch_otfg_m<P, 0, 1>(op, dst, src, mode, dp, which);
   return launch_otfg_m<P, 0, 0>(op, dst, src, mode, dp, which);

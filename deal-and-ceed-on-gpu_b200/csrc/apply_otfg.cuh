@@ -5,7 +5,7 @@
 // coefficient in shared memory before it applies it:
 //   for each coordinate field x_d: gather -> the same sum-factorised evaluation as the solution (values and
 //   gradient at the quadrature points; Gauss: interpolate, then collocation derivative)
-//     -> stage[3 d + e][q] = d x_d / d xi_e, stage[9][q] = |x(q)|^2 (Helmholtz only)
+//     -> the line contractions write d x_d / d xi_e straight into a staged Jacobian (+ |x(q)|^2, Helmholtz only)
 //   then the solution field; at every quadrature point
 //     G = w_q / det(J) adj(J) adj(J)^T  (== JxW J^-1 J^-T, JacobianFunctor, bp5/step-64.cu:84-114)
 //     a(x) JxW with a = 10 / (0.05 + 2 |x|^2)  (VaryingCoefficientFunctor, step-64/step-64.cu:100-118)
@@ -34,31 +34,47 @@ struct ApplyOtfgParams {
   KernelTables<N> tab;
 };
 
-template <int P, int HELM, int CPT>
+// collocation: a second S0 array, so that the evaluation of a coordinate field needs ONE barrier (publish | lines)
+// instead of two -- the next field publishes into the other array while slow threads still read this one
+#ifndef BP5_OTFG_PREFETCH
+#define BP5_OTFG_PREFETCH 1
+#endif
+#ifndef BP5_OTFG_DB
+#define BP5_OTFG_DB 0
+#endif
+template <int P, int HELM, int CPT, int QUAD = 0>
 struct ApplyOtfgCfg {
   static constexpr int N = P + 1, N2 = N * N, N3 = N2 * N;
   using L = SmemLayout<N, CPT>;
   static constexpr int ACTIVE = CPT * N2;
   static constexpr int NT = ((ACTIVE + 31) / 32) * 32;
-  static constexpr int GPL = 9 + HELM;                                  // Jacobian entries (+ |x|^2) per point
-  static constexpr int STAGE_DOUBLES = CPT * GPL * N3;
-  static constexpr int WORK_DOUBLES = CPT * (2 * L::A_CS + L::B_CS);    // S0, S1 (layout A), S2 (layout B)
+  // the staged Jacobian: d x_f / d xi in layout-A arrays and d x_f / d eta in layout-B arrays, written straight by
+  // the line contractions of the coordinate fields; d x_f / d zeta (and |x|^2, Helmholtz) dense, private to the
+  // home thread of the column
+  static constexpr int JA_DOUBLES = 3 * CPT * L::A_CS, JB_DOUBLES = 3 * CPT * L::B_CS;
+  static constexpr int JZ_PLANES = 3 + HELM;
+  static constexpr int STAGE_DOUBLES = JA_DOUBLES + JB_DOUBLES + JZ_PLANES * CPT * N3;
+  static constexpr bool DB = QUAD == 1 && BP5_OTFG_DB != 0;
+  static constexpr int WORK_DOUBLES = CPT * ((DB ? 3 : 2) * L::A_CS + L::B_CS);    // S0 (x2), S1 (layout A), S2 (layout B)
   static constexpr size_t SMEM_BYTES = ((size_t)STAGE_DOUBLES + WORK_DOUBLES) * 8;
 };
 
 // QUAD, HELM, OVERWRITE as in bp5_apply_kernel (0 add, 1 store cell-interior DoFs, 2 = 1 + partials of src.(A src))
 template <int P, int QUAD, int HELM, int CPT, int OVERWRITE>
-__global__ void __launch_bounds__(ApplyOtfgCfg<P, HELM, CPT>::NT)
+__global__ void __launch_bounds__(ApplyOtfgCfg<P, HELM, CPT, QUAD>::NT)
     bp5_apply_otfg_kernel(const __grid_constant__ ApplyOtfgParams<P + 1> prm) {
-  using Cfg = ApplyOtfgCfg<P, HELM, CPT>;
-  constexpr int N = Cfg::N, N2 = Cfg::N2, N3 = Cfg::N3, GPL = Cfg::GPL;
+  using Cfg = ApplyOtfgCfg<P, HELM, CPT, QUAD>;
+  constexpr bool DB = Cfg::DB;
+  constexpr int N = Cfg::N, N2 = Cfg::N2, N3 = Cfg::N3;
   using L = typename Cfg::L;
   constexpr int A1 = L::A_S1, A2 = L::A_S2, B1 = L::B_S1, B2 = L::B_S2;
   constexpr int RC = N == 9 ? 3 : N;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *St = reinterpret_cast<double *>(smem_raw);      // [CPT][GPL][N3]
-  double *S0 = St + Cfg::STAGE_DOUBLES;
-  double *S1 = S0 + CPT * L::A_CS;
+  double *JA = reinterpret_cast<double *>(smem_raw);      // [3][CPT][A_CS]
+  double *JB = JA + Cfg::JA_DOUBLES;                      // [3][CPT][B_CS]
+  double *JZ = JB + Cfg::JB_DOUBLES;                      // [3 (+1)][CPT][N3]
+  double *S0 = JA + Cfg::STAGE_DOUBLES;
+  double *S1 = S0 + (DB ? 2 : 1) * CPT * L::A_CS;
   double *S2 = S1 + CPT * L::A_CS;
 
   if (prm.skip != nullptr && *prm.skip != 0) return;
@@ -68,7 +84,8 @@ __global__ void __launch_bounds__(ApplyOtfgCfg<P, HELM, CPT>::NT)
   const int r = tid % N2;
   const int a = r % N, b = r / N;
   double *s0 = S0 + c * L::A_CS, *s1 = S1 + c * L::A_CS, *s2 = S2 + c * L::B_CS;
-  double *st = St + c * GPL * N3 + b * N + a;             // this thread's column: + plane * N3 + k * N2
+  [[maybe_unused]] double *s0b = s0 + CPT * L::A_CS;      // DB: the second S0 array (fields y and u)
+  double *jz = JZ + c * N3 + b * N + a;                   // this thread's column: + field * CPT * N3 + k * N2
   const double *__restrict__ Bx = prm.tab.B[0], *__restrict__ By = prm.tab.B[1], *__restrict__ Bz = prm.tab.B[2];
   const double *__restrict__ BTx = prm.tab.BT[0], *__restrict__ BTy = prm.tab.BT[1], *__restrict__ BTz = prm.tab.BT[2];
   const double *__restrict__ Dx = prm.tab.D[0], *__restrict__ Dy = prm.tab.D[1], *__restrict__ Dz = prm.tab.D[2];
@@ -88,10 +105,13 @@ __global__ void __launch_bounds__(ApplyOtfgCfg<P, HELM, CPT>::NT)
   double *__restrict__ dst = prm.dst;
   [[maybe_unused]] double dot_acc = 0.0;
 
-  // values (mv, home column) and gradient (s1: d/dxi, s2: d/deta, t: d/dzeta in registers) of one field at the
-  // quadrature points; the phases of bp5_apply_body.  Ends behind a barrier.
-  auto evaluate = [&](const double (&u)[N], double (&t)[N], double (&mv)[N]) {
+  // values (mv, home column) and gradient (o1, layout A: d/dxi; o2, layout B: d/deta; t: d/dzeta in registers) of
+  // one field at the quadrature points; the phases of bp5_apply_body.  Ends behind a barrier.
+  // sb: the S0 array of this evaluation; last_barrier: somebody reads o1 / o2 or rewrites sb right afterwards
+  auto evaluate = [&](const double (&u)[N], double (&t)[N], double (&mv)[N], double *o1, double *o2, double *sb,
+                      bool last_barrier) {
     if constexpr (QUAD == 1) {
+      double *s0 = sb;
       if (active) {
 #pragma unroll
         for (int k = 0; k < N; ++k) s0[hA + k * A2] = u[k];
@@ -104,12 +124,12 @@ __global__ void __launch_bounds__(ApplyOtfgCfg<P, HELM, CPT>::NT)
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
-        contract_to_smem<N, RC, -1>(s1 + xA, 1, Dx, v);
+        contract_to_smem<N, RC, -1>(o1 + xA, 1, Dx, v);
 #pragma unroll
         for (int j = 0; j < N; ++j) v[j] = s0[yA + j * A1];
-        contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, v);
+        contract_to_smem<N, RC, -1>(o2 + yB, B1, Dy, v);
       }
-      __syncthreads();
+      if (!DB || last_barrier) __syncthreads();
     } else {
       if (active) contract_to_smem<N, RC, 1>(s0 + hA, A2, Bz, u);
       __syncthreads();
@@ -127,14 +147,14 @@ __global__ void __launch_bounds__(ApplyOtfgCfg<P, HELM, CPT>::NT)
         contract_in_regs<N, 1>(w, By, v);
 #pragma unroll
         for (int q = 0; q < N; ++q) s0[yA + q * A1] = w[q];
-        contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, w);
+        contract_to_smem<N, RC, -1>(o2 + yB, B1, Dy, w);
       }
       __syncthreads();
       if (active) {
         double v[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = s0[xA + i];
-        contract_to_smem<N, RC, -1>(s1 + xA, 1, Dx, v);
+        contract_to_smem<N, RC, -1>(o1 + xA, 1, Dx, v);
 #pragma unroll
         for (int k = 0; k < N; ++k) mv[k] = s0[hA + k * A2];
         contract_in_regs<N, -1>(t, Dz, mv);
@@ -143,53 +163,62 @@ __global__ void __launch_bounds__(ApplyOtfgCfg<P, HELM, CPT>::NT)
     }
   };
 
-  for (long long tile = prm.tile_begin + blockIdx.x; tile < n_tiles; tile += tstride) {
-    const int base = active ? __ldg(cell_base + tile * CPT + c) : kNoCell;
-    int idx[N];
-    column_indices<N>(idx, l2g_irr, base, ab_off, ab_irr, sz);
+  // the gather of a field's columns is issued one evaluation ahead (the x coordinates of the next tile behind the
+  // solution field of this one): its L2 latency hides behind the contractions of the field before
+  constexpr bool PF = BP5_OTFG_PREFETCH != 0;
+  auto gather = [&](double (&v)[N], const double *__restrict__ fld, int bs) {
+    int ix[N];
+    column_indices<N>(ix, l2g_irr, bs, ab_off, ab_irr, sz);
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = (bs == kNoCell) ? 0.0 : __ldg(fld + ix[k]);
+  };
+  long long tile = prm.tile_begin + blockIdx.x;
+  int base = (active && tile < n_tiles) ? __ldg(cell_base + tile * CPT + c) : kNoCell;
+  double col[N];
+  if constexpr (PF) gather(col, prm.cx, base);
+  for (; tile < n_tiles; tile += tstride) {
     double t[N], mv[N];
+    [[maybe_unused]] double nxt[N];
     // ---------------- geometry: Jacobian (and |x|^2) of the tile's cells at the quadrature points -> stage
 #pragma unroll 1
     for (int f = 0; f < 3; ++f) {
-      const double *__restrict__ fld = f == 0 ? prm.cx : f == 1 ? prm.cy : prm.cz;
-      double col[N];
-#pragma unroll
-      for (int k = 0; k < N; ++k) col[k] = (base == kNoCell) ? 0.0 : __ldg(fld + idx[k]);
-      evaluate(col, t, mv);
+      if constexpr (PF) gather(nxt, f == 0 ? prm.cy : f == 1 ? prm.cz : prm.src, base);
+      else gather(col, f == 0 ? prm.cx : f == 1 ? prm.cy : prm.cz, base);
+      evaluate(col, t, mv, JA + (f * CPT + c) * L::A_CS, JB + (f * CPT + c) * L::B_CS, (DB && (f & 1)) ? s0b : s0, false);
       if (active) {
-        double *jp = st + 3 * f * N3;
+        double *zp = jz + f * CPT * N3;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-          jp[k * N2] = s1[hA + k * A2];
-          jp[N3 + k * N2] = s2[hB + k * B2];
-          jp[2 * N3 + k * N2] = t[k];
+          zp[k * N2] = t[k];
           if constexpr (HELM) {
-            double *xp = st + 9 * N3 + k * N2;
+            double *xp = jz + 3 * CPT * N3 + k * N2;
             *xp = (f == 0 ? 0.0 : *xp) + mv[k] * mv[k];
           }
         }
       }
-      // no barrier: the next evaluation first writes S0, which nobody reads any more; S1 / S2 are written two
-      // barriers later
+      if constexpr (PF) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) col[k] = nxt[k];
+      }
+      // no barrier: the next evaluation first writes S0 (DB: the other S0), which nobody reads any more
     }
     // ---------------- the solution field
-    {
-      double u[N];
-#pragma unroll
-      for (int k = 0; k < N; ++k) u[k] = (base == kNoCell) ? 0.0 : __ldg(prm.src + idx[k]);
-      evaluate(u, t, mv);
-    }
+    const int base_n = (active && tile + tstride < n_tiles) ? __ldg(cell_base + (tile + tstride) * CPT + c) : kNoCell;
+    if constexpr (PF) gather(nxt, prm.cx, base_n);
+    else gather(col, prm.src, base);
+    evaluate(col, t, mv, s1, s2, DB ? s0b : s0, true);
     // ---------------- quadrature-point phase (home): G from the staged Jacobian, g <- G g (+ mass term)
     if (active) {
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const int wA = hA + k * A2, wB = hB + k * B2;
-        const double *jq = st + k * N2;
         double J[3][3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
-#pragma unroll
-          for (int e = 0; e < 3; ++e) J[d][e] = jq[(3 * d + e) * N3];
+        for (int d = 0; d < 3; ++d) {
+          J[d][0] = JA[(d * CPT + c) * L::A_CS + wA];
+          J[d][1] = JB[(d * CPT + c) * L::B_CS + wB];
+          J[d][2] = jz[d * CPT * N3 + k * N2];
+        }
         // adj = det * J^-1 (rows: d xi_d / d x_f times det)
         const double a00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], a01 = J[0][2] * J[2][1] - J[0][1] * J[2][2],
                      a02 = J[0][1] * J[1][2] - J[0][2] * J[1][1];
@@ -214,7 +243,7 @@ __global__ void __launch_bounds__(ApplyOtfgCfg<P, HELM, CPT>::NT)
         if constexpr (OVERWRITE == 2) dot_acc += ur * vr + us * vs + ut * vt;
         if constexpr (HELM) {
           const double m_old = mv[k];
-          mv[k] = m_old * (10.0 / (0.05 + 2.0 * jq[9 * N3]) * (w * det));
+          mv[k] = m_old * (10.0 / (0.05 + 2.0 * jz[3 * CPT * N3 + k * N2]) * (w * det));
           if constexpr (OVERWRITE == 2) dot_acc += m_old * mv[k];
         }
       }
@@ -223,6 +252,8 @@ __global__ void __launch_bounds__(ApplyOtfgCfg<P, HELM, CPT>::NT)
     // ---------------- integrate and scatter
     const bool col_interior = OVERWRITE != 0 && a > 0 && a < P && b > 0 && b < P;
     const bool do_scatter = base != kNoCell;
+    int idx[N];
+    column_indices<N>(idx, l2g_irr, base, ab_off, ab_irr, sz);
     if constexpr (QUAD == 1) {
       if (active) {
         double v[N];
@@ -290,6 +321,11 @@ __global__ void __launch_bounds__(ApplyOtfgCfg<P, HELM, CPT>::NT)
     }
     // no barrier here: the next tile first writes S0 -- the home columns (read last by their own threads) under
     // Gauss, an array nobody reads after the line phase under collocation
+    base = base_n;
+    if constexpr (PF) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) col[k] = nxt[k];
+    }
   }
   if constexpr (OVERWRITE == 2) {
     __syncthreads();

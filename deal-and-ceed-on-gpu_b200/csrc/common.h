@@ -121,6 +121,8 @@ struct bp5_operator_s {
   unsigned int *mfc_l2g[8] = {nullptr}, *mfc_constraint_mask[8] = {nullptr};
   double *mfc_inv_jacobian[8] = {nullptr}, *mfc_jxw[8] = {nullptr}, *mfc_q_points[8] = {nullptr};
   int64_t mfc_n_cells[8] = {0};
+  bool otf_general = false;     // BP5_GEOM_ON_THE_FLY on a deformed mesh: the general kernel (apply_otfg.cuh) instead of the
+                                // collocation + Poisson one (apply_otf.cuh)
   double *coords = nullptr;     // BP5_GEOM_ON_THE_FLY: nodal coordinates [3][n_owned + n_ghost] instead of the metric
   double *metric = nullptr;     // [tile][cpt][planes][n^3]; planes: 6 (Poisson) or 7 (Helmholtz: + a*JxW)
   int metric_planes = 6;

@@ -59,4 +59,28 @@ template <> struct OtfTileCells<4> { static constexpr int value = BP5_OTF_CPT_P4
 template <> struct OtfTileCells<5> { static constexpr int value = BP5_OTF_CPT_P5; };
 template <> struct OtfTileCells<6> { static constexpr int value = BP5_OTF_CPT_P6; };
 template <> struct OtfTileCells<7> { static constexpr int value = BP5_OTF_CPT_P7; };
+
+// the general on-the-fly kernel (apply_otfg.cuh) stages the Jacobian of the tile's cells next to three work arrays
+// (round 2, deformed mesh, 11-16 M DoFs, vmult GDoF/s Gauss / collocation + Helmholtz, profiles/r2_otf_general_tuning.log:
+//  p=4 1/2/3 cells 16.3/15.7/15.7 and 18.8/17.8/17.6; p=5 1/2/3 cells 12.5/15.2/15.9 and 16.3/16.9/18.5;
+//  p=6 1/2/3 cells 17.8/17.3/16.2 and 20.3/19.8/18.7)
+// (-DBP5_OTFG_CPT_Pn=... overrides one entry for tuning builds)
+template <int P> struct OtfgTileCells { static constexpr int value = OtfTileCells<P>::value; };
+#ifndef BP5_OTFG_CPT_P4
+#define BP5_OTFG_CPT_P4 1
+#endif
+#ifndef BP5_OTFG_CPT_P5
+#define BP5_OTFG_CPT_P5 3
+#endif
+#ifdef BP5_OTFG_CPT_P3
+template <> struct OtfgTileCells<3> { static constexpr int value = BP5_OTFG_CPT_P3; };
+#endif
+template <> struct OtfgTileCells<4> { static constexpr int value = BP5_OTFG_CPT_P4; };
+template <> struct OtfgTileCells<5> { static constexpr int value = BP5_OTFG_CPT_P5; };
+#ifdef BP5_OTFG_CPT_P6
+template <> struct OtfgTileCells<6> { static constexpr int value = BP5_OTFG_CPT_P6; };
+#endif
+#ifdef BP5_OTFG_CPT_P7
+template <> struct OtfgTileCells<7> { static constexpr int value = BP5_OTFG_CPT_P7; };
+#endif
 }  // namespace bp5
