@@ -171,6 +171,12 @@ __device__ __forceinline__ double ld_stream(const double *p, uint64_t policy) {
   return v;
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS): the one-tile-ahead gather without registers (BP5_SMEM_PREFETCH)
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Local dof indices of the N points of one thread's z-column in a cell with
 // descriptor `base` (>= 0: affine, < 0: explicit table slot, kNoCell: no cell,
 // indices are 0 and the values are never used).  Branch-free on the common path
@@ -465,7 +471,18 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
 #define BP5_PREFETCH_GATHER(P) 1
 #endif
 #endif
-  constexpr bool kPrefetch = BP5_PREFETCH_GATHER(P) != 0;   // values of the next tile in registers one tile ahead
+  // BP5_SMEM_PREFETCH (collocation, conforming meshes): the next tile's columns are copied asynchronously (LDGSTS)
+  // straight into S0 -- free from the end of the line phase (2) to the next tile's start -- instead of waiting in N
+  // registers: the copy replaces the publishing stores, the home thread reads its column back for the z-derivative.
+  // ptxas then needs 48-78 instead of 106-194 registers.  Measured at 148 M DoFs (profiles/r2_smem_prefetch_probe.log):
+  // p = 8 cell loop 2.67 -> 2.33 ms (2 -> 4 CTAs/SM), merged CG 32.8 -> 34.8 GDoF*it/s; p = 5, 6 (shared memory
+  // already limits the CTAs) 1-2 % slower -- the copy is in flight for 60 % of a tile instead of a whole one.
+  // Shipped for p = 8.  Value: bit m = used by the kernels of mode OVERWRITE == m.
+#ifndef BP5_SMEM_PREFETCH
+#define BP5_SMEM_PREFETCH(P) ((P) == 8 ? 7 : 0)
+#endif
+  constexpr bool kSmemPf = ((BP5_SMEM_PREFETCH(P) >> OVERWRITE) & 1) != 0 && QUAD == 1 && HANG == 0;
+  constexpr bool kPrefetch = BP5_PREFETCH_GATHER(P) != 0 && !kSmemPf;   // values of the next tile in registers one tile ahead
   // HANG: the mask words travel with the cell descriptors (they select the strides of the gather)
   [[maybe_unused]] unsigned int w_cur = 0, w_nxt = 0;
   if constexpr (HANG) {
@@ -476,6 +493,14 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
   auto sz_of = [&](unsigned int w) { return HANG ? prm.hang_sz[(w >> 8) & 7u] : sz; };
   [[maybe_unused]] double u_nxt[N];
   if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_cur, off_of(w_cur), ab_irr, sz_of(w_cur));
+  if constexpr (kSmemPf) {
+    if (active && tile0 < n_tiles) {
+      int ix[N];
+      column_indices<N>(ix, l2g_irr, base_cur, off_of(w_cur), ab_irr, sz_of(w_cur));
+#pragma unroll
+      for (int k = 0; k < N; ++k) cp_async8(s0 + hA + k * A2, src + ix[k]);
+    }
+  }
 
   uint32_t parity = 0;
   [[maybe_unused]] double dot_acc = 0.0;
@@ -483,7 +508,13 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
     double u[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) u[k] = kPrefetch ? u_nxt[k] : 0.0;
-    if constexpr (!kPrefetch) gather_column<N>(u, src, l2g_irr, base_cur, off_of(w_cur), ab_irr, sz_of(w_cur));
+    if constexpr (kSmemPf) {
+      cp_async_wait_all();      // this thread's own column has landed (the others': behind the barrier of phase 1)
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) u[k] = s0[hA + k * A2];
+      }
+    } else if constexpr (!kPrefetch) gather_column<N>(u, src, l2g_irr, base_cur, off_of(w_cur), ab_irr, sz_of(w_cur));
     // issue next tile's gather and the descriptor load of the tile after it
     if constexpr (kPrefetch) gather_column<N>(u_nxt, src, l2g_irr, base_nxt, off_of(w_nxt), ab_irr, sz_of(w_nxt));
     const int base_n2 =
@@ -519,8 +550,10 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
       // ---------------- Gauss-Lobatto collocation: u is already at the q-points
       // (1) home (i=a, j=b): publish the column, z-derivative in registers
       if (active) {
+        if constexpr (!kSmemPf) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) s0[hA + k * A2] = u[k];
+          for (int k = 0; k < N; ++k) s0[hA + k * A2] = u[k];
+        }
 #ifdef BP5_GLL_DOUBLE_PUBLISH      // tuning builds: a second copy in layout B for the y-lines (no 2.8x conflict read of s0)
 #pragma unroll
         for (int k = 0; k < N; ++k) s2[hB + k * B2] = u[k];
@@ -547,6 +580,14 @@ __device__ __forceinline__ void bp5_apply_body(const ApplyParams<P + 1> &prm) {
         contract_to_smem<N, RC, -1>(s2 + yB, B1, Dy, v);
       }
       __syncthreads();
+      if constexpr (kSmemPf) {   // S0 is free until the next tile starts: fetch its columns behind the rest of this one
+        if (active && tile + tstride < n_tiles) {
+          int ix[N];
+          column_indices<N>(ix, l2g_irr, base_nxt, off_of(w_nxt), ab_irr, sz_of(w_nxt));
+#pragma unroll
+          for (int k = 0; k < N; ++k) cp_async8(s0 + hA + k * A2, src + ix[k]);
+        }
+      }
     } else {
       // ---------------- Gauss quadrature: interpolate to the q-points first
       // (1) home (i=a, j=b): z-interpolation
