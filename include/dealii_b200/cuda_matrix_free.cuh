@@ -159,11 +159,15 @@ template <int dim, typename Number = double> class MatrixFree {
     if (mapping.degree != dof_handler.degree) throw ExcMessage("MappingQGeneric degree must equal fe_degree");
     if (quad.n_points_1d != dof_handler.degree + 1) throw ExcMessage("n_q_points_1d must be fe_degree + 1");
     // the ghost exchange of a partitioned mesh happens behind the library operator (BP5::PoissonOperator on a
-    // communicator); this generic path drives one block, where the flag has nothing to overlap
-    (void)additional_data.overlap_communication_computation;
+    // communicator); this generic path drives ONE block, where overlap_communication_computation (bp5/step-64.cu:241)
+    // has nothing to overlap.  On a triangulation that is split over several ranks it must not silently build the
+    // whole mesh on every rank: fail loudly.
+    const Triangulation<dim> &t = dof_handler.get_triangulation();
+    if (t.communicator != nullptr && t.communicator->size() > 1)
+      throw ExcMessage("CUDAWrappers::MatrixFree (user-written functors) drives one block; on a partitioned mesh use "
+                       "BP5::PoissonOperator, whose cell loop overlaps the ghost exchange");
     use_coloring = additional_data.use_coloring;
     bp5_operator_destroy(op); op = nullptr;
-    const Triangulation<dim> &t = dof_handler.get_triangulation();
     bp5_problem_t pr{};
     pr.degree = (int32_t)dof_handler.degree; pr.quadrature = quad.abi_kind; pr.operator_kind = BP5_OP_POISSON;
     pr.geometry_mode = BP5_GEOM_STORED;

@@ -113,3 +113,53 @@ def test_facade_process_grid_matches_the_python_layer(tmp_path):
     lines = subprocess.check_output([str(exe)], text=True).split("\n")
     for w in range(1, 25):
         assert tuple(int(v) for v in lines[w - 1].split()) == tuple(process_grid(w)), w
+
+
+def test_generic_functor_path_rejects_a_partitioned_triangulation(tmp_path):
+    """CUDAWrappers::MatrixFree (the reference's user-functor interface) drives one block: asked to reinit on a
+    triangulation split over two ranks it throws instead of silently building the whole mesh on every rank (or
+    silently ignoring overlap_communication_computation, bp5/step-64.cu:241).  The check runs before any device call,
+    so the probe needs no GPU."""
+    import subprocess
+    src = tmp_path / "mf_probe.cu"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstring>
+#include "dealii_b200/dealii_b200.h"
+#include "dealii_b200/cuda_matrix_free.cuh"
+using namespace dealii;
+struct TwoRanks : b200::Communicator {
+  int rank() const override { return 0; }
+  int size() const override { return 2; }
+  void allgather(const void *s, void *r, std::size_t n) override { std::memcpy(r, s, n); std::memcpy((char *)r + n, s, n); }
+  void barrier() override {}
+};
+int main() {
+  TwoRanks comm;
+  Triangulation<3> tria(&comm);
+  Point<3> p2;
+  for (int d = 0; d < 3; ++d) p2[d] = 4.;
+  GridGenerator::subdivided_hyper_rectangle(tria, std::vector<unsigned int>(3, 4), Point<3>(), p2);
+  FE_Q<3> fe(2);
+  DoFHandler<3> dof_handler(tria);
+  dof_handler.distribute_dofs(fe);
+  AffineConstraints<double> constraints;
+  CUDAWrappers::MatrixFree<3, double> mf;
+  CUDAWrappers::MatrixFree<3, double>::AdditionalData ad;
+  ad.overlap_communication_computation = true;
+  try {
+    mf.reinit(MappingQGeneric<3>(2), dof_handler, constraints, QGauss<1>(3), ad);
+  } catch (const ExcMessage &e) {
+    std::printf("%s\n", e.what());
+    return std::strstr(e.what(), "partitioned mesh") ? 0 : 2;
+  }
+  return 1;
+}
+''')
+    exe = tmp_path / "mf_probe"
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O0",
+                           "-ccbin", "/usr/bin/g++", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", os.path.join(ROOT, "deal-and-ceed-on-gpu_b200"), "-lbp5b200",
+                           "-Xlinker", "-rpath", "-Xlinker", os.path.join(ROOT, "deal-and-ceed-on-gpu_b200")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr[-500:])
