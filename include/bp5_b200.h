@@ -47,7 +47,9 @@ enum bp5_status {
 
 enum { BP5_QUAD_GAUSS = 0, BP5_QUAD_GLL = 1 };     /* bp5/step-64.cu:243-247 (COLLOCATION) */
 enum { BP5_OP_POISSON = 0, BP5_OP_HELMHOLTZ = 1 }; /* bp5/step-64.cu:147 ; step-64/step-64.cu:201 */
-enum { BP5_GEOM_STORED = 0, BP5_GEOM_ON_THE_FLY = 1 };
+enum { BP5_GEOM_STORED = 0,      /* merged coefficient precomputed and streamed (evaluate_coefficients(JacobianFunctor), bp5/step-64.cu:256-258) */
+       BP5_GEOM_ON_THE_FLY = 1 }; /* only nodal coordinates stored (24 B/DoF), the cell kernel rebuilds G (and a(x) JxW): both quadratures,    */
+                                  /* both operators, affine and deformed meshes; not with refined meshes or the coloured cell order            */
 enum { BP5_CELL_ORDER_DEFAULT = 0,  /* one pass, skeleton DoFs accumulated with atomics (use_coloring = false, bp5/step-64.cu:243) */
        BP5_CELL_ORDER_COLORED = 1 }; /* eight parity colours, one pass each, plain adds: bitwise reproducible (use_coloring = true) */
 enum { BP5_CONTROL_ITERATION_NUMBER = 0, /* IterationNumberControl, bp5/step-64.cu:443 */
