@@ -11,8 +11,9 @@
 //     a(x) JxW with a = 10 / (0.05 + 2 |x|^2)  (VaryingCoefficientFunctor, step-64/step-64.cu:100-118)
 //   exactly what setup.cu:write_cell_metric stores, so the two geometry modes agree to rounding.
 // Thread roles, shared-memory layouts, scatter and the fused src.(A src) are those of apply.cuh; four evaluations
-// per tile instead of one make this a memory-saving mode (the specialised collocation kernel of apply_otf.cuh and
-// the affine fast path of apply.cuh stay the fast ones for their cases).
+// per tile instead of one make this a memory-saving mode: 0.52-0.59 of the stored-metric CG rate with a quarter of
+// the geometry bytes (ncu: shared-memory pipe 76 %, fp64 pipe 40 %).  The four-fields-at-once
+// collocation kernel of apply_otf.cuh keeps p <= 4, the affine fast path of apply.cuh undeformed Poisson meshes.
 // Algorithmic bytes: 16 (src, dst) + 24 (coordinates) per DoF.
 #pragma once
 #include "apply.cuh"
@@ -34,11 +35,14 @@ struct ApplyOtfgParams {
   KernelTables<N> tab;
 };
 
-// collocation: a second S0 array, so that the evaluation of a coordinate field needs ONE barrier (publish | lines)
-// instead of two -- the next field publishes into the other array while slow threads still read this one
+// tuning switches (profiles/r2_otf_general_tuning.log: both within +-5 %)
+// BP5_OTFG_PREFETCH: the gather of a field is issued one evaluation ahead (N more registers)
 #ifndef BP5_OTFG_PREFETCH
 #define BP5_OTFG_PREFETCH 1
 #endif
+// BP5_OTFG_DB (collocation): a second S0 array, so that the evaluation of a coordinate field needs ONE barrier
+// (publish | lines) instead of two -- the next field publishes into the other array while slow threads still read
+// this one
 #ifndef BP5_OTFG_DB
 #define BP5_OTFG_DB 0
 #endif
